@@ -1,0 +1,218 @@
+"""Generate golden fixtures from the UNMODIFIED reference (runs only where /root/reference exists).
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+The reference modules are imported read-only from /root/reference/code.  Randomness that the
+reference draws from torch's RNG (nn.Dropout, F.dropout2d) is made reproducible by temporarily
+replacing ``torch.nn.functional.dropout`` / ``dropout2d`` with functions that apply keep-masks drawn
+from a numpy RandomState stream (so the fixtures only store a seed); no reference source is edited
+or copied.  Parameters come from ``wsl_oracle.synth_params`` (numpy stream) and are loaded with
+``load_state_dict`` so the fixtures do not need to store 2.4 M weights.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference/code"
+sys.path.insert(0, HERE)
+sys.path.insert(0, REF)
+
+import wsl_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def elem_masks(seed, n, h, w):
+    """Keep masks (uint8) for the five encoder nn.Dropout layers, keyed like the oracle expects."""
+    rs = np.random.RandomState(seed)
+    names = ["encoder.in_conv.conv_conv.3"] + [f"encoder.down{i}.maxpool_conv.1.conv_conv.3" for i in range(1, 5)]
+    out = {}
+    for i, nm in enumerate(names):
+        keep = rs.uniform(size=(n, O.FT[i], h >> i, w >> i)) >= O.ENC_DROP[i]
+        out[nm] = torch.from_numpy(keep.astype(np.uint8))
+    return out
+
+
+def chan_masks(seed, n):
+    rs = np.random.RandomState(seed)
+    return [torch.from_numpy((rs.uniform(size=(n, c)) >= 0.5).astype(np.uint8)) for c in O.FT]
+
+
+class PatchedDropout:
+    """Context manager: F.dropout / F.dropout2d consume queued keep-masks instead of torch RNG."""
+
+    def __init__(self, elem, chan):
+        self.elem = [elem[k] for k in sorted(elem, key=lambda s: ("down" in s, s))] if elem else []
+        self.chan = list(chan) if chan else []
+
+    def __enter__(self):
+        self._d, self._d2 = F.dropout, F.dropout2d
+        eq, cq = list(self.elem), list(self.chan)
+
+        def dropout(x, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return x
+            m = eq.pop(0)
+            assert m.shape == x.shape, (m.shape, x.shape)
+            return x * m.to(x.dtype) * (1.0 / (1.0 - p))
+
+        def dropout2d(x, p=0.5, training=True, inplace=False):
+            m = cq.pop(0)
+            return x * (m.to(x.dtype) * (1.0 / (1.0 - p)))[:, :, None, None]
+
+        F.dropout, F.dropout2d = dropout, dropout2d
+        torch.nn.functional.dropout, torch.nn.functional.dropout2d = dropout, dropout2d
+        return self
+
+    def __exit__(self, *a):
+        F.dropout, F.dropout2d = self._d, self._d2
+        torch.nn.functional.dropout, torch.nn.functional.dropout2d = self._d, self._d2
+
+
+def grad_summary(named_grads):
+    """Per-parameter (sum, abs-sum, l2) plus full copies of the small tensors."""
+    keys, stats, small = [], [], {}
+    for k, g in named_grads.items():
+        g = g.double()
+        keys.append(k)
+        stats.append([g.sum().item(), g.abs().sum().item(), g.norm().item()])
+        if g.numel() <= 600:
+            small["g:" + k] = g.float().numpy()
+    return keys, np.asarray(stats, dtype=np.float64), small
+
+
+def losses_kat():
+    from utils import losses as RL
+    from utils.gate_crf_loss import ModelLossSemsegGatedCRF
+
+    g = torch.Generator().manual_seed(1234)
+    logits = torch.randn(2, 4, 32, 32, generator=g)
+    img = torch.rand(2, 1, 32, 32, generator=g)
+    lab = torch.full((2, 32, 32), 4, dtype=torch.uint8)
+    m = torch.rand(2, 32, 32, generator=g) < 0.1
+    lab[m] = torch.randint(0, 4, (int(m.sum()),), generator=g, dtype=torch.uint8)
+    logits2 = torch.randn(2, 4, 32, 32, generator=g)
+
+    lg = logits.clone().requires_grad_(True)
+    s = torch.softmax(lg, 1)
+    out = {"logits": logits.numpy(), "logits2": logits2.numpy(), "image": img.numpy(), "label": lab.numpy()}
+
+    def tv_ref(pred):  # script-local function, train_weakly_supervised_pCE_TV_2D.py:58-65 (not importable: the
+        # script parses argv and imports tensorboardX at module level) -> oracle restatement is the pin here
+        return O.tv_loss(pred)
+
+    ce = torch.nn.CrossEntropyLoss(ignore_index=4)(lg, lab.long())
+    crf = ModelLossSemsegGatedCRF()(s, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 32, 32)["loss"]
+    ms = RL.MumfordShah_Loss()(img, s)
+    pseudo = torch.argmax(s.detach(), 1, keepdim=True)
+    pd = RL.pDLoss(4, 4)(s, pseudo)
+    # pDLoss with ignored pixels: mark label==4 pixels ignored, others by scribble label
+    pd_ign = RL.pDLoss(4, 4)(s, lab.long().unsqueeze(1))
+    dice = RL.DiceLoss(4)(s, pseudo)
+    ent = RL.entropy_minmization(s)
+    mse = RL.softmax_mse_loss(lg, logits2)
+    names = ["pce", "gatedcrf", "mumford_shah", "pdice_argmax", "pdice_ignore", "dice", "entropy", "tv"]
+    vals = [ce, crf, ms, pd, pd_ign, dice, ent, tv_ref(s)]
+    for nm, v in zip(names, vals):
+        out["loss:" + nm] = np.float64(v.item())
+        (gr,) = torch.autograd.grad(v, lg, retain_graph=True)
+        out["grad:" + nm] = gr.numpy()
+    out["softmax_mse"] = mse.detach().numpy()
+    (gr,) = torch.autograd.grad(mse.sum(), lg, retain_graph=True)
+    out["grad:softmax_mse_sum"] = gr.numpy()
+    beta = 0.37
+    s2 = torch.softmax(logits2, 1)
+    out["beta"] = np.float64(beta)
+    out["pseudo_mix"] = torch.argmax(beta * s.detach() + (1 - beta) * s2, 1).numpy().astype(np.uint8)
+    # composite step losses
+    tot = ce + 0.1 * crf
+    (gr,) = torch.autograd.grad(tot, lg, retain_graph=True)
+    out["loss:step_pce_gatedcrf"] = np.float64(tot.item())
+    out["grad:step_pce_gatedcrf"] = gr.numpy()
+    # non-square / OOB-heavy case for the CRF border quirk (F10)
+    g2 = torch.Generator().manual_seed(77)
+    y2 = torch.softmax(torch.randn(1, 4, 16, 48, generator=g2), 1).requires_grad_(True)
+    i2 = torch.rand(1, 1, 16, 48, generator=g2)
+    c2 = ModelLossSemsegGatedCRF()(y2, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, i2, 16, 48)["loss"]
+    (g2y,) = torch.autograd.grad(c2, y2)
+    out["crf2:y"], out["crf2:image"] = y2.detach().numpy(), i2.numpy()
+    out["crf2:loss"], out["crf2:grad_y"] = np.float64(c2.item()), g2y.numpy()
+    np.savez_compressed(os.path.join(OUT, "losses_kat.npz"), **out)
+    print("losses_kat:", {k: float(out[k]) for k in out if k.startswith("loss:")})
+
+
+def net_golden(cct, n=2, hw=32, pseed=11, mseed=5, cseed=9):
+    from networks.unet import UNet, UNet_CCT
+
+    decs = ("main_decoder", "aux_decoder1") if cct else ("decoder",)
+    params = O.synth_params(1, 4, decs, pseed)
+    model = (UNet_CCT if cct else UNet)(1, 4)
+    assert list(model.state_dict().keys()) == list(params.keys()), "oracle key order != reference state_dict"
+    model.load_state_dict(params)
+    image, label = O.synth_batch(n, hw, hw, seed=2022, frac=0.06)
+    em = elem_masks(mseed, n, hw, hw)
+    cm = chan_masks(cseed, n) if cct else None
+    out = {"pseed": pseed, "mseed": mseed, "cseed": cseed, "n": n, "hw": hw,
+           "image": image.numpy(), "label": label.numpy()}
+
+    # eval forward (main head deterministic; aux head needs the channel masks even in eval, F5)
+    model.eval()
+    with torch.no_grad(), PatchedDropout(None, cm):
+        o = model(image)
+    if cct:
+        out["eval_main"], out["eval_aux"] = o[0].numpy(), o[1].numpy()
+    else:
+        out["eval_main"] = o.numpy()
+
+    # train forward + pCE+GatedCRF (+ DMPLS for cct) backward
+    model.train()
+    from utils import losses as RL
+    from utils.gate_crf_loss import ModelLossSemsegGatedCRF
+    with PatchedDropout(em, cm):
+        o = model(image)
+    main, aux = (o if cct else (o, None))
+    out["train_main"] = main.detach().numpy()
+    ce = torch.nn.CrossEntropyLoss(ignore_index=4)
+    soft = torch.softmax(main, 1)
+    if cct:
+        out["train_aux"] = aux.detach().numpy()
+        beta = 0.4321
+        soft2 = torch.softmax(aux, 1)
+        loss_ce = 0.5 * (ce(main, label.long()) + ce(aux, label.long()))
+        pseudo = torch.argmax(beta * soft.detach() + (1 - beta) * soft2.detach(), 1)
+        pdl = RL.pDLoss(4, 4)
+        loss = loss_ce + 0.5 * 0.5 * (pdl(soft, pseudo.unsqueeze(1)) + pdl(soft2, pseudo.unsqueeze(1)))
+        out["beta"] = np.float64(beta)
+        out["pseudo"] = pseudo.numpy().astype(np.uint8)
+    else:
+        crf = ModelLossSemsegGatedCRF()(soft, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, image, hw, hw)["loss"]
+        loss = ce(main, label.long()) + 0.1 * crf
+    model.zero_grad()
+    loss.backward()
+    out["loss"] = np.float64(loss.item())
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    keys, stats, small = grad_summary(grads)
+    out["grad_keys"] = np.array(keys)
+    out["grad_stats"] = stats
+    out.update(small)
+    sd = model.state_dict()
+    for k in ("encoder.in_conv.conv_conv.1.running_mean", "encoder.in_conv.conv_conv.1.running_var",
+              "encoder.down4.maxpool_conv.1.conv_conv.5.running_mean",
+              "encoder.down4.maxpool_conv.1.conv_conv.5.running_var"):
+        out["stat:" + k] = sd[k].numpy()
+    name = "unet_cct_dmpls" if cct else "unet_pce_gatedcrf"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", out["loss"], "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    losses_kat()
+    net_golden(False)
+    net_golden(True)

@@ -1,0 +1,374 @@
+"""CPU oracle for the WSL4MIS segmentation-training hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``wsl4mis_b200/`` may import this file; only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` do, and there only as the checker / the timed CPU baseline.
+
+This is a from-scratch *functional* restatement (plain torch fp32/fp64 ops on CPU tensors) of the
+reference's per-step arithmetic.  The reference itself is pure PyTorch with no native code, so the
+arithmetic lives in torch; the restatement is pinned against the unmodified reference modules by
+``oracle/make_golden.py`` (runs in the build container where ``/root/reference`` exists) and the
+fixtures it writes to ``tests/golden/`` (checked by ``tests/test_oracle_golden.py``).
+
+Every function cites the reference ``file:line`` (relative to ``/root/reference/code``) it follows.
+Parameter dictionaries use the reference's ``state_dict`` key names verbatim.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+FT = (16, 32, 64, 128, 256)            # networks/unet.py:291
+ENC_DROP = (0.05, 0.1, 0.2, 0.3, 0.5)  # networks/unet.py:292
+BN_EPS = 1e-5                          # nn.BatchNorm2d default, networks/unet.py:20
+BN_MOM = 0.1
+LRELU = 0.01                           # nn.LeakyReLU default, networks/unet.py:21
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter construction
+# ----------------------------------------------------------------------------------------------
+def unet_param_shapes(in_chns: int, class_num: int, decoders: Sequence[str] = ("decoder",)):
+    """Ordered {state_dict key: shape} for UNet (decoders=('decoder',)) or UNet_CCT
+    (decoders=('main_decoder','aux_decoder1')).  Order follows module registration order in
+    networks/unet.py:71-121,286-298,327-339 so it equals ``reference_model.state_dict().keys()``."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(prefix, cin, cout, k):
+        shapes[f"{prefix}.weight"] = (cout, cin, k, k)
+        shapes[f"{prefix}.bias"] = (cout,)
+
+    def bn(prefix, c):
+        shapes[f"{prefix}.weight"] = (c,)
+        shapes[f"{prefix}.bias"] = (c,)
+        shapes[f"{prefix}.running_mean"] = (c,)
+        shapes[f"{prefix}.running_var"] = (c,)
+        shapes[f"{prefix}.num_batches_tracked"] = ()
+
+    def block(prefix, cin, cout):
+        conv(f"{prefix}.0", cin, cout, 3)
+        bn(f"{prefix}.1", cout)
+        conv(f"{prefix}.4", cout, cout, 3)
+        bn(f"{prefix}.5", cout)
+
+    block("encoder.in_conv.conv_conv", in_chns, FT[0])
+    for i in range(1, 5):
+        block(f"encoder.down{i}.maxpool_conv.1.conv_conv", FT[i - 1], FT[i])
+    for d in decoders:
+        for j, (c1, c2) in enumerate(((FT[4], FT[3]), (FT[3], FT[2]), (FT[2], FT[1]), (FT[1], FT[0])), 1):
+            conv(f"{d}.up{j}.conv1x1", c1, c2, 1)
+            block(f"{d}.up{j}.conv.conv_conv", 2 * c2, c2)
+        conv(f"{d}.out_conv", FT[0], class_num, 3)
+    return shapes
+
+
+def synth_params(in_chns: int, class_num: int, decoders: Sequence[str], seed: int,
+                 dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Deterministic, torch-RNG-independent parameters (numpy RandomState stream, stable across
+    versions) so golden fixtures only need to store a seed.  Scales mimic kaiming-uniform fan-in
+    init; BN affine/running stats are randomised so every term of the BN formula is exercised."""
+    import numpy as np
+
+    rs = np.random.RandomState(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for k, shp in unet_param_shapes(in_chns, class_num, decoders).items():
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros((), dtype=torch.long)
+            continue
+        if k.endswith("running_var"):
+            a = rs.uniform(0.5, 1.5, size=shp)
+        elif k.endswith("running_mean"):
+            a = rs.uniform(-0.2, 0.2, size=shp)
+        elif len(shp) == 4:
+            fan_in = shp[1] * shp[2] * shp[3]
+            b = math.sqrt(3.0 / fan_in) * 1.4
+            a = rs.uniform(-b, b, size=shp)
+        elif ".1." in k[-12:] or ".5." in k[-12:]:  # BN weight / bias
+            a = rs.uniform(0.6, 1.4, size=shp) if k.endswith("weight") else rs.uniform(-0.3, 0.3, size=shp)
+        else:  # conv bias
+            a = rs.uniform(-0.1, 0.1, size=shp)
+        out[k] = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# network forward (functional)
+# ----------------------------------------------------------------------------------------------
+def _apply_elem_dropout(x, p, training, mask):
+    """nn.Dropout(p) (networks/unet.py:22).  ``mask`` (uint8/bool keep mask, same shape as x) makes
+    it deterministic; otherwise torch's RNG is used like the reference does."""
+    if not training or p == 0.0:
+        return x
+    if mask is None:
+        return F.dropout(x, p, True)
+    return x * mask.to(x.dtype) * (1.0 / (1.0 - p))
+
+
+def conv_block(p, prefix, x, training, drop_p, masks=None, new_stats=None):
+    """ConvBlock, networks/unet.py:13-29: conv3x3+bias -> BN -> LeakyReLU -> Dropout -> conv3x3 -> BN
+    -> LeakyReLU.  Running statistics are not mutated in ``p``; updated values are written to
+    ``new_stats`` (dict) when given."""
+    for idx, bnidx, dp in ((0, 1, drop_p), (4, 5, 0.0)):
+        x = F.conv2d(x, p[f"{prefix}.{idx}.weight"], p[f"{prefix}.{idx}.bias"], padding=1)
+        rm = p[f"{prefix}.{bnidx}.running_mean"].clone()
+        rv = p[f"{prefix}.{bnidx}.running_var"].clone()
+        x = F.batch_norm(x, rm, rv, p[f"{prefix}.{bnidx}.weight"], p[f"{prefix}.{bnidx}.bias"],
+                         training, BN_MOM, BN_EPS)
+        if new_stats is not None and training:
+            new_stats[f"{prefix}.{bnidx}.running_mean"] = rm
+            new_stats[f"{prefix}.{bnidx}.running_var"] = rv
+        x = F.leaky_relu(x, LRELU)
+        if dp > 0.0:
+            x = _apply_elem_dropout(x, dp, training, None if masks is None else masks.get(f"{prefix}.3"))
+    return x
+
+
+def encoder_forward(p, x, training, masks=None, new_stats=None):
+    """Encoder.forward, networks/unet.py:92-98 (+ DownBlock :32-44: MaxPool2d(2) then ConvBlock)."""
+    feats = [conv_block(p, "encoder.in_conv.conv_conv", x, training, ENC_DROP[0], masks, new_stats)]
+    for i in range(1, 5):
+        x_in = F.max_pool2d(feats[-1], 2)
+        feats.append(conv_block(p, f"encoder.down{i}.maxpool_conv.1.conv_conv", x_in, training,
+                                ENC_DROP[i], masks, new_stats))
+    return feats
+
+
+def decoder_forward(p, dname, feats, training, new_stats=None):
+    """Decoder.forward, networks/unet.py:123-135; UpBlock (bilinear branch) :63-68:
+    conv1x1 -> bilinear x2 (align_corners=True) -> cat([skip, up]) -> ConvBlock(p=0)."""
+    x = feats[4]
+    for j, skip in enumerate((feats[3], feats[2], feats[1], feats[0]), 1):
+        t = F.conv2d(x, p[f"{dname}.up{j}.conv1x1.weight"], p[f"{dname}.up{j}.conv1x1.bias"])
+        t = F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
+        x = conv_block(p, f"{dname}.up{j}.conv.conv_conv", torch.cat([skip, t], 1), training, 0.0,
+                       None, new_stats)
+    return F.conv2d(x, p[f"{dname}.out_conv.weight"], p[f"{dname}.out_conv.bias"], padding=1)
+
+
+def unet_forward(p, x, training=True, masks=None, new_stats=None):
+    """UNet.forward, networks/unet.py:300-303."""
+    return decoder_forward(p, "decoder", encoder_forward(p, x, training, masks, new_stats), training, new_stats)
+
+
+def channel_dropout(x, keep):
+    """Dropout(x, p=0.5) = F.dropout2d with training=True always (networks/unet.py:254-256, F5):
+    per-(n,c) Bernoulli keep mask, survivors scaled by 2.  ``keep`` is a [N,C] 0/1 tensor."""
+    if keep is None:
+        return F.dropout2d(x, 0.5)
+    return x * (keep.to(x.dtype) * 2.0)[:, :, None, None]
+
+
+def unet_cct_forward(p, x, training=True, masks=None, chan_keep=None, new_stats=None):
+    """UNet_CCT.forward, networks/unet.py:341-346.  ``chan_keep`` is a list of five [N,C_i] keep masks
+    for the aux branch (None -> torch RNG, as the reference)."""
+    feats = encoder_forward(p, x, training, masks, new_stats)
+    main = decoder_forward(p, "main_decoder", feats, training, new_stats)
+    aux_feats = [channel_dropout(f, None if chan_keep is None else chan_keep[i]) for i, f in enumerate(feats)]
+    aux = decoder_forward(p, "aux_decoder1", aux_feats, training, new_stats)
+    return main, aux
+
+
+# ----------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------
+def pce_loss(logits, label, ignore_index=4):
+    """CrossEntropyLoss(ignore_index=4)(outputs, label.long()), constructed at
+    train_weakly_supervised_pCE_2D.py:81 and called at :100.  Mean over labelled pixels; NaN when
+    no pixel is labelled (torch semantics)."""
+    return F.cross_entropy(logits, label.long(), ignore_index=ignore_index)
+
+
+def gated_crf_loss(y, image, radius=5, sigma_xy=6.0, sigma_rgb=0.1, weight=1.0):
+    """ModelLossSemsegGatedCRF.forward for the argument pattern every WSL4MIS script uses
+    (utils/gate_crf_loss.py:20-117 with kernels_desc=[{'weight':1,'xy':6,'rgb':0.1}], radius 5, no
+    masks, Potts compatibility; called at train_weakly_supervised_pCE_GatedCRFLoss_2D.py:115-122).
+
+    Restated without F.unfold: loop over the (2r+1)^2-1 offsets on zero-padded tensors.  Zero padding
+    of the *features* (gate_crf_loss.py:188) means an out-of-bounds neighbour has xy=(0,0)/sigma and
+    intensity 0, so its kernel value is non-zero and is counted in ``kernels.sum()`` (:99) while
+    contributing nothing to the pairwise product."""
+    N, C, H, W = y.shape
+    dt = y.dtype
+    xs = torch.arange(W, dtype=dt).view(1, 1, 1, W).expand(N, 1, H, W) / sigma_xy      # :174-181, :154
+    ys = torch.arange(H, dtype=dt).view(1, 1, H, 1).expand(N, 1, H, W) / sigma_xy
+    inten = F.adaptive_avg_pool2d(image.to(dt), (H, W)) / sigma_rgb                      # :127-132
+    feat = torch.cat([xs, ys, inten], 1)
+    r = radius
+    fpad = F.pad(feat, (r, r, r, r))
+    ypad = F.pad(y, (r, r, r, r))
+    ksum = torch.zeros((), dtype=dt)
+    pair = torch.zeros((), dtype=dt)
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            if dy == 0 and dx == 0:
+                continue                                                                # centre := 0, :171
+            fn = fpad[:, :, r + dy:r + dy + H, r + dx:r + dx + W]
+            k = weight * torch.exp(-0.5 * ((fn - feat) ** 2).sum(1, keepdim=True))       # :168-170
+            yn = ypad[:, :, r + dy:r + dy + H, r + dx:r + dx + W]
+            ksum = ksum + k.sum()
+            pair = pair + (k * yn * y).sum()
+    return (ksum - pair) / (N * H * W)                                                  # :63, :97-99, :116
+
+
+def mumford_shah_loss(image, prob):
+    """MumfordShah_Loss.forward(image, prediction), utils/losses.py:275-309, as written: the image is
+    passed as ``output`` and the softmax as ``target``."""
+    loss = prob.new_zeros(())
+    isum = image.sum((2, 3))                                      # :286-287 denominator
+    for k in range(prob.shape[1]):
+        t = prob[:, k:k + 1].expand(-1, image.shape[1], -1, -1)
+        cent = (t * image).sum((2, 3)) / isum
+        lvl = t - cent[:, :, None, None]
+        loss = loss + (lvl * lvl * image).sum()
+    dh = (prob[:, :, 1:, :] - prob[:, :, :-1, :]).abs().sum()    # gradientLoss2d :296-304 ('l1')
+    dw = (prob[:, :, :, 1:] - prob[:, :, :, :-1]).abs().sum()
+    return loss + dh + dw
+
+
+def pdice_loss(prob, target, n_classes=4, ignore_index=4):
+    """pDLoss.forward, utils/losses.py:195-232.  ``target`` is [N,1,H,W] integer.
+
+    As written in the reference the ignore mask keeps its channel dim ([N,1,H,W], :219-220) while the
+    per-class score/target slices are [N,H,W] (:229), so ``score * target * ignore_mask`` (:209-211)
+    broadcasts to [N,N,H,W]: every per-pixel product is multiplied by the *batch-summed* mask at that
+    pixel location, M[h,w] = sum_a mask[a,h,w] (= N when nothing is ignored, as in the DMPLS script
+    where the target is an argmax map).  Reproduced as written (found by the golden fixtures)."""
+    keep = (target != ignore_index).to(prob.dtype)[:, 0]           # [N,H,W]
+    msum = keep.sum(0, keepdim=True)                                # [1,H,W]  batch-summed mask
+    loss = prob.new_zeros(())
+    for i in range(n_classes):
+        t = (target == i).to(prob.dtype)[:, 0]
+        s = prob[:, i]
+        inter = (s * t * msum).sum()
+        ysum = (t * t * msum).sum()
+        zsum = (s * s * msum).sum()
+        loss = loss + (1 - (2 * inter + 1e-5) / (zsum + ysum + 1e-5))
+    return loss / n_classes
+
+
+def dice_loss(prob, target, n_classes=4):
+    """DiceLoss.forward (softmax=False, weight=None), utils/losses.py:156-192 (no mask, plain sums)."""
+    loss = prob.new_zeros(())
+    for i in range(n_classes):
+        t = (target == i).to(prob.dtype)[:, 0]
+        s = prob[:, i]
+        loss = loss + (1 - (2 * (s * t).sum() + 1e-5) / ((s * s).sum() + (t * t).sum() + 1e-5))
+    return loss / n_classes
+
+
+def mix_pseudo_label(p1, p2, beta):
+    """argmax(beta*p1 + (1-beta)*p2, dim=1), train_weakly_supervised_segmentation_pCE_ours_proposed.py:119-120."""
+    return torch.argmax(beta * p1.detach() + (1.0 - beta) * p2.detach(), dim=1)
+
+
+def tv_loss(prob):
+    """tv_loss, train_weakly_supervised_pCE_TV_2D.py:58-65."""
+    mn = -F.max_pool2d(-prob, (3, 3), 1, 1)
+    contour = torch.relu(F.max_pool2d(mn, (3, 3), 1, 1) - mn)
+    return contour.abs().mean()
+
+
+def entropy_minimization(prob):
+    """entropy_minmization, utils/losses.py:235-239."""
+    return (-(prob * torch.log(prob + 1e-6)).sum(1)).mean()
+
+
+def softmax_mse(a_logits, b_logits):
+    """softmax_mse_loss (sigmoid=False), utils/losses.py:65-82."""
+    return (F.softmax(a_logits, 1) - F.softmax(b_logits, 1)) ** 2
+
+
+# ----------------------------------------------------------------------------------------------
+# step bodies (loss composition) and the optimiser
+# ----------------------------------------------------------------------------------------------
+def step_loss_pce_gatedcrf(logits, image, label):
+    """train_weakly_supervised_pCE_GatedCRFLoss_2D.py:111-123."""
+    soft = torch.softmax(logits, 1)
+    ce = pce_loss(logits, label)
+    crf = gated_crf_loss(soft, image)
+    return ce + 0.1 * crf, ce, crf
+
+
+def step_loss_dmpls(logits1, logits2, label, beta):
+    """train_weakly_supervised_segmentation_pCE_ours_proposed.py:108-125."""
+    s1, s2 = torch.softmax(logits1, 1), torch.softmax(logits2, 1)
+    ce = 0.5 * (pce_loss(logits1, label) + pce_loss(logits2, label))
+    pseudo = mix_pseudo_label(s1, s2, beta).unsqueeze(1)
+    pse = 0.5 * (pdice_loss(s1, pseudo) + pdice_loss(s2, pseudo))
+    return ce + 0.5 * pse, ce, pse, pseudo[:, 0]
+
+
+def step_loss_pce_ms(logits, image, label):
+    """train_weakly_supervised_pCE_MumfordShah_Loss_2D.py:98-103."""
+    soft = torch.softmax(logits, 1)
+    ce = pce_loss(logits, label)
+    ms = mumford_shah_loss(image, soft)
+    return ce + 1e-6 * ms, ce, ms
+
+
+def step_loss_pce_tv(logits, label):
+    """train_weakly_supervised_pCE_TV_2D.py:109-114 (tv on outputs_soft[1:], batch slice, F12)."""
+    soft = torch.softmax(logits, 1)
+    ce = pce_loss(logits, label)
+    tv = tv_loss(soft[1:])
+    return ce + 1e-2 * tv, ce, tv
+
+
+def sgd_step(params, grads, moms, lr, momentum=0.9, weight_decay=1e-4):
+    """optim.SGD(lr, momentum=0.9, weight_decay=1e-4).step(), train_weakly_supervised_pCE_2D.py:79-80,104.
+    torch semantics: g += wd*w; first step buf = g, afterwards buf = mu*buf + g; w -= lr*buf.
+    ``moms[k] is None`` marks the first step."""
+    for k in params:
+        g = grads[k] + weight_decay * params[k]
+        moms[k] = g.clone() if moms.get(k) is None else moms[k] * momentum + g
+        params[k] = params[k] - lr * moms[k]
+
+
+def poly_lr(base_lr, iter_num, max_iterations):
+    """train_weakly_supervised_pCE_2D.py:106-108 (applied after the step, using the pre-increment iter)."""
+    return base_lr * (1.0 - iter_num / max_iterations) ** 0.9
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic batch
+# ----------------------------------------------------------------------------------------------
+def synth_batch(n, h=256, w=256, seed=2022, frac=0.03, dense=False):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(n, 1, h, w, generator=g)
+    if dense:
+        label = torch.randint(0, 4, (n, h, w), generator=g, dtype=torch.uint8)
+    else:
+        label = torch.full((n, h, w), 4, dtype=torch.uint8)
+        m = torch.rand(n, h, w, generator=g) < frac
+        vals = torch.randint(0, 4, (int(m.sum()),), generator=g, dtype=torch.uint8)
+        label[m] = vals
+        label[0, 0, 0] = 1  # at least one labelled pixel
+    return image, label
+
+
+def full_step(p, image, label, variant="pce_gatedcrf", cct=False, masks=None, chan_keep=None, beta=0.5):
+    """One forward+loss+backward of a BASELINE config on CPU.  Returns (loss, grads dict, outputs)."""
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+    if cct:
+        main, aux = unet_cct_forward(leaves, image, True, masks, chan_keep)
+    else:
+        main, aux = unet_forward(leaves, image, True, masks), None
+    if variant == "pce":
+        loss = pce_loss(main, label)
+    elif variant == "pce_gatedcrf":
+        loss = step_loss_pce_gatedcrf(main, image, label)[0]
+    elif variant == "pce_ms":
+        loss = step_loss_pce_ms(main, image, label)[0]
+    elif variant == "pce_tv":
+        loss = step_loss_pce_tv(main, label)[0]
+    elif variant == "dmpls":
+        loss = step_loss_dmpls(main, aux, label, beta)[0]
+    else:
+        raise ValueError(variant)
+    names = [k for k, v in leaves.items() if v.requires_grad]
+    gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, gs)}
+    return loss.detach(), grads, (main.detach(), None if aux is None else aux.detach())
