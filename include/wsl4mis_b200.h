@@ -1,0 +1,146 @@
+/*
+ * wsl4mis_b200 -- C ABI of the B200 (sm_100a) kernels behind the WSL4MIS segmentation-training hot path.
+ *
+ * The reference (HiLab-git/WSL4MIS) has no native code and no FFI: every operation below is, in the reference,
+ * a stock PyTorch call made from Python.  Each entry point therefore cites the reference *Python* call site
+ * (paths relative to /root/reference/code) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*-compatible handle), never
+ *     allocates, never synchronises; the caller owns all buffers;
+ *   - return 0 on success, negative on error; wsl_last_error() returns a thread-local message;
+ *   - "act" tensors are channels-last (NHWC) bf16; logits / probabilities / losses are fp32 NCHW;
+ *   - `ws` is a caller-provided workspace of wsl_workspace_floats() floats, zero-initialised ONCE by the
+ *     caller (kernels leave its ticket words zero again); one workspace must not be shared by two kernels
+ *     that may run concurrently.
+ */
+#ifndef WSL4MIS_B200_H
+#define WSL4MIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* cudaStream_t;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+const char* wsl_last_error(void);
+int wsl_abi_version(void);
+int wsl_workspace_floats(void);
+
+/* ---- losses (utils/losses.py, utils/gate_crf_loss.py, torch CrossEntropyLoss) ---------------------------- */
+
+/* torch.softmax(outputs,1) + CrossEntropyLoss(ignore_index)(outputs,label.long()):
+ * train_weakly_supervised_pCE_2D.py:81,98,100.  probs may be NULL.  out2 = {loss, labelled-pixel count}. */
+int wsl_softmax_pce_fwd(const float* logits, const uint8_t* label, float* probs, int N, int C, int H, int W,
+                        int ignore_index, float* out2, float* ws, cudaStream_t stream);
+
+/* d(w_ce*pCE + <gprobs*gprobs_scale, softmax(logits)>)/dlogits, times *grad_out (NULL -> 1).
+ * Replaces autograd through softmax / log_softmax+nll_loss.  label/gprobs may be NULL. */
+int wsl_head_bwd(const float* probs, const uint8_t* label, const float* ce_stats, const float* grad_out,
+                 float w_ce, const float* gprobs, float gprobs_scale, int N, int C, int H, int W,
+                 int ignore_index, float* dlogits, cudaStream_t stream);
+
+/* ModelLossSemsegGatedCRF.forward(y, [{'weight':w,'xy':sxy,'rgb':srgb}], radius, image, H, W)['loss']:
+ * utils/gate_crf_loss.py:20-117 (fast path: no masks, Potts).  Also emits d loss / d y into gprobs (may be
+ * NULL).  out2 = {loss, kernels.sum()}. */
+int wsl_gatedcrf_fwd(const float* probs, const float* image, float* gprobs, int N, int C, int H, int W,
+                     int radius, float sigma_xy, float sigma_rgb, float weight, float* out2, float* ws,
+                     cudaStream_t stream);
+
+/* MumfordShah_Loss()(image, prediction): utils/losses.py:275-309.  centroids: [N*C] scratch kept for bwd. */
+int wsl_mumford_shah_fwd(const float* image, const float* probs, int N, int C, int H, int W, float* out1,
+                         float* centroids, float* ws, cudaStream_t stream);
+int wsl_mumford_shah_bwd(const float* image, const float* probs, const float* centroids, int N, int C, int H,
+                         int W, float scale, int accumulate, float* gprobs, cudaStream_t stream);
+
+/* argmax(beta*p1 + (1-beta)*p2, dim=1): train_weakly_supervised_segmentation_pCE_ours_proposed.py:117-120.
+ * p2 may be NULL (plain argmax). */
+int wsl_mix_argmax(const float* p1, const float* p2, float beta, float one_minus_beta, int N, int C, int H, int W,
+                   uint8_t* out, cudaStream_t stream);
+
+/* batch-summed ignore mask of pDLoss (utils/losses.py:219-220 + the [N,1,H,W] broadcast at :209-211). */
+int wsl_mask_count(const uint8_t* target, int N, int H, int W, int ignore_index, float* msum, cudaStream_t stream);
+
+/* pDLoss(n_classes=4, ignore_index)(probs, target): utils/losses.py:195-232.  msum NULL -> constant mconst.
+ * out13 = {loss, I[4], Y[4], Z[4]} (kept for the backward). */
+int wsl_pdice_fwd(const float* probs, const uint8_t* target, const float* msum, float mconst, int N, int C, int H,
+                  int W, float* out13, float* ws, cudaStream_t stream);
+int wsl_pdice_bwd(const float* probs, const uint8_t* target, const float* msum, float mconst, const float* sums13,
+                  int N, int C, int H, int W, float scale, int accumulate, float* gprobs, cudaStream_t stream);
+
+/* tv_loss(pred): train_weakly_supervised_pCE_TV_2D.py:58-65.  planes = N'*C.  gprobs_zeroed may be NULL;
+ * when given it must be zero-filled and receives grad_scale * d loss / d pred. */
+int wsl_tv_loss(const float* probs, int planes, int H, int W, float grad_scale, float* gprobs_zeroed, float* out1,
+                float* ws, cudaStream_t stream);
+
+/* ---- network operators (networks/unet.py) ---------------------------------------------------------------- */
+
+/* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the
+ * data gradient.  Two channels-last sources model torch.cat([x2,x1],1) (unet.py:67).
+ * out_mode 0: bf16 NHWC with CoutStore channels; 1: fp32 NCHW with CoutStore channels. */
+int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const float* wpk,
+                    const float* bias, void* out, int out_mode, int N, int H, int W, int CinP, int CoutP,
+                    int CoutStore, int ksize, cudaStream_t stream);
+
+/* weight (+bias) gradient of the same convolutions, accumulated into zero-filled fp32 torch-layout grads. */
+int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int CoutP,
+                     float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
+
+/* tcgen05 implicit-GEMM convolution (conv_tc.cu): same contract as wsl_conv_direct for bf16 NHWC sources with
+ * channel counts that are multiples of 16.  wpk_bf16: [taps][CoutP][CinP] (K-major).  Requires wsl_tc_available(). */
+int wsl_tc_available(void);
+int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
+                void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
+                cudaStream_t stream);
+/* nn.BatchNorm2d training statistics (unet.py:20,24): save = {mean[C], invstd[C]}, ss = {scale[C], shift[C]};
+ * running stats / num_batches_tracked updated in place when non-NULL. */
+int wsl_bn_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
+                 float* ss, float* ws, cudaStream_t stream);
+int wsl_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, int C, float* ss, cudaStream_t stream);
+
+/* BN-affine + LeakyReLU(slope) + Dropout(p) (unet.py:20-22) and, when pooled != NULL, MaxPool2d(2) (unet.py:38)
+ * of the result.  mask: optional uint8 keep mask (NHWC); NULL -> counter RNG on `seed` (+ *seed_ptr when non-NULL, so a
+ * captured CUDA graph draws fresh masks every replay). */
+int wsl_bn_act_fwd(const void* y, const float* ss, int N, int H, int W, int C, float slope, float drop_p,
+                   const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr, void* act,
+                   void* pooled, uint8_t* pool_idx, cudaStream_t stream);
+
+/* backward of the same chain: dA = g0 + cs1*g1 + maxpool-routed gpool (each optional) -> dY (bf16), dgamma, dbeta. */
+int wsl_bn_bwd(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+               const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
+               const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
+               cudaStream_t stream);
+
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:56-57) and its transpose. */
+int wsl_upsample2x_fwd(const void* t, int N, int h, int w, int C, void* u, cudaStream_t stream);
+int wsl_upsample2x_bwd(const void* du, int N, int h, int w, int C, void* dt, cudaStream_t stream);
+
+/* F.dropout2d(x, 0.5) of the aux branch (unet.py:254-256,344): cs[N*C] in {0, 1/(1-p)}. */
+int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long* seed_ptr, int n, float p, float* cs,
+                      cudaStream_t stream);
+int wsl_chan_scale(const void* a, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream);
+
+/* layout helpers at the API boundary */
+int wsl_nchw_f32_to_nhwc_bf16(const float* src, int N, int Creal, int H, int W, int CP, void* dst, cudaStream_t stream);
+int wsl_nhwc_bf16_to_nchw_f32(const void* src, int N, int C, int H, int W, float* dst, cudaStream_t stream);
+
+/* fp32 torch-layout conv weight -> packed operands (any output may be NULL), see net_ops.cu */
+int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,
+                          int ci_count, float* wf, float* wd, void* bf, void* bd, cudaStream_t stream);
+
+/* optim.SGD(lr, momentum, weight_decay).step() over a flat fp32 buffer (train_weakly_supervised_pCE_2D.py:79-80,104);
+ * lr is read from lr_ptr (device) when non-NULL so a captured CUDA graph follows the poly schedule (:106-108). */
+int wsl_sgd_step(float* param, const float* grad, float* mom, long long n, const float* lr_ptr, float lr,
+                 float momentum, float weight_decay, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSL4MIS_B200_H */

@@ -1,0 +1,412 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (3x3 pad 1 / 1x1) on channels-last bf16 activations.
+//
+//   D[128 pixels, NT couts] (fp32, TMEM) = sum_{tap} sum_{kblock} A_tap[128 x KBLK] * B_tap[KBLK x NT]
+//
+//   * A: one TMA 4-D box (KBLK channels x 16 w x 8 h x 1 image) per (tap, k-block) at the tap-shifted pixel
+//     coordinate; TMA's out-of-bounds zero fill IS the convolution's zero padding (im2col-free).
+//   * B: packed weights [tap][Cout][Cin] bf16 (K-major), one 3-D box (KBLK x NT x 1) per (tap, k-block).
+//   * both land in 128B/64B/32B-swizzled shared memory (swizzle span = KBLK*2 bytes) and are consumed by
+//     tcgen05.mma.cta_group::1.kind::f16 (M=128, N=NT, K=16) issued by one elected thread; fp32 accumulators in TMEM.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//     (tcgen05.ld 32x32b -> +bias -> bf16 NHWC / fp32 NCHW stores).
+//   * mbarrier ring (full/empty) of STAGES stages between TMA and MMA; tcgen05.commit releases a stage.
+//
+// The same kernel is the data-gradient (dgrad) kernel when fed tap-flipped, transposed weights, and the 1x1
+// convolution with TAPS = 1.  Two source tensors model torch.cat([skip, up], 1) without materialising it.
+// Reference call sites: networks/unet.py:19,23 (3x3), :55 (1x1), :67 (concat), :120 (out_conv).
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <string.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 24)) {
+      printf("wsl conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major operand, swizzle span = SW bytes (32/64/128):
+//   canonical layout ((8,m),(T,2)):((SW/16,SBO),(1,.)) in 16-byte units -> 8-row groups SBO = 8*SW bytes apart.
+template <int SW>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  constexpr uint64_t layout = (SW == 128) ? 2 : (SW == 64) ? 4 : 6;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);          // start address  [0,14)
+  d |= (uint64_t)1 << 16;                            // LBO (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)((8 * SW) >> 4) << 32;              // SBO [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= layout << 61;                                 // swizzle mode
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn_major = 0, int b_mn_major = 0, int m = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct ConvTcParams {
+  int N, H, W;
+  int C0, C1;        // channels of source 0 / source 1 (C1 may be 0)
+  int CoutP;         // padded output channels (rows of the packed weight)
+  int CoutStore;     // channels stored per pixel (bf16 NHWC) or real channels (fp32 NCHW)
+  int taps, ks;
+  int tiles_x, tiles_y;
+  int out_mode;
+  const float* bias;
+  void* out;
+};
+
+constexpr int TILE_W = 16, TILE_H = 8, TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+
+template <int KBLK, int NT, int STAGES>
+struct ConvSmem {
+  static constexpr int A_BYTES = TILE_M * KBLK * 2;
+  static constexpr int B_BYTES = NT * KBLK * 2;
+  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int KBLK, int NT, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0,
+                                                                 const __grid_constant__ CUtensorMap map_a1,
+                                                                 const __grid_constant__ CUtensorMap map_b, const ConvTcParams p) {
+  using S = ConvSmem<KBLK, NT, STAGES>;
+  constexpr int SW = KBLK * 2;
+  constexpr uint32_t TMEM_COLS = NT < 32 ? 32 : NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int n = tile / (p.tiles_x * p.tiles_y);
+  const int tr = tile - n * p.tiles_x * p.tiles_y;
+  const int y0 = (tr / p.tiles_x) * TILE_H, x0 = (tr % p.tiles_x) * TILE_W;
+  const int n0 = blockIdx.y * NT;
+  const int pad = p.ks >> 1;
+  const int kb0 = p.C0 / KBLK, kb1 = p.C1 / KBLK;
+  const int iters = p.taps * (kb0 + kb1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_a0);
+    prefetch_tmap(&map_b);
+    if (kb1) prefetch_tmap(&map_a1);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < p.taps; ++t) {
+        const int dy = t / p.ks - pad, dx = t % p.ks - pad;
+        for (int kb = 0; kb < kb0 + kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
+          if (kb < kb0) tma_load_4d(&map_a0, &full_bar[s], a_dst, kb * KBLK, x0 + dx, y0 + dy, n);
+          else          tma_load_4d(&map_a1, &full_bar[s], a_dst, (kb - kb0) * KBLK, x0 + dx, y0 + dy, n);
+          tma_load_3d(&map_b, &full_bar[s], b_dst, kb * KBLK, n0, t);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(NT);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+        const uint64_t adesc = make_kmajor_desc<SW>(a_addr);
+        const uint64_t bdesc = make_kmajor_desc<SW>(b_addr);
+#pragma unroll
+        for (int k = 0; k < KBLK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte start-address field
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
+        if (it == iters - 1) umma_commit(accum_bar); // accumulator complete -> epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile
+    const int gy = y0 + m / TILE_W, gx = x0 + m % TILE_W;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const bool inb = (gy < p.H) && (gx < p.W);
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += p.bias[n0 + c + j];
+      }
+      if (!inb) continue;
+      if (p.out_mode == 0) {
+        if (n0 + c < p.CoutStore) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)n * p.H + gy) * p.W + gx) * p.CoutStore + n0 + c;
+          float lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+          reinterpret_cast<uint4*>(o)[0] = pack8(lo);
+          if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c + j < p.CoutStore) o[(((long long)n * p.CoutStore + n0 + c + j) * p.H + gy) * p.W + gx] = v[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int kblk) {
+  return kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+struct MapKey {
+  const void* ptr; long long d[4]; int b[4]; int rank; int sw;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ULL; }
+    return (size_t)h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// bf16 tensor, dims innermost-first; strides derived (dense).  Cached by (ptr, dims, box, swizzle).
+int get_map(const void* ptr, int rank, const long long* dims, const int* box, int kblk, CUtensorMap* out) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.rank = rank; key.sw = kblk;
+  for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { wsl_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return -3; }
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t bdim[4], estr[4];
+  unsigned long long stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bdim[i] = (cuuint32_t)box[i];
+    estr[i] = 1;
+    stride *= (unsigned long long)dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { wsl_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -4; }
+  std::lock_guard<std::mutex> g(g_map_mu);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
+template <int KBLK, int NT, int STAGES>
+int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTcParams& p, cudaStream_t stream) {
+  using S = ConvSmem<KBLK, NT, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KBLK, NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { wsl_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -5; }
+    attr = true;
+  }
+  dim3 grid(p.N * p.tiles_x * p.tiles_y, p.CoutP / NT);
+  conv_tc_kernel<KBLK, NT, STAGES><<<grid, NUM_THREADS, S::TOTAL, stream>>>(a0, a1, b, p);
+  return wsl_check_launch("conv_tc");
+}
+
+template <int KBLK>
+int dispatch_nt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTcParams& p, int nt, cudaStream_t stream) {
+  switch (nt) {
+    case 16:  return launch_conv<KBLK, 16, 6>(a0, a1, b, p, stream);
+    case 32:  return launch_conv<KBLK, 32, 6>(a0, a1, b, p, stream);
+    case 64:  return launch_conv<KBLK, 64, 6>(a0, a1, b, p, stream);
+    case 128: return launch_conv<KBLK, 128, 5>(a0, a1, b, p, stream);
+  }
+  wsl_set_error("conv_tc: unsupported N tile %d", nt);
+  return -1;
+}
+
+}  // namespace
+
+WSL_API int wsl_tc_available(void) { return get_encode() != nullptr ? 1 : 0; }
+
+WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+                        int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc: ksize must be 1 or 3");
+  WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc: source channels must be multiples of 16 (got %d,%d)", C0, C1);
+  WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc: CoutP must be a multiple of 16");
+  WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_conv_tc: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
+  // k-block = largest of 64/32/16 dividing both sources' channel counts
+  int kblk = 64;
+  while (kblk > 16 && (C0 % kblk != 0 || (C1 > 0 && C1 % kblk != 0))) kblk >>= 1;
+  int nt = CoutP >= 128 ? 128 : CoutP;
+  WSL_REQUIRE(CoutP % nt == 0 && (nt == 16 || nt == 32 || nt == 64 || nt == 128), "wsl_conv_tc: unsupported CoutP %d", CoutP);
+  const int CinP = C0 + C1, T = ksize * ksize;
+  CUtensorMap a0, a1, b;
+  {
+    long long d[4] = {C0, W, H, N};
+    int bx[4] = {kblk, TILE_W, TILE_H, 1};
+    int rc = get_map(src0, 4, d, bx, kblk, &a0);
+    if (rc) return rc;
+  }
+  if (C1 > 0) {
+    long long d[4] = {C1, W, H, N};
+    int bx[4] = {kblk, TILE_W, TILE_H, 1};
+    int rc = get_map(src1, 4, d, bx, kblk, &a1);
+    if (rc) return rc;
+  } else {
+    a1 = a0;
+  }
+  {
+    long long d[3] = {CinP, CoutP, T};
+    int bx[3] = {kblk, nt, 1};
+    int rc = get_map(wpk_bf16, 3, d, bx, kblk, &b);
+    if (rc) return rc;
+  }
+  ConvTcParams p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore; p.taps = T; p.ks = ksize;
+  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.bias = bias; p.out = out;
+  switch (kblk) {
+    case 64: return dispatch_nt<64>(a0, a1, b, p, nt, stream);
+    case 32: return dispatch_nt<32>(a0, a1, b, p, nt, stream);
+    default: return dispatch_nt<16>(a0, a1, b, p, nt, stream);
+  }
+}

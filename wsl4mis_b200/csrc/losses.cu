@@ -1,0 +1,619 @@
+// Weakly-supervised loss stack for 4-class 2D segmentation, fp32 NCHW probabilities/logits.
+// Each kernel cites the reference lines (relative to /root/reference/code) whose result it reproduces.
+#include "common.cuh"
+
+namespace {
+
+constexpr int C4 = 4;
+constexpr int TPB = 256;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ------------------------------------------------------------------------------------------------
+// K7: softmax + partial cross-entropy.  torch.softmax(outputs,1) (train_weakly_supervised_pCE_2D.py:98)
+// and CrossEntropyLoss(ignore_index=4) (:81,:100) in one pass: 17 B/pixel algorithmic (4 logits, 1 label
+// byte ... plus 16 B/pixel of probabilities when they are requested by a downstream regulariser).
+// Each thread owns 4 consecutive pixels (float4 per class plane).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) softmax_pce_fwd_kernel(
+    const float* __restrict__ logits, const uint8_t* __restrict__ label, float* __restrict__ probs,
+    int HW, long long nquads, int ignore_index, float* partials, unsigned* ticket, float* out) {
+  float acc[2] = {0.f, 0.f};  // nll sum, labelled count
+  const int qpi = HW >> 2;
+  for (long long q = blockIdx.x * (long long)TPB + threadIdx.x; q < nquads; q += (long long)gridDim.x * TPB) {
+    const long long n = q / qpi;
+    const int r = (int)(q - n * qpi);
+    const float* base = logits + n * C4 * (long long)HW + r * 4;
+    float x[C4][4];
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      float4 v = ld4(base + (long long)c * HW);
+      x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
+    }
+    int lab[4] = {ignore_index, ignore_index, ignore_index, ignore_index};
+    if (label != nullptr) {
+      uchar4 l4 = *reinterpret_cast<const uchar4*>(label + n * (long long)HW + r * 4);
+      lab[0] = l4.x; lab[1] = l4.y; lab[2] = l4.z; lab[3] = l4.w;
+    }
+    float p[C4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float m = fmaxf(fmaxf(x[0][j], x[1][j]), fmaxf(x[2][j], x[3][j]));
+      float e[C4], s = 0.f;
+#pragma unroll
+      for (int c = 0; c < C4; ++c) { e[c] = expf(x[c][j] - m); s += e[c]; }
+      const float inv = 1.0f / s;
+#pragma unroll
+      for (int c = 0; c < C4; ++c) p[c][j] = e[c] * inv;
+      if (lab[j] != ignore_index && lab[j] < C4) {
+        float xl = lab[j] == 0 ? x[0][j] : lab[j] == 1 ? x[1][j] : lab[j] == 2 ? x[2][j] : x[3][j];
+        acc[0] += logf(s) - (xl - m);
+        acc[1] += 1.f;
+      }
+    }
+    if (probs != nullptr) {
+      float* pb = probs + n * C4 * (long long)HW + r * 4;
+#pragma unroll
+      for (int c = 0; c < C4; ++c) st4(pb + (long long)c * HW, make_float4(p[c][0], p[c][1], p[c][2], p[c][3]));
+    }
+  }
+  __shared__ double res[2];
+  if (block_reduce_final<2, TPB>(acc, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      out[0] = (float)(res[0] / res[1]);  // 0 labelled pixels -> NaN, as torch
+      out[1] = (float)res[1];
+    }
+  }
+}
+
+// Backward of (w_ce * pCE + <gprobs, softmax>) w.r.t. logits:
+//   dlogit_c = w_ce * go * (p_c - [c==label]) / count   (labelled pixels only)
+//            + gs * p_c * (g_c - sum_k g_k p_k)         (softmax Jacobian applied to gprobs)
+// `go` (upstream grad of the pCE scalar) is read from device memory when go_ptr != nullptr; gprobs already
+// carries its own upstream scaling.
+__global__ void __launch_bounds__(TPB) head_bwd_kernel(
+    const float* __restrict__ probs, const uint8_t* __restrict__ label, const float* __restrict__ ce_stats,
+    const float* __restrict__ go_ptr, float w_ce, const float* __restrict__ gprobs, float gs,
+    int HW, long long nquads, int ignore_index, float* __restrict__ dlogits) {
+  const int qpi = HW >> 2;
+  const float go = go_ptr ? *go_ptr : 1.0f;
+  const float cew = (label != nullptr && w_ce != 0.f) ? w_ce * go / ce_stats[1] : 0.f;
+  const float gsc = gs;
+  for (long long q = blockIdx.x * (long long)TPB + threadIdx.x; q < nquads; q += (long long)gridDim.x * TPB) {
+    const long long n = q / qpi;
+    const int r = (int)(q - n * qpi);
+    const long long off = n * C4 * (long long)HW + r * 4;
+    float p[C4][4], g[C4][4];
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      float4 v = ld4(probs + off + (long long)c * HW);
+      p[c][0] = v.x; p[c][1] = v.y; p[c][2] = v.z; p[c][3] = v.w;
+      if (gprobs) {
+        float4 w = ld4(gprobs + off + (long long)c * HW);
+        g[c][0] = w.x; g[c][1] = w.y; g[c][2] = w.z; g[c][3] = w.w;
+      } else {
+        g[c][0] = g[c][1] = g[c][2] = g[c][3] = 0.f;
+      }
+    }
+    int lab[4] = {ignore_index, ignore_index, ignore_index, ignore_index};
+    if (cew != 0.f) {
+      uchar4 l4 = *reinterpret_cast<const uchar4*>(label + n * (long long)HW + r * 4);
+      lab[0] = l4.x; lab[1] = l4.y; lab[2] = l4.z; lab[3] = l4.w;
+    }
+    float d[C4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C4; ++c) dot += g[c][j] * p[c][j];
+      const bool on = (lab[j] != ignore_index) && (lab[j] < C4);
+#pragma unroll
+      for (int c = 0; c < C4; ++c) {
+        float v = gsc * p[c][j] * (g[c][j] - dot);
+        if (on) v += cew * (p[c][j] - (lab[j] == c ? 1.f : 0.f));
+        d[c][j] = v;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C4; ++c) st4(dlogits + off + (long long)c * HW, make_float4(d[c][0], d[c][1], d[c][2], d[c][3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: Gated CRF (utils/gate_crf_loss.py:20-117 for kernels_desc=[{weight,xy,rgb}], no masks, Potts).
+//   k_ij = w * exp(-0.5*(|dxy|^2/sxy^2 + (I_i-I_j)^2/srgb^2)),  j in the (2R+1)^2 window, j != i
+//   s_i  = sum_j k_ij y_j                (in-bounds j only: unfold zero-pads y, :89,:188)
+//   loss = (sum_ij k_ij - sum_i <s_i, y_i>) / (N*H*W)                              (:63,:97-99,:116)
+//   dL/dy_i = -2 s_i / (N*H*W)           (k symmetric; OOB terms carry no gradient)
+// Out-of-bounds neighbours: features are zero padded (:188), so k_i,oob = w*exp(-0.5*(x_i^2+y_i^2)/sxy^2
+// - 0.5*I_i^2/srgb^2) independent of the offset; it is added analytically (count * value) to sum k (F10).
+// Nothing is materialised: 20 B/pixel read (y, I) + 16 B/pixel written (grad) = 36 B/pixel.
+// Thread layout: lane = column, each thread owns RT vertically adjacent pixels; a neighbour value read
+// from shared memory is reused for up to 2R+1 of the thread's pixels.
+// ------------------------------------------------------------------------------------------------
+template <int R, int RT, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) gatedcrf_kernel(
+    const float* __restrict__ probs, const float* __restrict__ image, float* __restrict__ gprobs,
+    int N, int H, int W, float inv2sxy2 /*0.5/sxy^2*/, float inv2srgb2, float weight, float gscale /* -2*w/denom */,
+    int tiles_x, int tiles_y, float* partials, unsigned* ticket, float* out, float inv_denom) {
+  constexpr int D = 2 * R + 1;
+  constexpr int TW = 32, TH = RT * WARPS;
+  constexpr int HW_ = TW + 2 * R, HH_ = TH + 2 * R;
+  constexpr float LOG2E = 1.4426950408889634f;
+  extern __shared__ float smem[];
+  float* sI = smem;                       // [HH_][HW_]
+  float4* sY = reinterpret_cast<float4*>(smem + ((HH_ * HW_ + 3) & ~3));  // [HH_][HW_]
+  __shared__ float s_lw[D * D];           // log2 of spatial weight (incl. kernel weight) per offset
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    int dy = i / D - R, dx = i % D - R;
+    s_lw[i] = (dy == 0 && dx == 0) ? -INFINITY : (-(float)(dx * dx + dy * dy) * inv2sxy2) * LOG2E + log2f(weight);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float cI = -inv2srgb2 * LOG2E;
+  float acc[2] = {0.f, 0.f};  // sum k, sum <s,y>
+  const long long HW = (long long)H * W;
+  const int ntiles = N * tiles_x * tiles_y;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int tr = tile - n * tiles_x * tiles_y;
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < HH_ * HW_; i += blockDim.x) {
+      const int hy = i / HW_, hx = i - hy * HW_;
+      const int gy = y0 + hy - R, gx = x0 + hx - R;
+      float iv = INFINITY;                 // (I_i - inf)^2 * c = -inf -> exp2 = 0 : OOB excluded from the loop
+      float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const long long o = (long long)gy * W + gx;
+        iv = image[n * HW + o];
+        const float* pp = probs + n * C4 * HW + o;
+        yv = make_float4(pp[0], pp[HW], pp[2 * HW], pp[3 * HW]);
+      }
+      sI[i] = iv;
+      sY[i] = yv;
+    }
+    __syncthreads();
+    const int ly0 = warp * RT;            // first owned row (tile-local)
+    float Ic[RT];
+    float4 s[RT];
+    float ks[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      Ic[i] = sI[(ly0 + i + R) * HW_ + lane + R];
+      Ic[i] = isinf(Ic[i]) ? 0.f : Ic[i];  // own pixel OOB (ragged tile): results discarded below
+      s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ks[i] = 0.f;
+    }
+#pragma unroll 1
+    for (int dxi = 0; dxi < D; ++dxi) {
+#pragma unroll
+      for (int jr = 0; jr < RT + 2 * R; ++jr) {
+        const int idx = (ly0 + jr) * HW_ + lane + dxi;
+        const float Ij = sI[idx];
+        const float4 yj = sY[idx];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          const int dyi = jr - i;            // = dy + R, compile-time after unrolling
+          if (dyi >= 0 && dyi < D) {
+            const float d = Ij - Ic[i];
+            const float k = ex2_approx(fmaf(d * d, cI, s_lw[dyi * D + dxi]));
+            ks[i] += k;
+            s[i].x = fmaf(k, yj.x, s[i].x);
+            s[i].y = fmaf(k, yj.y, s[i].y);
+            s[i].z = fmaf(k, yj.z, s[i].z);
+            s[i].w = fmaf(k, yj.w, s[i].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const int gy = y0 + ly0 + i, gx = x0 + lane;
+      if (gy < H && gx < W) {
+        const float4 yc = sY[(ly0 + i + R) * HW_ + lane + R];
+        // analytic OOB part of sum k (F10)
+        const int nx = min(gx + R, W - 1) - max(gx - R, 0) + 1;
+        const int ny = min(gy + R, H - 1) - max(gy - R, 0) + 1;
+        const int noob = D * D - nx * ny;
+        float kk = ks[i];
+        if (noob > 0) {
+          const float e = -((float)gx * gx + (float)gy * gy) * inv2sxy2 - Ic[i] * Ic[i] * inv2srgb2;
+          kk += (float)noob * weight * expf(e);
+        }
+        acc[0] += kk;
+        acc[1] += s[i].x * yc.x + s[i].y * yc.y + s[i].z * yc.z + s[i].w * yc.w;
+        if (gprobs) {
+          float* gp = gprobs + n * C4 * HW + (long long)gy * W + gx;
+          gp[0] = gscale * s[i].x; gp[HW] = gscale * s[i].y; gp[2 * HW] = gscale * s[i].z; gp[3 * HW] = gscale * s[i].w;
+        }
+      }
+    }
+  }
+  __shared__ double res[2];
+  if (block_reduce_final<2, 32 * WARPS>(acc, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      out[0] = (float)((res[0] - res[1]) * (double)inv_denom);
+      out[1] = (float)res[0];   // kernels.sum() (for diagnostics / tests)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: Mumford-Shah as written in the reference (utils/losses.py:275-309, image <-> prediction roles
+// swapped, F11):  level = sum_{n,k} sum_px (p_k - c_nk)^2 I,  c_nk = sum(p_k I)/sum(I);
+// tv = sum|d_h p| + sum|d_w p|.   Expanded: sum (p-c)^2 I = sum p^2 I - (sum p I)^2 / sum I.
+// grid = (chunks, N); per block 10 partial sums: A_k = sum p_k^2 I, B_k = sum p_k I (k<4), S = sum I, TV.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) ms_fwd_kernel(
+    const float* __restrict__ image, const float* __restrict__ probs, int H, int W,
+    float* partials, unsigned* ticket, float* out /*[1]*/, float* cent /*[N][4]*/, int N) {
+  const int n = blockIdx.y;
+  const long long HW = (long long)H * W;
+  const float* I = image + n * HW;
+  const float* P = probs + n * C4 * HW;
+  float acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < HW; i += (long long)gridDim.x * TPB) {
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    const float iv = I[i];
+    acc[8] += iv;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      const float p = P[c * HW + i];
+      acc[c] += p * p * iv;
+      acc[4 + c] += p * iv;
+      if (y + 1 < H) acc[9] += fabsf(P[c * HW + i + W] - p);
+      if (x + 1 < W) acc[9] += fabsf(P[c * HW + i + 1] - p);
+    }
+  }
+  // block-level partial -> partials[(n*gridDim.x + bx)*10 + k]; last block of the whole grid finalises
+  __shared__ float s_w[TPB / 32][10];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    float r = warp_sum(acc[k]);
+    if (lane == 0) s_w[warp][k] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    float r = 0.f;
+    for (int w = 0; w < TPB / 32; ++w) r += s_w[w][threadIdx.x];
+    partials[((size_t)n * gridDim.x + blockIdx.x) * 10 + threadIdx.x] = r;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // finalize: one warp per sample (strided), fixed order, double accumulation
+  __shared__ double s_loss[TPB / 32];
+  double wl = 0.0;
+  for (int nn = warp; nn < N; nn += TPB / 32) {
+    double a[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a[k] = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) a[k] += (double)__ldcg(&partials[((size_t)nn * gridDim.x + b) * 10 + k]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if (lane == 0) {
+      double l = a[9];
+      for (int c = 0; c < C4; ++c) {
+        const double cen = a[4 + c] / a[8];
+        cent[nn * C4 + c] = (float)cen;
+        l += a[c] - a[4 + c] * cen;
+      }
+      wl += l;
+    }
+  }
+  if (lane == 0) s_loss[warp] = wl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) t += s_loss[w];
+    out[0] = (float)t;
+    *ticket = 0u;
+  }
+}
+
+// d/dp_k = 2 (p_k - c_nk) I   (the centroid's own derivative cancels: sum (p-c) I = 0)
+//        + sign(p - p_up) - sign(p_down - p) + sign(p - p_left) - sign(p_right - p)
+__global__ void __launch_bounds__(TPB) ms_bwd_kernel(
+    const float* __restrict__ image, const float* __restrict__ probs, const float* __restrict__ cent,
+    int N, int H, int W, float scale, int accumulate, float* __restrict__ gprobs) {
+  const long long HW = (long long)H * W, total = (long long)N * C4 * HW;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long nc = i / HW, o = i - nc * HW;
+    const int n = (int)(nc / C4);
+    const int y = (int)(o / W), x = (int)(o - (long long)y * W);
+    const float p = probs[i];
+    float g = 2.f * (p - cent[nc]) * image[n * HW + o];
+    auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
+    if (y > 0) g += sgn(p - probs[i - W]);
+    if (y + 1 < H) g -= sgn(probs[i + W] - p);
+    if (x > 0) g += sgn(p - probs[i - 1]);
+    if (x + 1 < W) g -= sgn(probs[i + 1] - p);
+    g *= scale;
+    gprobs[i] = accumulate ? gprobs[i] + g : g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: dynamically mixed pseudo labels + (partial) Dice.
+//   pseudo = argmax_c(beta*p1 + (1-beta)*p2)   (train_weakly_supervised_segmentation_pCE_ours_proposed.py:117-120)
+//   pDLoss (utils/losses.py:195-232) per class:  1 - (2*I+eps)/(Z+Y+eps),  I = sum s*t*M, Y = sum t*M, Z = sum s^2*M
+//   with M[h,w] = sum_n mask[n,h,w] -- the [N,1,H,W] x [N,H,W] broadcast in the reference (losses.py:209-211,
+//   219-220,229) multiplies every pixel by the batch-summed ignore mask at that location.
+// The rounding of the mix follows torch: two fp32 multiplies and one fp32 add, no FMA contraction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) mix_argmax_kernel(
+    const float* __restrict__ p1, const float* __restrict__ p2, float beta, float omb, int HW, long long npix,
+    uint8_t* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
+    const long long n = i / HW, o = i - n * HW;
+    const float* a = p1 + n * C4 * (long long)HW + o;
+    const float* b = p2 ? p2 + n * C4 * (long long)HW + o : nullptr;
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      float v = b ? __fadd_rn(__fmul_rn(beta, a[(long long)c * HW]), __fmul_rn(omb, b[(long long)c * HW])) : a[(long long)c * HW];
+      if (v > best) { best = v; arg = c; }   // first maximum wins, as torch.argmax
+    }
+    out[i] = (uint8_t)arg;
+  }
+}
+
+// msum[h,w] = number of samples whose target at (h,w) is not ignore_index
+__global__ void __launch_bounds__(TPB) mask_count_kernel(const uint8_t* __restrict__ target, int N, int HW, int ignore_index,
+                                                         float* __restrict__ msum) {
+  for (int o = blockIdx.x * TPB + threadIdx.x; o < HW; o += gridDim.x * TPB) {
+    int c = 0;
+    for (int n = 0; n < N; ++n) c += (target[(long long)n * HW + o] != ignore_index);
+    msum[o] = (float)c;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) pdice_fwd_kernel(
+    const float* __restrict__ probs, const uint8_t* __restrict__ target, const float* __restrict__ msum, float mconst,
+    int HW, long long npix, float* partials, unsigned* ticket, float* out /*[1 + 12]*/) {
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
+    const long long n = i / HW, o = i - n * HW;
+    const float m = msum ? msum[o] : mconst;
+    const int t = target[i];
+    const float* p = probs + n * C4 * (long long)HW + o;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      const float s = p[(long long)c * HW];
+      const float tt = (t == c) ? 1.f : 0.f;
+      acc[c] += s * tt * m;        // I
+      acc[4 + c] += tt * m;        // Y
+      acc[8 + c] += s * s * m;     // Z
+    }
+  }
+  __shared__ double res[12];
+  if (block_reduce_final<12, TPB>(acc, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      double loss = 0.0;
+      for (int c = 0; c < C4; ++c) {
+        loss += 1.0 - (2.0 * res[c] + 1e-5) / (res[8 + c] + res[4 + c] + 1e-5);
+        out[1 + c] = (float)res[c]; out[5 + c] = (float)res[4 + c]; out[9 + c] = (float)res[8 + c];
+      }
+      out[0] = (float)(loss / C4);
+    }
+  }
+}
+
+// d loss / d s_c(px) = -(1/C) * [ 2 t M (Z+Y+eps) - (2I+eps) 2 s M ] / (Z+Y+eps)^2
+__global__ void __launch_bounds__(TPB) pdice_bwd_kernel(
+    const float* __restrict__ probs, const uint8_t* __restrict__ target, const float* __restrict__ msum, float mconst,
+    const float* __restrict__ sums /*out of fwd: [1+12]*/, int HW, long long npix, float scale, int accumulate,
+    float* __restrict__ gprobs) {
+  float a[C4], b[C4];
+#pragma unroll
+  for (int c = 0; c < C4; ++c) {
+    const double den = (double)sums[9 + c] + (double)sums[5 + c] + 1e-5;
+    const double num = 2.0 * (double)sums[1 + c] + 1e-5;
+    a[c] = (float)(-(double)scale / C4 * 2.0 / den);          // coefficient of t*M
+    b[c] = (float)((double)scale / C4 * 2.0 * num / (den * den));  // coefficient of s*M
+  }
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
+    const long long n = i / HW, o = i - n * HW;
+    const float m = msum ? msum[o] : mconst;
+    const int t = target[i];
+    const long long base = n * C4 * (long long)HW + o;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      const float s = probs[base + (long long)c * HW];
+      const float g = (a[c] * ((t == c) ? 1.f : 0.f) + b[c] * s) * m;
+      float* gp = gprobs + base + (long long)c * HW;
+      *gp = accumulate ? *gp + g : g;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11: TV / contour-length loss (train_weakly_supervised_pCE_TV_2D.py:58-65):
+//   mn = minpool3(p), contour = relu(maxpool3(mn) - mn), loss = mean(contour); pools see only in-bounds
+//   pixels (max_pool2d pads with -inf).  Backward routes like autograd: +g to the argmin of the window
+//   that attains the max, -g to the argmin of the centre window (first extremum in row-major scan order).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float minpool_at(const float* P, int H, int W, int y, int x, int* arg) {
+  float best = INFINITY;
+  int a = -1;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      float v = P[yy * W + xx];
+      if (a < 0 || v < best) { best = v; a = yy * W + xx; }
+    }
+  if (arg) *arg = a;
+  return best;
+}
+
+__global__ void __launch_bounds__(TPB) tv_kernel(
+    const float* __restrict__ probs, int planes, int H, int W, float gscale /*go/numel*/, float* __restrict__ gprobs,
+    float* partials, unsigned* ticket, float* out) {
+  const long long HW = (long long)H * W, total = (long long)planes * HW;
+  float acc[1] = {0.f};
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long pl = i / HW;
+    const int o = (int)(i - pl * HW), y = o / W, x = o - y * W;
+    const float* P = probs + pl * HW;
+    int argc;
+    const float mc = minpool_at(P, H, W, y, x, &argc);
+    float mx = -INFINITY;
+    int argm = -1, argmx = -1;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        int a;
+        float v = minpool_at(P, H, W, yy, xx, &a);
+        if (v > mx || argmx < 0) { mx = v; argm = a; argmx = yy * W + xx; }
+      }
+    const float c = mx - mc;
+    if (c > 0.f) {
+      acc[0] += c;
+      if (gprobs) {
+        atomicAdd(gprobs + pl * HW + argm, gscale);
+        atomicAdd(gprobs + pl * HW + argc, -gscale);
+      }
+    }
+  }
+  __shared__ double res[1];
+  if (block_reduce_final<1, TPB>(acc, partials, ticket, res)) {
+    if (threadIdx.x == 0) out[0] = (float)(res[0] / (double)total);
+  }
+}
+
+inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;   // multiple of the SM count; grid-stride loops cover the rest
+  return (int)b;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+WSL_API int wsl_softmax_pce_fwd(const float* logits, const uint8_t* label, float* probs, int N, int C, int H, int W,
+                                int ignore_index, float* out2, float* ws, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_softmax_pce_fwd: C must be 4 (got %d)", C);
+  WSL_REQUIRE(((long long)H * W) % 4 == 0, "wsl_softmax_pce_fwd: H*W must be a multiple of 4");
+  const long long nq = (long long)N * H * W / 4;
+  const int grid = grid_for(nq, TPB);
+  softmax_pce_fwd_kernel<<<grid, TPB, 0, stream>>>(logits, label, probs, H * W, nq, ignore_index, ws + 64,
+                                                   reinterpret_cast<unsigned*>(ws), out2);
+  return wsl_check_launch("softmax_pce_fwd");
+}
+
+WSL_API int wsl_head_bwd(const float* probs, const uint8_t* label, const float* ce_stats, const float* grad_out,
+                         float w_ce, const float* gprobs, float gprobs_scale, int N, int C, int H, int W,
+                         int ignore_index, float* dlogits, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_head_bwd: C must be 4 (got %d)", C);
+  WSL_REQUIRE(((long long)H * W) % 4 == 0, "wsl_head_bwd: H*W must be a multiple of 4");
+  const long long nq = (long long)N * H * W / 4;
+  head_bwd_kernel<<<grid_for(nq, TPB), TPB, 0, stream>>>(probs, label, ce_stats, grad_out, w_ce, gprobs, gprobs_scale,
+                                                         H * W, nq, ignore_index, dlogits);
+  return wsl_check_launch("head_bwd");
+}
+
+WSL_API int wsl_gatedcrf_fwd(const float* probs, const float* image, float* gprobs, int N, int C, int H, int W,
+                             int radius, float sigma_xy, float sigma_rgb, float weight, float* out2, float* ws,
+                             cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_gatedcrf_fwd: C must be 4 (got %d)", C);
+  WSL_REQUIRE(radius == 5, "wsl_gatedcrf_fwd: fused path is compiled for radius 5 (got %d)", radius);
+  constexpr int R = 5, RT = 8, WARPS = 4;
+  constexpr int TW = 32, TH = RT * WARPS;
+  const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
+  const long long ntiles = (long long)N * tx * ty;
+  int grid = (int)(ntiles < WSL_MAX_PARTIAL_BLOCKS ? ntiles : 148 * 12);
+  const size_t smem = (((TH + 2 * R) * (TW + 2 * R) + 3) & ~3) * sizeof(float) + (size_t)(TH + 2 * R) * (TW + 2 * R) * sizeof(float4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gatedcrf_kernel<R, RT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const double denom = (double)N * H * W;
+  gatedcrf_kernel<R, RT, WARPS><<<grid, 32 * WARPS, smem, stream>>>(
+      probs, image, gprobs, N, H, W, 0.5f / (sigma_xy * sigma_xy), 0.5f / (sigma_rgb * sigma_rgb), weight,
+      (float)(-2.0 / denom), tx, ty, ws + 64, reinterpret_cast<unsigned*>(ws), out2, (float)(1.0 / denom));
+  return wsl_check_launch("gatedcrf_fwd");
+}
+
+WSL_API int wsl_mumford_shah_fwd(const float* image, const float* probs, int N, int C, int H, int W, float* out1,
+                                 float* centroids, float* ws, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_mumford_shah_fwd: C must be 4 (got %d)", C);
+  int chunks = (int)(((long long)H * W + TPB * 4 - 1) / (TPB * 4));
+  if (chunks > 64) chunks = 64;
+  WSL_REQUIRE((long long)chunks * N * 10 <= (long long)WSL_MAX_PARTIAL_BLOCKS * 32, "wsl_mumford_shah_fwd: batch too large for workspace");
+  ms_fwd_kernel<<<dim3(chunks, N), TPB, 0, stream>>>(image, probs, H, W, ws + 64, reinterpret_cast<unsigned*>(ws), out1,
+                                                     centroids, N);
+  return wsl_check_launch("mumford_shah_fwd");
+}
+
+WSL_API int wsl_mumford_shah_bwd(const float* image, const float* probs, const float* centroids, int N, int C, int H,
+                                 int W, float scale, int accumulate, float* gprobs, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_mumford_shah_bwd: C must be 4 (got %d)", C);
+  ms_bwd_kernel<<<grid_for((long long)N * C * H * W, TPB), TPB, 0, stream>>>(image, probs, centroids, N, H, W, scale,
+                                                                             accumulate, gprobs);
+  return wsl_check_launch("mumford_shah_bwd");
+}
+
+WSL_API int wsl_mix_argmax(const float* p1, const float* p2, float beta, float one_minus_beta, int N, int C, int H, int W,
+                           uint8_t* out, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_mix_argmax: C must be 4 (got %d)", C);
+  const long long npix = (long long)N * H * W;
+  mix_argmax_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(p1, p2, beta, one_minus_beta, H * W, npix, out);
+  return wsl_check_launch("mix_argmax");
+}
+
+WSL_API int wsl_mask_count(const uint8_t* target, int N, int H, int W, int ignore_index, float* msum, cudaStream_t stream) {
+  mask_count_kernel<<<grid_for((long long)H * W, TPB), TPB, 0, stream>>>(target, N, H * W, ignore_index, msum);
+  return wsl_check_launch("mask_count");
+}
+
+WSL_API int wsl_pdice_fwd(const float* probs, const uint8_t* target, const float* msum, float mconst, int N, int C, int H,
+                          int W, float* out13, float* ws, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_pdice_fwd: C must be 4 (got %d)", C);
+  const long long npix = (long long)N * H * W;
+  pdice_fwd_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(probs, target, msum, mconst, H * W, npix, ws + 64,
+                                                            reinterpret_cast<unsigned*>(ws), out13);
+  return wsl_check_launch("pdice_fwd");
+}
+
+WSL_API int wsl_pdice_bwd(const float* probs, const uint8_t* target, const float* msum, float mconst, const float* sums13,
+                          int N, int C, int H, int W, float scale, int accumulate, float* gprobs, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_pdice_bwd: C must be 4 (got %d)", C);
+  const long long npix = (long long)N * H * W;
+  pdice_bwd_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(probs, target, msum, mconst, sums13, H * W, npix, scale,
+                                                            accumulate, gprobs);
+  return wsl_check_launch("pdice_bwd");
+}
+
+WSL_API int wsl_tv_loss(const float* probs, int planes, int H, int W, float grad_scale, float* gprobs_zeroed, float* out1,
+                        float* ws, cudaStream_t stream) {
+  const long long total = (long long)planes * H * W;
+  tv_kernel<<<grid_for(total, TPB), TPB, 0, stream>>>(probs, planes, H, W, grad_scale / (float)total, gprobs_zeroed,
+                                                      ws + 64, reinterpret_cast<unsigned*>(ws), out1);
+  return wsl_check_launch("tv_loss");
+}

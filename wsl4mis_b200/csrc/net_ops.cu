@@ -1,0 +1,806 @@
+// Network operators for the U-Net hot path on channels-last (NHWC) bf16 activations:
+//   * direct (CUDA-core) convolution forward / data-gradient / weight-gradient -- used for the layers that do
+//     not map to tcgen05 tiles (Cin = 1, tiny problems) and as the on-device cross-check of conv_tc.cu;
+//   * training-mode BatchNorm statistics, normalise + LeakyReLU + dropout (+ fused 2x2 max-pool), and the
+//     matching backward (reference: networks/unet.py:18-26,38);
+//   * bilinear x2 upsample (align_corners=True, networks/unet.py:56-57) forward / backward;
+//   * channel dropout of the aux branch (networks/unet.py:254-256,344);
+//   * weight packing, fused SGD (train_weakly_supervised_pCE_2D.py:79-80,104).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr float BN_EPS_DEFAULT = 1e-5f;
+
+// ================================================================================================
+// direct convolution (forward and, with flipped/transposed packed weights, data gradient)
+// ================================================================================================
+// Source: up to two channels-last tensors concatenated along C (torch.cat([x2, x1], 1), unet.py:67) or one
+// fp32 single-channel image.  Weights: fp32 [taps][CinP][CoutP] (CinP, CoutP multiples of 16, zero padded).
+// CTA = 16x16 pixels x 16 output channels, 128 threads, each thread 2 pixels (rows py, py+8) x 16 channels.
+template <int KS>
+__global__ void __launch_bounds__(128) conv_direct_kernel(
+    const void* __restrict__ src0, int C0, const void* __restrict__ src1, int C1, int src_f32,
+    const float* __restrict__ wpk, const float* __restrict__ bias, void* __restrict__ out, int out_mode,
+    int N, int H, int W, int CinP, int CoutP, int CoutStore, int tiles_x, int tiles_y) {
+  constexpr int PAD = KS / 2, HT = 16 + 2 * PAD, TAPS = KS * KS;
+  __shared__ float s_in[16][HT][HT + 1];
+  __shared__ __align__(16) float s_w[TAPS][16][16];
+  const int tile = blockIdx.x;
+  const int n = tile / (tiles_x * tiles_y);
+  const int tr = tile - n * tiles_x * tiles_y;
+  const int y0 = (tr / tiles_x) * 16, x0 = (tr % tiles_x) * 16;
+  const int cob = blockIdx.y * 16;
+  const int px = threadIdx.x & 15, py = threadIdx.x >> 4;
+  float acc[2][16];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
+  const int Cin = C0 + C1;
+  for (int c0 = 0; c0 < CinP; c0 += 16) {
+    __syncthreads();
+    // ---- input halo tile -> smem (fp32, channel-planar) ----
+    for (int i = threadIdx.x; i < HT * HT * 2; i += 128) {
+      const int half = i & 1, p = i >> 1;
+      const int hy = p / HT, hx = p - hy * HT;
+      const int gy = y0 + hy - PAD, gx = x0 + hx - PAD;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const long long pix = ((long long)n * H + gy) * W + gx;
+        const int c = c0 + half * 8;
+        if (src_f32) {
+          if (c < Cin) {
+            const float* s = reinterpret_cast<const float*>(src0) + pix * C0 + c;
+            for (int j = 0; j < 8 && c + j < Cin; ++j) v[j] = s[j];
+          }
+        } else if (c < C0) {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src0) + pix * C0 + c), v);
+        } else if (c < Cin) {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src1) + pix * C1 + (c - C0)), v);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_in[half * 8 + j][hy][hx] = v[j];
+    }
+    // ---- weights chunk -> smem ----
+    for (int i = threadIdx.x; i < TAPS * 16 * 16; i += 128) {
+      const int co = i & 15, ci = (i >> 4) & 15, t = i >> 8;
+      s_w[t][ci][co] = wpk[((size_t)t * CinP + c0 + ci) * CoutP + cob + co];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < 16; ++ci) {
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) {
+        const int dy = t / KS, dx = t % KS;
+        const float a0 = s_in[ci][py + dy][px + dx];
+        const float a1 = s_in[ci][py + 8 + dy][px + dx];
+        const float4* wv = reinterpret_cast<const float4*>(&s_w[t][ci][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = wv[q];
+          acc[0][q * 4 + 0] = fmaf(a0, w.x, acc[0][q * 4 + 0]); acc[1][q * 4 + 0] = fmaf(a1, w.x, acc[1][q * 4 + 0]);
+          acc[0][q * 4 + 1] = fmaf(a0, w.y, acc[0][q * 4 + 1]); acc[1][q * 4 + 1] = fmaf(a1, w.y, acc[1][q * 4 + 1]);
+          acc[0][q * 4 + 2] = fmaf(a0, w.z, acc[0][q * 4 + 2]); acc[1][q * 4 + 2] = fmaf(a1, w.z, acc[1][q * 4 + 2]);
+          acc[0][q * 4 + 3] = fmaf(a0, w.w, acc[0][q * 4 + 3]); acc[1][q * 4 + 3] = fmaf(a1, w.w, acc[1][q * 4 + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int gy = y0 + py + r * 8, gx = x0 + px;
+    if (gy >= H || gx >= W) continue;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = acc[r][c] + (bias ? bias[cob + c] : 0.f);
+    if (out_mode == 0) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (((long long)n * H + gy) * W + gx) * CoutStore + cob;
+      float lo[8], hi[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi[c] = v[8 + c]; }
+      if (cob + 8 <= CoutStore) reinterpret_cast<uint4*>(o)[0] = pack8(lo);
+      if (cob + 16 <= CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+    } else {  // fp32 NCHW with CoutStore real channels
+      float* o = reinterpret_cast<float*>(out);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (cob + c < CoutStore) o[(((long long)n * CoutStore + cob + c) * H + gy) * W + gx] = v[c];
+    }
+  }
+}
+
+// ================================================================================================
+// direct weight gradient:  dW[co][ci][dy][dx] = sum_{n,y,x} dY[n,y,x,co] * X[n,y+dy-P,x+dx-P,ci]
+// CTA = 16 co x 16 ci x all taps, 256 threads (co = t%16, ci = t/16); loops over 8x16 pixel tiles of its split,
+// accumulates in registers, then atomically adds into the (pre-zeroed) fp32 torch-layout gradient.
+// ================================================================================================
+template <int KS>
+__global__ void __launch_bounds__(256) wgrad_direct_kernel(
+    const void* __restrict__ src0, int C0, const void* __restrict__ src1, int C1, int src_f32,
+    const __nv_bfloat16* __restrict__ dy, int CoutP, float* __restrict__ dw, float* __restrict__ dbias,
+    int N, int H, int W, int CoutReal, int tiles_x, int tiles_y) {
+  constexpr int PAD = KS / 2, TH = 8, TW = 16, HH = TH + 2 * PAD, HWD = TW + 2 * PAD, TAPS = KS * KS;
+  __shared__ float s_g[TH * TW][16];
+  __shared__ float s_x[HH * HWD][17];
+  const int Cin = C0 + C1;
+  const int ci_blocks = (Cin + 15) / 16;
+  const int cob = (blockIdx.x / ci_blocks) * 16, cib = (blockIdx.x % ci_blocks) * 16;
+  const int co = threadIdx.x & 15, ci = threadIdx.x >> 4;
+  float acc[TAPS];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
+  float bsum = 0.f;
+  const int ntiles = N * tiles_x * tiles_y;
+  for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int tr = tile - n * tiles_x * tiles_y;
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+    __syncthreads();
+    {  // dY tile: 128 px x 16 co, one 16-byte vector per thread
+      const int p = threadIdx.x >> 1, half = threadIdx.x & 1;
+      const int gy = y0 + p / TW, gx = x0 + p % TW;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (gy < H && gx < W)
+        unpack8(*reinterpret_cast<const uint4*>(dy + (((long long)n * H + gy) * W + gx) * CoutP + cob + half * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_g[p][half * 8 + j] = v[j];
+    }
+    for (int i = threadIdx.x; i < HH * HWD * 2; i += 256) {
+      const int half = i & 1, p = i >> 1;
+      const int hy = p / HWD, hx = p - hy * HWD;
+      const int gy = y0 + hy - PAD, gx = x0 + hx - PAD;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const long long pix = ((long long)n * H + gy) * W + gx;
+        const int c = cib + half * 8;
+        if (src_f32) {
+          if (c < Cin) {
+            const float* s = reinterpret_cast<const float*>(src0) + pix * C0 + c;
+            for (int j = 0; j < 8 && c + j < Cin; ++j) v[j] = s[j];
+          }
+        } else if (c < C0) {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src0) + pix * C0 + c), v);
+        } else if (c < Cin) {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src1) + pix * C1 + (c - C0)), v);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_x[p][half * 8 + j] = v[j];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = 0; p < TH * TW; ++p) {
+      const float g = s_g[p][co];
+      const int py = p / TW, pxx = p % TW;
+      bsum += g;
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) acc[t] = fmaf(g, s_x[(py + t / KS) * HWD + pxx + t % KS][ci], acc[t]);
+    }
+  }
+  if (cob + co < CoutReal && cib + ci < Cin) {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) atomicAdd(dw + ((size_t)(cob + co) * Cin + cib + ci) * TAPS + t, acc[t]);
+  }
+  if (dbias != nullptr && cib == 0 && ci == 0 && cob + co < CoutReal) atomicAdd(dbias + cob + co, bsum);
+}
+
+// ================================================================================================
+// BatchNorm (training): per-channel statistics over N*H*W of a channels-last bf16 tensor
+// ================================================================================================
+// thread (row r = t / cg, group g = t % cg) owns 8 channels; rows stride over pixels.
+// Partials [block][2][C]; the last block finalises in fixed order (deterministic):
+//   save[0:C] = mean, save[C:2C] = invstd; ss[0:C] = gamma*invstd, ss[C:2C] = beta - mean*scale;
+//   running_mean/var updated with momentum (unbiased variance), num_batches_tracked += 1.
+__global__ void __launch_bounds__(TPB) bn_stats_kernel(
+    const __nv_bfloat16* __restrict__ y, long long P, int C, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt, float momentum,
+    float eps, float* __restrict__ save, float* __restrict__ ss, float* partials, unsigned* ticket) {
+  extern __shared__ float s_red[];  // [TPB][16]
+  const int cg = C >> 3, rows = TPB / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  if (r < rows) {
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + p * C + g * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = sum[j]; s_red[threadIdx.x * 16 + 8 + j] = sq[j]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    const int gg = c >> 3, j = c & 7;
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; ++rr) { a += s_red[(rr * cg + gg) * 16 + j]; b += s_red[(rr * cg + gg) * 16 + 8 + j]; }
+    partials[((size_t)blockIdx.x * 2 + 0) * C + c] = a;
+    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = b;
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    double a = 0.0, b = 0.0;
+    for (int bl = 0; bl < (int)gridDim.x; ++bl) {
+      a += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
+      b += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
+    }
+    const double mean = a / (double)P;
+    double var = b / (double)P - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    save[c] = (float)mean;
+    save[C + c] = invstd;
+    const float sc = gamma[c] * invstd;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - (float)mean * sc;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      const double unb = (P > 1) ? var * (double)P / (double)(P - 1) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (nbt) *nbt += 1;
+    *ticket = 0u;
+  }
+}
+
+// eval mode: scale/shift from running statistics
+__global__ void bn_eval_prepare_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                       float eps, int C, float* ss) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+    ss[c] = sc;
+    ss[C + c] = beta[c] - rm[c] * sc;
+  }
+}
+
+// A = dropout(leaky_relu(y*scale + shift)); optional fused 2x2 max-pool of A (DownBlock, unet.py:38).
+// mask: optional uint8 keep-mask (tests / parity); otherwise counter-based RNG keyed on (seed, element index).
+__device__ __forceinline__ void bn_act8(const uint4& raw, const float* __restrict__ ss, int C, int c0, float slope,
+                                        float drop_p, float inv_keep, const uint8_t* mask, unsigned long long seed,
+                                        long long eidx, float (&o)[8]) {
+  float v[8];
+  unpack8(raw, v);
+  uint2 mk = make_uint2(0x01010101u, 0x01010101u);
+  if (drop_p > 0.f && mask) mk = *reinterpret_cast<const uint2*>(mask + eidx);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float z = fmaf(v[j], ss[c0 + j], ss[C + c0 + j]);
+    z = z > 0.f ? z : z * slope;
+    if (drop_p > 0.f) {
+      bool keep;
+      if (mask) keep = ((j < 4 ? (mk.x >> (8 * j)) : (mk.y >> (8 * (j - 4)))) & 0xffu) != 0;
+      else keep = wsl_uniform(seed, (unsigned long long)(eidx + j)) >= drop_p;
+      z = keep ? z * inv_keep : 0.f;
+    }
+    o[j] = z;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
+    const __nv_bfloat16* __restrict__ y, const float* __restrict__ ss, int N, int H, int W, int C, float slope,
+    float drop_p, const uint8_t* __restrict__ mask, unsigned long long seed, const unsigned long long* seed_ptr,
+    __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ pooled, uint8_t* __restrict__ pool_idx) {
+  const int cg = C >> 3;
+  if (seed_ptr) seed += *seed_ptr;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (pooled == nullptr) {
+    const long long total = (long long)N * H * W * cg;
+    for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+      const long long p = i / cg;
+      const int c0 = (int)(i - p * cg) * 8;
+      float o[8];
+      bn_act8(*reinterpret_cast<const uint4*>(y + p * C + c0), ss, C, c0, slope, drop_p, inv_keep, mask, seed, p * C + c0, o);
+      *reinterpret_cast<uint4*>(act + p * C + c0) = pack8(o);
+    }
+  } else {
+    const int Hp = H >> 1, Wp = W >> 1;
+    const long long total = (long long)N * Hp * Wp * cg;
+    for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+      const long long q = i / cg;
+      const int c0 = (int)(i - q * cg) * 8;
+      const int xp = (int)(q % Wp), yp = (int)((q / Wp) % Hp);
+      const long long n = q / ((long long)Wp * Hp);
+      float best[8];
+      int arg[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long p = (n * H + yp * 2 + (k >> 1)) * W + xp * 2 + (k & 1);
+        float o[8];
+        bn_act8(*reinterpret_cast<const uint4*>(y + p * C + c0), ss, C, c0, slope, drop_p, inv_keep, mask, seed, p * C + c0, o);
+        const uint4 pk = pack8(o);
+        *reinterpret_cast<uint4*>(act + p * C + c0) = pk;
+        float ob[8];
+        unpack8(pk, ob);  // pool over the stored (bf16-rounded) activations
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (k == 0 || ob[j] > best[j]) { best[j] = ob[j]; arg[j] = k; }  // first maximum wins (torch)
+      }
+      *reinterpret_cast<uint4*>(pooled + q * C + c0) = pack8(best);
+      uint2 ai;
+      ai.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      ai.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(pool_idx + q * C + c0) = ai;
+    }
+  }
+}
+
+// ---- BatchNorm backward -------------------------------------------------------------------------
+// dA(p,c) = g0[p,c] + cs1[n,c]*g1[p,c] + (pool_idx[q,c]==k ? gp[q,c] : 0)         (any of the three may be absent)
+// dz      = dA * dropout_factor * leaky'(z),   z = y*scale+shift,  xhat = (y-mean)*invstd
+// reduce : sum dz, sum dz*xhat  -> dbeta, dgamma, c1 = sum dz / P, c2 = sum dz*xhat / P
+// apply  : dY = scale * (dz - c1 - xhat*c2)
+struct BnBwdArgs {
+  const __nv_bfloat16* y;
+  const float* ss;     // scale, shift
+  const float* save;   // mean, invstd
+  const __nv_bfloat16* g0;
+  const __nv_bfloat16* g1;
+  const float* cs1;    // [N][C] channel scale for g1 (nullable -> 1)
+  const __nv_bfloat16* gp;
+  const uint8_t* pool_idx;
+  const uint8_t* mask;
+  unsigned long long seed;
+  const unsigned long long* seed_ptr;
+  float drop_p, slope;
+  int N, H, W, C;
+};
+
+__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, long long p, int c0, float (&dz)[8], float (&xh)[8]) {
+  float yv[8], g[8];
+  unpack8(*reinterpret_cast<const uint4*>(a.y + p * a.C + c0), yv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  const int x = (int)(p % a.W), yy = (int)((p / a.W) % a.H);
+  const long long n = p / ((long long)a.W * a.H);
+  if (a.g0) {
+    float t[8];
+    unpack8(*reinterpret_cast<const uint4*>(a.g0 + p * a.C + c0), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += t[j];
+  }
+  if (a.g1) {
+    float t[8];
+    unpack8(*reinterpret_cast<const uint4*>(a.g1 + p * a.C + c0), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += t[j] * (a.cs1 ? a.cs1[n * a.C + c0 + j] : 1.f);
+  }
+  if (a.gp) {
+    const long long q = (n * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (x >> 1);
+    const int k = ((yy & 1) << 1) | (x & 1);
+    const uint2 ai = *reinterpret_cast<const uint2*>(a.pool_idx + q * a.C + c0);
+    float t[8];
+    unpack8(*reinterpret_cast<const uint4*>(a.gp + q * a.C + c0), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int aj = (j < 4 ? (ai.x >> (8 * j)) : (ai.y >> (8 * (j - 4)))) & 0xff;
+      if (aj == k) g[j] += t[j];
+    }
+  }
+  const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  uint2 mk = make_uint2(0x01010101u, 0x01010101u);
+  if (a.drop_p > 0.f && a.mask) mk = *reinterpret_cast<const uint2*>(a.mask + p * a.C + c0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z = fmaf(yv[j], a.ss[c0 + j], a.ss[a.C + c0 + j]);
+    float d = g[j] * (z > 0.f ? 1.f : a.slope);
+    if (a.drop_p > 0.f) {
+      bool keep;
+      if (a.mask) keep = ((j < 4 ? (mk.x >> (8 * j)) : (mk.y >> (8 * (j - 4)))) & 0xffu) != 0;
+      else keep = wsl_uniform(a.seed, (unsigned long long)(p * a.C + c0 + j)) >= a.drop_p;
+      d = keep ? d * inv_keep : 0.f;
+    }
+    dz[j] = d;
+    xh[j] = (yv[j] - a.save[c0 + j]) * a.save[a.C + c0 + j];
+  }
+}
+
+__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
+                                                            float* partials, unsigned* ticket) {
+  extern __shared__ float s_red[];
+  if (a.seed_ptr) a.seed += *a.seed_ptr;
+  const int C = a.C, cg = C >> 3, rows = TPB / cg;
+  const long long P = (long long)a.N * a.H * a.W;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (r < rows) {
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+      float dz[8], xh[8];
+      bn_bwd_dz8(a, p, g * 8, dz, xh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], xh[j], s2[j]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    const int gg = c >> 3, j = c & 7;
+    float x = 0.f, y = 0.f;
+    for (int rr = 0; rr < rows; ++rr) { x += s_red[(rr * cg + gg) * 16 + j]; y += s_red[(rr * cg + gg) * 16 + 8 + j]; }
+    partials[((size_t)blockIdx.x * 2 + 0) * C + c] = x;
+    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = y;
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    double x = 0.0, y = 0.0;
+    for (int bl = 0; bl < (int)gridDim.x; ++bl) {
+      x += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
+      y += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
+    }
+    dbeta[c] = (float)x;
+    dgamma[c] = (float)y;
+    coef[c] = (float)(x / (double)P);
+    coef[C + c] = (float)(y / (double)P);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+__global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
+                                                           __nv_bfloat16* __restrict__ dy) {
+  const int C = a.C, cg = C >> 3;
+  if (a.seed_ptr) a.seed += *a.seed_ptr;
+  const long long total = (long long)a.N * a.H * a.W * cg;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long p = i / cg;
+    const int c0 = (int)(i - p * cg) * 8;
+    float dz[8], xh[8], o[8];
+    bn_bwd_dz8(a, p, c0, dz, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a.ss[c0 + j] * (dz[j] - coef[c0 + j] - xh[j] * coef[C + c0 + j]);
+    *reinterpret_cast<uint4*>(dy + p * C + c0) = pack8(o);
+  }
+}
+
+// ================================================================================================
+// bilinear x2 upsample, align_corners=True (nn.Upsample(scale_factor=2, mode='bilinear'), unet.py:56-57)
+// index arithmetic follows ATen's area_pixel_compute_source_index for align_corners: src = dst*(in-1)/(out-1)
+// ================================================================================================
+__device__ __forceinline__ void up_src(int d, int in, int out, int& i0, int& i1, float& lam) {
+  const float r = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const float s = r * (float)d;
+  i0 = (int)s;
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  lam = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ t, int N, int h, int w, int C,
+                                                             __nv_bfloat16* __restrict__ u) {
+  const int cg = C >> 3, H = 2 * h, W = 2 * w;
+  const long long total = (long long)N * H * W * cg;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long p = i / cg;
+    const int c0 = (int)(i - p * cg) * 8;
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const long long n = p / ((long long)W * H);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up_src(y, h, H, y0, y1, ly);
+    up_src(x, w, W, x0, x1, lx);
+    float a[8], b[8], c[8], d[8], o[8];
+    const __nv_bfloat16* base = t + n * (long long)h * w * C + c0;
+    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x0) * C), a);
+    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x1) * C), b);
+    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x0) * C), c);
+    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x1) * C), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+    *reinterpret_cast<uint4*>(u + p * C + c0) = pack8(o);
+  }
+}
+
+// gather form of the transpose: each low-res pixel collects from the <=7x7 high-res pixels that can touch it
+__global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ du, int N, int h, int w, int C,
+                                                             __nv_bfloat16* __restrict__ dt) {
+  const int cg = C >> 3, H = 2 * h, W = 2 * w;
+  const long long total = (long long)N * h * w * cg;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long p = i / cg;
+    const int c0 = (int)(i - p * cg) * 8;
+    const int xi = (int)(p % w), yi = (int)((p / w) % h);
+    const long long n = p / ((long long)w * h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int Y = max(0, 2 * yi - 3); Y <= min(H - 1, 2 * yi + 3); ++Y) {
+      int y0, y1;
+      float ly;
+      up_src(Y, h, H, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == yi) wy += 1.f - ly;
+      if (y1 == yi) wy += ly;
+      if (wy == 0.f) continue;
+      for (int X = max(0, 2 * xi - 3); X <= min(W - 1, 2 * xi + 3); ++X) {
+        int x0, x1;
+        float lx;
+        up_src(X, w, W, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == xi) wx += 1.f - lx;
+        if (x1 == xi) wx += lx;
+        if (wx == 0.f) continue;
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(du + ((n * H + Y) * (long long)W + X) * C + c0), g);
+        const float ww = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, g[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dt + p * C + c0) = pack8(acc);
+  }
+}
+
+// ================================================================================================
+// channel dropout (aux branch), misc elementwise
+// ================================================================================================
+__global__ void chan_mask_gen_kernel(unsigned long long seed, const unsigned long long* seed_ptr, int n, float p, float* cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seed_ptr) seed += *seed_ptr;
+  if (i < n) cs[i] = (wsl_uniform(seed, (unsigned long long)i) >= p) ? 1.f / (1.f - p) : 0.f;
+}
+
+__global__ void __launch_bounds__(TPB) chan_scale_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ cs,
+                                                         long long HW, int C, long long total_vec, __nv_bfloat16* __restrict__ d) {
+  const int cg = C >> 3;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total_vec; i += (long long)gridDim.x * TPB) {
+    const long long p = i / cg;
+    const int c0 = (int)(i - p * cg) * 8;
+    const long long n = p / HW;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + p * C + c0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= cs[n * C + c0 + j];
+    *reinterpret_cast<uint4*>(d + p * C + c0) = pack8(v);
+  }
+}
+
+// fp32 NCHW [N,Creal,H,W] -> bf16 NHWC [N,H,W,CP] (zero padded channels); used for dlogits
+__global__ void __launch_bounds__(TPB) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int Creal, int CP, long long HW,
+                                                                    long long npix, __nv_bfloat16* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
+    const long long n = i / HW, o = i - n * HW;
+    for (int c0 = 0; c0 < CP; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < Creal) ? src[(n * Creal + c0 + j) * HW + o] : 0.f;
+      *reinterpret_cast<uint4*>(dst + i * CP + c0) = pack8(v);
+    }
+  }
+}
+
+// bf16 NHWC -> fp32 NCHW (feature export for tests / API)
+__global__ void __launch_bounds__(TPB) nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int C, long long HW,
+                                                                    long long total, float* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    const long long n = p / HW, o = p - n * HW;
+    dst[(n * C + c) * HW + o] = __bfloat162float(src[i]);
+  }
+}
+
+// ================================================================================================
+// weight packing and SGD
+// ================================================================================================
+// w: fp32 [Cout][Cin][KS][KS] (torch layout).  Outputs (any may be null):
+//   wf  fp32 [T][CinP][CoutP]      forward operand of conv_direct
+//   bf  bf16 [T][CoutP][CinP]      tcgen05 B operand, forward  (K-major: Cin contiguous)
+// and, for the input-channel slice [ci_begin, ci_begin+ci_count) (one slice per concatenated source), SliceP =
+// ci_count rounded up to 16:
+//   wd  fp32 [T][CoutP][SliceP]    dgrad operand of conv_direct (tap flipped, roles swapped)
+//   bd  bf16 [T][SliceP][CoutP]    tcgen05 B operand, dgrad    (K-major: Cout contiguous), tap flipped
+__global__ void __launch_bounds__(TPB) pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int T, int CoutP,
+                                                           int CinP, int ci_begin, int ci_count, float* wf, float* wd,
+                                                           __nv_bfloat16* bf, __nv_bfloat16* bd) {
+  const long long total = (long long)T * CoutP * CinP;
+  const int SliceP = (ci_count + 15) & ~15;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int ci = (int)(i % CinP), co = (int)((i / CinP) % CoutP), t = (int)(i / ((long long)CinP * CoutP));
+    const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * T + t] : 0.f;
+    if (wf) wf[((size_t)t * CinP + ci) * CoutP + co] = v;
+    if (bf) bf[((size_t)t * CoutP + co) * CinP + ci] = __float2bfloat16(v);
+    const int cs = ci - ci_begin;
+    if (cs >= 0 && cs < SliceP) {
+      const float vs = (cs < ci_count) ? v : 0.f;
+      if (wd) wd[((size_t)(T - 1 - t) * CoutP + co) * SliceP + cs] = vs;
+      if (bd) bd[((size_t)(T - 1 - t) * SliceP + cs) * CoutP + co] = __float2bfloat16(vs);
+    }
+  }
+}
+
+// torch.optim.SGD(momentum, weight_decay), dampening 0, no nesterov: g += wd*p; buf = mu*buf + g; p -= lr*buf
+// (zero-initialised buf reproduces torch's first-step "buf = g").
+__global__ void __launch_bounds__(TPB) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                  long long n, const float* lr_ptr, float lr, float mu, float wd) {
+  const float l = lr_ptr ? *lr_ptr : lr;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    const float gg = fmaf(wd, p[i], g[i]);
+    const float b = fmaf(mu, m[i], gg);
+    m[i] = b;
+    p[i] = p[i] - l * b;
+  }
+}
+
+inline int grid_for(long long items) {
+  long long b = (items + TPB - 1) / TPB;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+inline int bn_grid(long long P, int C) {
+  const int rows = TPB / (C / 8);
+  long long b = (P + (long long)rows * 8 - 1) / ((long long)rows * 8);
+  if (b < 1) b = 1;
+  if (b > 296) b = 296;
+  return (int)b;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+WSL_API int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const float* wpk,
+                            const float* bias, void* out, int out_mode, int N, int H, int W, int CinP, int CoutP,
+                            int CoutStore, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_direct: ksize must be 1 or 3");
+  WSL_REQUIRE(CinP % 16 == 0 && CoutP % 16 == 0, "wsl_conv_direct: padded channel counts must be multiples of 16");
+  WSL_REQUIRE(src_f32 || (C0 % 8 == 0 && C1 % 8 == 0), "wsl_conv_direct: bf16 sources need C %% 8 == 0");
+  const int tx = (W + 15) / 16, ty = (H + 15) / 16;
+  dim3 grid(N * tx * ty, CoutP / 16);
+  if (ksize == 3)
+    conv_direct_kernel<3><<<grid, 128, 0, stream>>>(src0, C0, src1, C1, src_f32, wpk, bias, out, out_mode, N, H, W, CinP, CoutP, CoutStore, tx, ty);
+  else
+    conv_direct_kernel<1><<<grid, 128, 0, stream>>>(src0, C0, src1, C1, src_f32, wpk, bias, out, out_mode, N, H, W, CinP, CoutP, CoutStore, tx, ty);
+  return wsl_check_launch("conv_direct");
+}
+
+WSL_API int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int CoutP,
+                             float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_wgrad_direct: ksize must be 1 or 3");
+  WSL_REQUIRE(CoutP % 16 == 0, "wsl_wgrad_direct: CoutP must be a multiple of 16");
+  const int Cin = C0 + C1;
+  const int tx = (W + 15) / 16, ty = (H + 7) / 8;
+  const int ob = (CoutP / 16) * ((Cin + 15) / 16);
+  int splits = (148 * 6 + ob - 1) / ob;
+  const int ntiles = N * tx * ty;
+  if (splits > ntiles) splits = ntiles;
+  if (splits < 1) splits = 1;
+  dim3 grid(ob, splits);
+  if (ksize == 3)
+    wgrad_direct_kernel<3><<<grid, 256, 0, stream>>>(src0, C0, src1, C1, src_f32, (const __nv_bfloat16*)dy, CoutP, dw, dbias, N, H, W, CoutReal, tx, ty);
+  else
+    wgrad_direct_kernel<1><<<grid, 256, 0, stream>>>(src0, C0, src1, C1, src_f32, (const __nv_bfloat16*)dy, CoutP, dw, dbias, N, H, W, CoutReal, tx, ty);
+  return wsl_check_launch("wgrad_direct");
+}
+
+WSL_API int wsl_bn_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
+                         float* ss, float* ws, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0 && C <= 2048 && TPB % (C / 8) == 0, "wsl_bn_stats: unsupported channel count %d", C);
+  const int grid = bn_grid(P, C);
+  WSL_REQUIRE((long long)grid * 2 * C + 64 <= WSL_WS_FLOATS, "wsl_bn_stats: workspace too small");
+  bn_stats_kernel<<<grid, TPB, TPB * 16 * sizeof(float), stream>>>((const __nv_bfloat16*)y, P, C, gamma, beta, running_mean,
+                                                                   running_var, num_batches_tracked, momentum, eps, save, ss,
+                                                                   ws + 64, reinterpret_cast<unsigned*>(ws));
+  return wsl_check_launch("bn_stats");
+}
+
+WSL_API int wsl_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                float eps, int C, float* ss, cudaStream_t stream) {
+  bn_eval_prepare_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C, ss);
+  return wsl_check_launch("bn_eval_prepare");
+}
+
+WSL_API int wsl_bn_act_fwd(const void* y, const float* ss, int N, int H, int W, int C, float slope, float drop_p,
+                           const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr, void* act,
+                           void* pooled, uint8_t* pool_idx, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0, "wsl_bn_act_fwd: C %% 8 != 0");
+  WSL_REQUIRE(pooled == nullptr || (H % 2 == 0 && W % 2 == 0), "wsl_bn_act_fwd: pooling needs even H, W");
+  const long long items = (long long)N * H * W * (C / 8) / (pooled ? 4 : 1);
+  bn_act_fwd_kernel<<<grid_for(items), TPB, 0, stream>>>((const __nv_bfloat16*)y, ss, N, H, W, C, slope, drop_p, mask, seed,
+                                                         seed_ptr, (__nv_bfloat16*)act, (__nv_bfloat16*)pooled, pool_idx);
+  return wsl_check_launch("bn_act_fwd");
+}
+
+WSL_API int wsl_bn_bwd(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+                       const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
+                       const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
+                       cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0 && TPB % (C / 8) == 0, "wsl_bn_bwd: unsupported channel count %d", C);
+  BnBwdArgs a;
+  a.y = (const __nv_bfloat16*)y; a.ss = ss; a.save = save; a.g0 = (const __nv_bfloat16*)g0; a.g1 = (const __nv_bfloat16*)g1;
+  a.cs1 = cs1; a.gp = (const __nv_bfloat16*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
+  a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
+  const long long P = (long long)N * H * W;
+  const int grid = bn_grid(P, C);
+  WSL_REQUIRE((long long)grid * 2 * C + 64 <= WSL_WS_FLOATS, "wsl_bn_bwd: workspace too small");
+  bn_bwd_reduce_kernel<<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws));
+  int rc = wsl_check_launch("bn_bwd_reduce");
+  if (rc) return rc;
+  bn_bwd_apply_kernel<<<grid_for(P * (C / 8)), TPB, 0, stream>>>(a, coef, (__nv_bfloat16*)dy);
+  return wsl_check_launch("bn_bwd_apply");
+}
+
+WSL_API int wsl_upsample2x_fwd(const void* t, int N, int h, int w, int C, void* u, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_fwd: C %% 8 != 0");
+  upsample2x_fwd_kernel<<<grid_for((long long)N * 4 * h * w * (C / 8)), TPB, 0, stream>>>((const __nv_bfloat16*)t, N, h, w, C, (__nv_bfloat16*)u);
+  return wsl_check_launch("upsample2x_fwd");
+}
+
+WSL_API int wsl_upsample2x_bwd(const void* du, int N, int h, int w, int C, void* dt, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_bwd: C %% 8 != 0");
+  upsample2x_bwd_kernel<<<grid_for((long long)N * h * w * (C / 8)), TPB, 0, stream>>>((const __nv_bfloat16*)du, N, h, w, C, (__nv_bfloat16*)dt);
+  return wsl_check_launch("upsample2x_bwd");
+}
+
+WSL_API int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long* seed_ptr, int n, float p, float* cs,
+                              cudaStream_t stream) {
+  chan_mask_gen_kernel<<<(n + 255) / 256, 256, 0, stream>>>(seed, seed_ptr, n, p, cs);
+  return wsl_check_launch("chan_mask_gen");
+}
+
+WSL_API int wsl_chan_scale(const void* a, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0, "wsl_chan_scale: C %% 8 != 0");
+  const long long tv = (long long)N * H * W * (C / 8);
+  chan_scale_kernel<<<grid_for(tv), TPB, 0, stream>>>((const __nv_bfloat16*)a, cs, (long long)H * W, C, tv, (__nv_bfloat16*)d);
+  return wsl_check_launch("chan_scale");
+}
+
+WSL_API int wsl_nchw_f32_to_nhwc_bf16(const float* src, int N, int Creal, int H, int W, int CP, void* dst, cudaStream_t stream) {
+  WSL_REQUIRE(CP % 8 == 0 && CP >= Creal, "wsl_nchw_f32_to_nhwc_bf16: bad padded channel count");
+  const long long npix = (long long)N * H * W;
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(npix), TPB, 0, stream>>>(src, Creal, CP, (long long)H * W, npix, (__nv_bfloat16*)dst);
+  return wsl_check_launch("nchw_f32_to_nhwc_bf16");
+}
+
+WSL_API int wsl_nhwc_bf16_to_nchw_f32(const void* src, int N, int C, int H, int W, float* dst, cudaStream_t stream) {
+  const long long total = (long long)N * H * W * C;
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total), TPB, 0, stream>>>((const __nv_bfloat16*)src, C, (long long)H * W, total, dst);
+  return wsl_check_launch("nhwc_bf16_to_nchw_f32");
+}
+
+WSL_API int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,
+                                  int ci_count, float* wf, float* wd, void* bf, void* bd, cudaStream_t stream) {
+  const int T = ksize * ksize;
+  WSL_REQUIRE(ci_begin % 16 == 0 || ci_count == 0, "wsl_pack_conv_weights: slice start must be a multiple of 16");
+  WSL_REQUIRE(ci_begin + ((ci_count + 15) & ~15) <= CinP || ci_count == 0, "wsl_pack_conv_weights: slice exceeds CinP");
+  pack_weights_kernel<<<grid_for((long long)T * CoutP * CinP), TPB, 0, stream>>>(w, Cout, Cin, T, CoutP, CinP, ci_begin, ci_count,
+                                                                                 wf, wd, (__nv_bfloat16*)bf, (__nv_bfloat16*)bd);
+  return wsl_check_launch("pack_conv_weights");
+}
+
+WSL_API int wsl_sgd_step(float* param, const float* grad, float* mom, long long n, const float* lr_ptr, float lr,
+                         float momentum, float weight_decay, cudaStream_t stream) {
+  sgd_kernel<<<grid_for(n), TPB, 0, stream>>>(param, grad, mom, n, lr_ptr, lr, momentum, weight_decay);
+  return wsl_check_launch("sgd_step");
+}

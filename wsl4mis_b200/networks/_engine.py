@@ -1,0 +1,395 @@
+"""Planned executor for the 2D U-Net family on the wsl4mis_b200 kernels.
+
+The reference builds its network out of per-layer nn.Modules and lets autograd walk them
+(networks/unet.py:13-135,286-346).  Here the nn.Modules are only *parameter containers* (same names,
+shapes and init order, so state_dicts interchange); the arithmetic is a fixed launch sequence over
+preallocated channels-last bf16 buffers:
+
+  forward   conv (tcgen05 implicit GEMM, or CUDA-core direct for Cin=1 / tiny maps) -> BN statistics ->
+            BN-affine + LeakyReLU + dropout (+ fused 2x2 max-pool)      [x2 per ConvBlock]
+            decoder: conv1x1 -> bilinear x2 -> two-source conv (concat never materialised)
+  backward  BN backward (fused with LeakyReLU/dropout/max-pool routing and the skip/aux/pool gradient sum)
+            -> weight gradient -> data gradient, in reverse order, gradients written into ONE flat fp32 buffer
+            (the DDP bucket).
+
+All launches go to torch's current stream, never allocate or synchronise, and are CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .._lib import LIB, call, workspace
+
+BF16 = torch.bfloat16
+LRELU_SLOPE = 0.01
+
+
+def _ceil16(c):
+    return (c + 15) // 16 * 16
+
+
+class ConvLayer:
+    """One nn.Conv2d (+ optional following BatchNorm2d/LeakyReLU/Dropout) and its packed operands."""
+
+    def __init__(self, name, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], drop_p: float, src_channels: Sequence[int]):
+        self.name, self.conv, self.bn, self.drop_p = name, conv, bn, float(drop_p)
+        self.ks = conv.kernel_size[0]
+        self.srcC = list(src_channels)
+        self.Cin, self.Cout = conv.in_channels, conv.out_channels
+        assert sum(self.srcC) == self.Cin
+        self.CinP, self.CoutP = _ceil16(self.Cin), _ceil16(self.Cout)
+        self.T = self.ks * self.ks
+        self._packs = None
+
+    def packs(self, dev):
+        if self._packs is None or self._packs["wf"].device != dev:
+            T, CinP, CoutP = self.T, self.CinP, self.CoutP
+            pk = {
+                "wf": torch.zeros(T * CinP * CoutP, dtype=torch.float32, device=dev),
+                "bf": torch.zeros(T * CinP * CoutP, dtype=BF16, device=dev),
+                "wd": [], "bd": [],
+                "bias": torch.zeros(CoutP, dtype=torch.float32, device=dev),
+            }
+            for c in self.srcC:
+                sp = _ceil16(c)
+                pk["wd"].append(torch.zeros(T * CoutP * sp, dtype=torch.float32, device=dev))
+                pk["bd"].append(torch.zeros(T * CoutP * sp, dtype=BF16, device=dev))
+            if self.bn is not None:
+                C = self.Cout
+                pk["ss"] = torch.zeros(2 * C, dtype=torch.float32, device=dev)
+            self._packs = pk
+        return self._packs
+
+    def pack(self, dev):
+        pk = self.packs(dev)
+        w = self.conv.weight
+        beg = 0
+        for i, c in enumerate(self.srcC):
+            call("wsl_pack_conv_weights", w, self.Cout, self.Cin, self.ks, self.CoutP, self.CinP, beg, c,
+                 pk["wf"] if i == 0 else None, pk["wd"][i], pk["bf"] if i == 0 else None, pk["bd"][i])
+            beg += c
+        if self.Cout == self.CoutP:
+            pk["bias"] = self.conv.bias.detach()
+        else:
+            pk["bias"][: self.Cout].copy_(self.conv.bias.detach())
+
+
+class UNetExecutor:
+    """Forward/backward launch sequences for Encoder + k Decoders (k=1: UNet, k=2: UNet_CCT)."""
+
+    MAX_SLOTS = 4
+
+    def __init__(self, model: nn.Module, encoder: nn.Module, decoders: List[nn.Module], aux_dropout: Sequence[bool]):
+        self.model = model
+        self.aux = list(aux_dropout)
+        self.layers: List[ConvLayer] = []
+        ft = encoder.ft_chns
+        self.ft = ft
+        self.in_chns = encoder.in_chns
+
+        def block(name, seq, srcC):
+            l1 = ConvLayer(f"{name}.0", seq[0], seq[1], seq[3].p, srcC)
+            l2 = ConvLayer(f"{name}.4", seq[4], seq[5], 0.0, [seq[4].in_channels])
+            self.layers += [l1, l2]
+            return (l1, l2)
+
+        self.enc_blocks = [block("encoder.in_conv.conv_conv", encoder.in_conv.conv_conv, [self.in_chns])]
+        for i in range(1, 5):
+            cb = getattr(encoder, f"down{i}").maxpool_conv[1]
+            self.enc_blocks.append(block(f"encoder.down{i}", cb.conv_conv, [ft[i - 1]]))
+        self.dec = []
+        for d in decoders:
+            ups = []
+            for j in range(1, 5):
+                ub = getattr(d, f"up{j}")
+                c1 = ConvLayer(f"up{j}.conv1x1", ub.conv1x1, None, 0.0, [ub.conv1x1.in_channels])
+                self.layers.append(c1)
+                c2 = ub.conv1x1.out_channels
+                ups.append((c1, block(f"up{j}.conv", ub.conv.conv_conv, [c2, c2])))
+            oc = ConvLayer("out_conv", d.out_conv, None, 0.0, [d.out_conv.in_channels])
+            self.layers.append(oc)
+            self.dec.append((ups, oc))
+        self.n_class = decoders[0].out_conv.out_channels
+        self.params = [p for p in model.parameters()]
+        self._gflat = None
+        self._gviews = None
+        self._bufs: Dict = {}
+        self._live: List[int] = []
+        self._seed_host = 0x5EED
+        self.use_tc = os.environ.get("WSL4MIS_NO_TC", "0") != "1"
+        self.stats = {"launches": 0}
+
+    # ---------------------------------------------------------------- buffers
+    def buf(self, slot, name, shape, dtype=BF16):
+        key = (slot, name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._bufs[key] = t
+        return t
+
+    def grads(self):
+        """Flat fp32 gradient bucket + per-parameter views (in model.parameters() order)."""
+        if self._gflat is None or self._gflat.device != self.dev:
+            n = sum(p.numel() for p in self.params)
+            self._gflat = torch.zeros(n, dtype=torch.float32, device=self.dev)
+            self._gviews, off = {}, 0
+            for p in self.params:
+                self._gviews[id(p)] = self._gflat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        return self._gflat, self._gviews
+
+    def gview(self, p):
+        return self.grads()[1][id(p)]
+
+    def _ws(self, tag):
+        return workspace(tag, self.dev)
+
+    # ---------------------------------------------------------------- primitive launches
+    def _tc_ok(self, layer_cin_list, H, W):
+        return (self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
+
+    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False):
+        pk = L.packs(self.dev)
+        s0 = srcs[0]
+        s1 = srcs[1] if len(srcs) > 1 else None
+        c0 = L.srcC[0]
+        c1 = L.srcC[1] if len(L.srcC) > 1 else 0
+        if not src_f32 and self._tc_ok(L.srcC, H, W):
+            call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
+        else:
+            call("wsl_conv_direct", s0, c0, s1, c1, 1 if src_f32 else 0, pk["wf"], pk["bias"], out, out_mode, N, H, W,
+                 L.CinP, L.CoutP, cout_store, L.ks)
+
+    def conv_dgrad(self, L: ConvLayer, i, dy, out, N, H, W):
+        pk = L.packs(self.dev)
+        ci = L.srcC[i]
+        sp = _ceil16(ci)
+        if self._tc_ok([L.CoutP], H, W):
+            call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
+        else:
+            call("wsl_conv_direct", dy, L.CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, L.CoutP, sp, ci, L.ks)
+
+    def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False):
+        s0 = srcs[0]
+        s1 = srcs[1] if len(srcs) > 1 else None
+        c0 = L.srcC[0]
+        c1 = L.srcC[1] if len(L.srcC) > 1 else 0
+        call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if src_f32 else 0, dy, L.CoutP, self.gview(L.conv.weight),
+             self.gview(L.conv.bias), N, H, W, L.Cout, L.ks)
+
+    def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None):
+        bn = L.bn
+        C = L.Cout
+        pk = L.packs(self.dev)
+        save = self.buf(slot, tag + ".save", (2 * C,), torch.float32)
+        ss = self.buf(slot, tag + ".ss", (2 * C,), torch.float32)
+        if training:
+            call("wsl_bn_stats", y, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"))
+        else:
+            call("wsl_bn_eval_prepare", bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), C, ss)
+        p = L.drop_p if training else 0.0
+        seed = self._layer_seed(L)
+        call("wsl_bn_act_fwd", y, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
+             act, pooled, pool_idx)
+        return save, ss
+
+    def bn_bwd(self, L: ConvLayer, y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, dy, N, H, W, slot, tag):
+        bn = L.bn
+        C = L.Cout
+        coef = self.buf(slot, tag + ".coef", (2 * C,), torch.float32)
+        p = L.drop_p
+        call("wsl_bn_bwd", y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
+             self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
+             self.gview(bn.bias), coef, dy, self._ws("bn"))
+
+    def _layer_seed(self, L):
+        return (self.layers.index(L) + 1) * 0x9E3779B1
+
+    # ---------------------------------------------------------------- forward
+    def pack_all(self):
+        for L in self.layers:
+            L.pack(self.dev)
+
+    def forward(self, x: torch.Tensor, training: bool, need_grad: bool, masks: Optional[dict] = None,
+                chan_keep: Optional[list] = None):
+        """x: fp32 [N, in_chns, H, W] CUDA.  Returns (list of fp32 NCHW logits, slot)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4, "input must be a CUDA fp32 NCHW tensor"
+        assert x.shape[1] == self.in_chns == 1, "executor is specialised to single-channel inputs (ACDC slices)"
+        N, _, H, W = x.shape
+        assert H % 16 == 0 and W % 16 == 0, "H, W must be multiples of 16 (4 pooling levels)"
+        self.dev = x.device
+        if not hasattr(self, "seed_dev") or self.seed_dev.device != self.dev:
+            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        x = x.contiguous()
+        slot = self._acquire_slot() if need_grad else "ng"
+        self.pack_all()
+        if training:
+            self.seed_dev.add_(1)
+        ft = self.ft
+        rec = {"N": N, "H": H, "W": W, "x": x, "training": training, "enc": [], "dec": [], "masks": masks}
+
+        def run_block(tag, blk, srcs, h, w, mask, pool, src_f32=False):
+            l1, l2 = blk
+            C = l1.Cout
+            y1 = self.buf(slot, tag + ".y1", (N, h, w, C))
+            a1 = self.buf(slot, tag + ".a1", (N, h, w, C))
+            y2 = self.buf(slot, tag + ".y2", (N, h, w, C))
+            a2 = self.buf(slot, tag + ".a2", (N, h, w, C))
+            self.conv_fwd(l1, srcs, y1, 0, N, h, w, C, src_f32)
+            sv1, ss1 = self.bn_fwd(l1, y1, a1, N, h, w, training, slot, tag + ".bn1", mask)
+            self.conv_fwd(l2, [a1], y2, 0, N, h, w, C)
+            pooled = idx = None
+            if pool:
+                pooled = self.buf(slot, tag + ".pool", (N, h // 2, w // 2, C))
+                idx = self.buf(slot, tag + ".pidx", (N, h // 2, w // 2, C), torch.uint8)
+            sv2, ss2 = self.bn_fwd(l2, y2, a2, N, h, w, training, slot, tag + ".bn2", None, pooled, idx)
+            return {"srcs": srcs, "y1": y1, "a1": a1, "y2": y2, "a2": a2, "sv1": sv1, "ss1": ss1, "sv2": sv2, "ss2": ss2,
+                    "pool": pooled, "pidx": idx, "mask": mask, "h": h, "w": w, "src_f32": src_f32}
+
+        # ---- encoder (unet.py:92-98) ----
+        src = [x]
+        h, w = H, W
+        for i, blk in enumerate(self.enc_blocks):
+            mask = None
+            if masks is not None and training:
+                mask = masks.get(i)
+            r = run_block(f"enc{i}", blk, src, h, w, mask, pool=(i < 4), src_f32=(i == 0))
+            rec["enc"].append(r)
+            if i < 4:
+                src = [r["pool"]]
+                h, w = h // 2, w // 2
+        feats = [r["a2"] for r in rec["enc"]]
+
+        # ---- decoders (unet.py:123-135; aux branch sees channel-dropped features, :344) ----
+        outs = []
+        for di, (ups, oc) in enumerate(self.dec):
+            drec = {"ups": [], "cs": None}
+            fe = feats
+            if self.aux[di]:
+                cs, fe = [], []
+                for i, f in enumerate(feats):
+                    c = self.buf(slot, f"dec{di}.cs{i}", (N, ft[i]), torch.float32)
+                    if chan_keep is not None:
+                        c.copy_(chan_keep[i].to(device=self.dev, dtype=torch.float32) * 2.0)
+                    else:
+                        call("wsl_chan_mask_gen", (di + 1) * 7919 + i, self.seed_dev, N * ft[i], 0.5, c)
+                    d = self.buf(slot, f"dec{di}.drop{i}", tuple(f.shape))
+                    call("wsl_chan_scale", f, c, N, f.shape[1], f.shape[2], ft[i], d)
+                    cs.append(c)
+                    fe.append(d)
+                drec["cs"] = cs
+            xlow = fe[4]
+            hh, ww = H // 16, W // 16
+            for j, (c1, blk) in enumerate(ups):
+                skip = fe[3 - j]
+                C2 = c1.Cout
+                t = self.buf(slot, f"dec{di}.up{j}.t", (N, hh, ww, C2))
+                self.conv_fwd(c1, [xlow], t, 0, N, hh, ww, C2)
+                u = self.buf(slot, f"dec{di}.up{j}.u", (N, 2 * hh, 2 * ww, C2))
+                call("wsl_upsample2x_fwd", t, N, hh, ww, C2, u)
+                hh, ww = 2 * hh, 2 * ww
+                r = run_block(f"dec{di}.up{j}", blk, [skip, u], hh, ww, None, pool=False)
+                r["xlow"] = xlow
+                drec["ups"].append(r)
+                xlow = r["a2"]
+            logits = torch.empty((N, self.n_class, H, W), dtype=torch.float32, device=self.dev)
+            self.conv_fwd(oc, [xlow], logits, 1, N, H, W, self.n_class)
+            drec["xlast"] = xlow
+            rec["dec"].append(drec)
+            outs.append(logits)
+        if need_grad:
+            self._recs[slot] = rec
+        return outs, slot
+
+    # ---------------------------------------------------------------- slots
+    def _acquire_slot(self):
+        if not hasattr(self, "_recs"):
+            self._recs = {}
+        for s in range(self.MAX_SLOTS):
+            if s not in self._live:
+                self._live.append(s)
+                return s
+        s = self._live.pop(0)  # recycle the oldest forward whose backward never came
+        self._live.append(s)
+        return s
+
+    # ---------------------------------------------------------------- backward
+    def backward(self, slot, grad_logits: Sequence[Optional[torch.Tensor]], zero_grads=True):
+        rec = self._recs.pop(slot)
+        if slot in self._live:
+            self._live.remove(slot)
+        N, H, W = rec["N"], rec["H"], rec["W"]
+        ft = self.ft
+        gflat, _ = self.grads()
+        if zero_grads:
+            gflat.zero_()
+        B = lambda name, shape, dt=BF16: self.buf(slot, "g." + name, shape, dt)
+
+        def block_bwd(tag, blk, r, g0, g1=None, cs1=None, gpool=None, need_dsrc=True):
+            """returns list of gradients w.r.t. the block's sources (None for the image)."""
+            l1, l2 = blk
+            h, w, C = r["h"], r["w"], l1.Cout
+            dy2 = B(tag + ".dy2", (N, h, w, C))
+            self.bn_bwd(l2, r["y2"], r["ss2"], r["sv2"], g0, g1, cs1, gpool, r["pidx"] if gpool is not None else None,
+                        None, dy2, N, h, w, slot, tag + ".bn2")
+            self.conv_wgrad(l2, [r["a1"]], dy2, N, h, w)
+            da1 = B(tag + ".da1", (N, h, w, C))
+            self.conv_dgrad(l2, 0, dy2, da1, N, h, w)
+            dy1 = B(tag + ".dy1", (N, h, w, C))
+            self.bn_bwd(l1, r["y1"], r["ss1"], r["sv1"], da1, None, None, None, None, r["mask"], dy1, N, h, w, slot,
+                        tag + ".bn1")
+            self.conv_wgrad(l1, r["srcs"], dy1, N, h, w, r["src_f32"])
+            outs = []
+            if need_dsrc:
+                for i, c in enumerate(l1.srcC):
+                    d = B(tag + f".dsrc{i}", (N, h, w, c))
+                    self.conv_dgrad(l1, i, dy1, d, N, h, w)
+                    outs.append(d)
+            return outs
+
+        # ---- decoders ----
+        skip_grads = [[] for _ in range(5)]   # per encoder level: list of (grad, cs or None)
+        for di, (ups, oc) in enumerate(self.dec):
+            g = grad_logits[di]
+            drec = rec["dec"][di]
+            if g is None:
+                continue
+            g = g.contiguous()
+            dl = B(f"dec{di}.dl", (N, H, W, 16))
+            call("wsl_nchw_f32_to_nhwc_bf16", g, N, self.n_class, H, W, 16, dl)
+            self.conv_wgrad(oc, [drec["xlast"]], dl, N, H, W)
+            da = B(f"dec{di}.dlast", (N, H, W, ft[0]))
+            self.conv_dgrad(oc, 0, dl, da, N, H, W)
+            for j in range(3, -1, -1):
+                c1, blk = ups[j]
+                r = drec["ups"][j]
+                dskip, du = block_bwd(f"dec{di}.up{j}", blk, r, da)
+                lvl = 3 - j
+                skip_grads[lvl].append((dskip, drec["cs"][lvl] if drec["cs"] else None))
+                hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
+                dt = B(f"dec{di}.up{j}.dt", (N, hh, ww, C2))
+                call("wsl_upsample2x_bwd", du, N, hh, ww, C2, dt)
+                self.conv_wgrad(c1, [r["xlow"]], dt, N, hh, ww)
+                da = B(f"dec{di}.up{j}.dxlow", (N, hh, ww, c1.Cin))
+                self.conv_dgrad(c1, 0, dt, da, N, hh, ww)
+            skip_grads[4].append((da, drec["cs"][4] if drec["cs"] else None))
+
+        # ---- encoder ----
+        gpool = None
+        for i in range(4, -1, -1):
+            r = rec["enc"][i]
+            srcs = skip_grads[i]
+            plain = [g for g, cs in srcs if cs is None]
+            scaled = [(g, cs) for g, cs in srcs if cs is not None]
+            assert len(plain) <= 1 and len(scaled) <= 1
+            g0 = plain[0] if plain else None
+            g1, cs1 = scaled[0] if scaled else (None, None)
+            d = block_bwd(f"enc{i}", self.enc_blocks[i], r, g0, g1, cs1, gpool, need_dsrc=(i > 0))
+            gpool = d[0] if i > 0 else None
+        return gflat
