@@ -136,9 +136,10 @@ int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int Cout
                           int ci_count, float* wf, float* wd, void* bf, void* bd, cudaStream_t stream);
 
 /* optim.SGD(lr, momentum, weight_decay).step() over a flat fp32 buffer (train_weakly_supervised_pCE_2D.py:79-80,104);
- * lr is read from lr_ptr (device) when non-NULL so a captured CUDA graph follows the poly schedule (:106-108). */
+ * lr is read from lr_ptr (device) when non-NULL so a captured CUDA graph follows the poly schedule (:106-108);
+ * grad_scale = 1/world_size turns the all-reduced gradient sum into DDP's mean. */
 int wsl_sgd_step(float* param, const float* grad, float* mom, long long n, const float* lr_ptr, float lr,
-                 float momentum, float weight_decay, cudaStream_t stream);
+                 float momentum, float weight_decay, float grad_scale, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

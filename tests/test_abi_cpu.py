@@ -1,0 +1,78 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads and exports every symbol that
+include/wsl4mis_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from wsl4mis_b200 import _build, _lib
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    if not os.path.exists(_lib.LIB_PATH):
+        _build.build()
+    return _lib.LIB_PATH
+
+
+def test_header_parses_and_names_are_prefixed():
+    protos = _lib.parse_header()
+    assert len(protos) >= 25
+    assert all(n.startswith("wsl_") for n in protos)
+    for must in ("wsl_softmax_pce_fwd", "wsl_gatedcrf_fwd", "wsl_conv_tc", "wsl_bn_stats", "wsl_sgd_step"):
+        assert must in protos
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    dll = ctypes.CDLL(lib_path)
+    for name in _lib.parse_header():
+        assert hasattr(dll, name), f"{name} declared in include/wsl4mis_b200.h but not exported"
+
+
+def test_no_undeclared_exports(lib_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("wsl_")}
+    declared = set(_lib.parse_header())
+    assert exported == declared, (exported - declared, declared - exported)
+
+
+def test_abi_version_and_workspace(lib_path):
+    dll = _lib.LIB.load()
+    assert dll.wsl_abi_version() == 1
+    assert dll.wsl_workspace_floats() >= 1 << 16
+
+
+def test_product_path_has_no_oracle_import():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, _, files in os.walk(os.path.join(root, "wsl4mis_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "wsl_oracle" not in src and "import oracle" not in src, f"{f} must not use the oracle"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    fresh = _lib._Lib()
+    with pytest.raises(RuntimeError, match="no CPU"):
+        fresh.load()
+
+
+def test_state_dict_layout_matches_oracle_key_order():
+    import torch  # noqa
+    import wsl_oracle as O
+    from wsl4mis_b200.networks.unet import UNet, UNet_CCT
+    assert list(UNet(1, 4).state_dict().keys()) == list(O.unet_param_shapes(1, 4, ("decoder",)).keys())
+    sd = UNet_CCT(1, 4).state_dict()
+    shapes = O.unet_param_shapes(1, 4, ("main_decoder", "aux_decoder1"))
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    assert len(sd) == 202
+
+
+def test_ramps():
+    from wsl4mis_b200.utils import ramps
+    assert ramps.sigmoid_rampup(0, 10) == pytest.approx(0.006737947, rel=1e-6)
+    assert ramps.sigmoid_rampup(10, 10) == 1.0 and ramps.sigmoid_rampup(5, 0) == 1.0
+    assert ramps.linear_rampup(5, 10) == 0.5 and ramps.cosine_rampdown(0, 10) == 1.0

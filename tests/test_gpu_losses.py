@@ -1,0 +1,173 @@
+"""Parity of the fused loss kernels (through the C ABI) against the CPU oracle and the reference-generated
+golden fixtures.  fp32 everywhere; tolerances are written next to each check."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import wsl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from wsl4mis_b200 import functional as Fn
+    from wsl4mis_b200.utils import losses as L
+    from wsl4mis_b200.utils.gate_crf_loss import ModelLossSemsegGatedCRF
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "losses_kat.npz"))
+
+
+def _t(a, grad=False):
+    t = torch.from_numpy(np.asarray(a)).to(DEV)
+    return t.requires_grad_(True) if grad else t
+
+
+def _check(val, grad, kat, key, rtol=2e-5, gtol=2e-4):
+    ref = float(kat["loss:" + key])
+    assert abs(val.item() - ref) <= rtol * max(1.0, abs(ref)), (key, val.item(), ref)
+    gref = torch.from_numpy(kat["grad:" + key])
+    scale = gref.abs().max().item() + 1e-12
+    err = (grad.cpu() - gref).abs().max().item()
+    assert err <= gtol * scale, (key, err, scale)
+
+
+def test_pce_matches_reference(kat):
+    lg = _t(kat["logits"], True)
+    loss, probs = Fn.softmax_pce(lg, _t(kat["label"]))
+    (g,) = torch.autograd.grad(loss, lg)
+    _check(loss, g, kat, "pce")
+    ref_soft = torch.softmax(torch.from_numpy(kat["logits"]), 1)
+    assert (probs.detach().cpu() - ref_soft).abs().max().item() < 2e-6
+    # module form with int64 targets, as the scripts call it
+    l2 = L.PartialCrossEntropy(4)(lg, _t(kat["label"]).long())
+    assert abs(l2.item() - loss.item()) < 1e-7
+
+
+def test_pce_no_labelled_pixel_is_nan():
+    lg = torch.randn(1, 4, 8, 8, device=DEV)
+    lab = torch.full((1, 8, 8), 4, dtype=torch.uint8, device=DEV)
+    assert torch.isnan(Fn.softmax_pce(lg, lab)[0])
+
+
+def test_gatedcrf_matches_reference(kat):
+    lg = _t(kat["logits"], True)
+    s = Fn.softmax4(lg)
+    img = _t(kat["image"])
+    out = ModelLossSemsegGatedCRF()(s, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 32, 32)["loss"]
+    (g,) = torch.autograd.grad(out, lg)
+    _check(out, g, kat, "gatedcrf", rtol=3e-5, gtol=5e-4)
+
+
+def test_gatedcrf_border_and_ragged_tiles(kat):
+    y = _t(kat["crf2:y"], True)
+    img = _t(kat["crf2:image"])
+    loss = Fn.gated_crf(y, img)
+    assert abs(loss.item() - float(kat["crf2:loss"])) < 3e-5 * abs(float(kat["crf2:loss"]))
+    (g,) = torch.autograd.grad(loss, y)
+    assert np.allclose(g.cpu().numpy(), kat["crf2:grad_y"], rtol=5e-4, atol=1e-7)
+
+
+def test_gatedcrf_rejects_unsupported():
+    y = torch.softmax(torch.randn(1, 4, 16, 16, device=DEV), 1)
+    img = torch.rand(1, 1, 16, 16, device=DEV)
+    with pytest.raises(NotImplementedError):
+        ModelLossSemsegGatedCRF()(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 3, img, 16, 16)
+    with pytest.raises(AssertionError):
+        ModelLossSemsegGatedCRF()(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 17, 16)
+
+
+def test_step_pce_gatedcrf(kat):
+    lg = _t(kat["logits"], True)
+    img, lab = _t(kat["image"]), _t(kat["label"])
+    ce, s = Fn.softmax_pce(lg, lab)
+    tot = ce + 0.1 * Fn.gated_crf(s, img)
+    (g,) = torch.autograd.grad(tot, lg)
+    _check(tot, g, kat, "step_pce_gatedcrf", rtol=3e-5, gtol=5e-4)
+
+
+def test_mumford_shah(kat):
+    lg = _t(kat["logits"], True)
+    loss = L.MumfordShah_Loss()(_t(kat["image"]), Fn.softmax4(lg))
+    (g,) = torch.autograd.grad(loss, lg)
+    _check(loss, g, kat, "mumford_shah", rtol=3e-5, gtol=5e-4)
+
+
+def test_pdice_and_dice(kat):
+    lg = _t(kat["logits"], True)
+    s = Fn.softmax4(lg)
+    pseudo = Fn.mix_argmax(s)
+    assert np.array_equal(pseudo.cpu().numpy(), torch.softmax(torch.from_numpy(kat["logits"]), 1).argmax(1).numpy())
+    for key, fn in (("pdice_argmax", lambda: L.pDLoss(4, 4)(s, pseudo.unsqueeze(1).long())),
+                    ("pdice_ignore", lambda: L.pDLoss(4, 4)(s, _t(kat["label"]).long().unsqueeze(1))),
+                    ("dice", lambda: L.DiceLoss(4)(s, pseudo.unsqueeze(1)))):
+        v = fn()
+        (g,) = torch.autograd.grad(v, lg, retain_graph=True)
+        _check(v, g, kat, key, rtol=2e-5, gtol=5e-4)
+
+
+def test_mix_argmax_bit_exact(kat):
+    s1 = torch.softmax(torch.from_numpy(kat["logits"]), 1)
+    s2 = torch.softmax(torch.from_numpy(kat["logits2"]), 1)
+    out = Fn.mix_argmax(s1.to(DEV), s2.to(DEV), float(kat["beta"]))
+    assert np.array_equal(out.cpu().numpy(), kat["pseudo_mix"])
+    # larger randomised case against the oracle on the same inputs (bit-exact label maps)
+    g = torch.Generator().manual_seed(3)
+    a = torch.softmax(torch.randn(4, 4, 64, 64, generator=g) * 3, 1)
+    b = torch.softmax(torch.randn(4, 4, 64, 64, generator=g) * 3, 1)
+    for beta in (1e-10, 0.25, 0.5, 0.999):
+        ref = O.mix_pseudo_label(a, b, beta).to(torch.uint8)
+        assert torch.equal(Fn.mix_argmax(a.to(DEV), b.to(DEV), beta).cpu(), ref)
+
+
+def test_tv_loss(kat):
+    lg = _t(kat["logits"], True)
+    v = L.tv_loss(Fn.softmax4(lg))
+    (g,) = torch.autograd.grad(v, lg)
+    _check(v, g, kat, "tv", rtol=2e-5, gtol=5e-4)
+
+
+def test_softmax_mse_and_entropy(kat):
+    a, b = _t(kat["logits"], True), _t(kat["logits2"])
+    mse = L.softmax_mse_loss(a, b)
+    assert np.allclose(mse.detach().cpu().numpy(), kat["softmax_mse"], atol=1e-6)
+    (g,) = torch.autograd.grad(mse.sum(), a)
+    assert np.allclose(g.cpu().numpy(), kat["grad:softmax_mse_sum"], atol=1e-6)
+    ent = L.entropy_minmization(Fn.softmax4(a))
+    assert abs(ent.item() - float(kat["loss:entropy"])) < 1e-5
+
+
+def test_full_size_properties():
+    """BASELINE-size (64x256x256) invariants that need no CPU oracle run."""
+    N, H, W = 64, 256, 256
+    g = torch.Generator(device="cpu").manual_seed(0)
+    img = torch.rand(N, 1, H, W, generator=g).to(DEV)
+    lab = torch.randint(0, 5, (N, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    zeros = torch.zeros(N, 4, H, W, device=DEV)
+    loss, probs = Fn.softmax_pce(zeros, lab)
+    assert abs(loss.item() - np.log(4.0)) < 1e-6              # uniform logits -> log C
+    assert (probs - 0.25).abs().max().item() == 0.0
+    # one-hot probabilities of a constant class: pairwise term equals the in-bounds kernel mass, so the
+    # loss reduces to the analytic OOB mass / denom, which must be >= 0 and tiny compared to sum(k)
+    onehot = torch.zeros(N, 4, H, W, device=DEV)
+    onehot[:, 2] = 1.0
+    out = torch.empty(2, device=DEV)
+    from wsl4mis_b200._lib import call, workspace
+    gp = torch.empty_like(onehot)
+    call("wsl_gatedcrf_fwd", onehot, img, gp, N, 4, H, W, 5, 6.0, 0.1, 1.0, out, workspace("crf"))
+    l_const, ksum = out[0].item(), out[1].item()
+    assert 0.0 <= l_const < 0.05 and ksum > 0
+    # shifting every logit by a constant leaves the CRF loss unchanged (softmax invariance)
+    lg = torch.randn(N, 4, H, W, generator=g).to(DEV)
+    a = Fn.gated_crf(Fn.softmax4(lg), img).item()
+    b = Fn.gated_crf(Fn.softmax4(lg + 3.0), img).item()
+    assert abs(a - b) < 1e-4 * abs(a)
+    # gradient of the CRF loss sums to ~0 over classes after the softmax Jacobian
+    lg.requires_grad_(True)
+    (gr,) = torch.autograd.grad(Fn.gated_crf(Fn.softmax4(lg), img), lg)
+    assert gr.sum(1).abs().max().item() < 1e-7

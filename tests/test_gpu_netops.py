@@ -1,0 +1,280 @@
+"""Unit parity of the network operator kernels (C ABI) against plain PyTorch fp32 references of the same
+op evaluated on the same bf16-rounded inputs.  bf16 outputs: tolerance = 1 bf16 ulp of the result scale
+(2^-8 relative) unless stated; fp32 outputs: 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _gpu_util import bf16_round, nchw, nhwc, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+if torch.cuda.is_available():
+    from wsl4mis_b200._lib import call, workspace
+
+BF = torch.bfloat16
+
+
+def _pack(w, c_slices):
+    """returns dict of packed operands for torch-layout weight w [Cout,Cin,k,k]"""
+    Cout, Cin, ks, _ = w.shape
+    T = ks * ks
+    CoutP, CinP = (Cout + 15) // 16 * 16, (Cin + 15) // 16 * 16
+    pk = {"wf": torch.zeros(T * CinP * CoutP, device=DEV), "bf": torch.zeros(T * CinP * CoutP, device=DEV, dtype=BF),
+          "wd": [], "bd": [], "CoutP": CoutP, "CinP": CinP}
+    beg = 0
+    for i, c in enumerate(c_slices):
+        sp = (c + 15) // 16 * 16
+        wd = torch.zeros(T * CoutP * sp, device=DEV)
+        bd = torch.zeros(T * CoutP * sp, device=DEV, dtype=BF)
+        call("wsl_pack_conv_weights", w, Cout, Cin, ks, CoutP, CinP, beg, c, pk["wf"] if i == 0 else None, wd,
+             pk["bf"] if i == 0 else None, bd)
+        pk["wd"].append(wd)
+        pk["bd"].append(bd)
+        beg += c
+    return pk
+
+
+CONV_CASES = [
+    # (N, H, W, C0, C1, Cout, ks)
+    (2, 16, 16, 16, 0, 16, 3), (2, 32, 32, 16, 0, 32, 3), (1, 16, 32, 32, 0, 32, 3), (2, 16, 16, 64, 0, 64, 3),
+    (1, 16, 16, 128, 0, 128, 3), (1, 8, 16, 256, 0, 256, 3), (1, 16, 16, 128, 128, 128, 3), (2, 16, 16, 16, 16, 16, 3),
+    (1, 32, 32, 32, 32, 32, 3), (1, 8, 16, 256, 0, 128, 1), (2, 16, 16, 32, 0, 16, 1), (1, 32, 32, 16, 0, 4, 3),
+    (3, 8, 16, 64, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("path", ["direct", "tc"])
+def test_conv_forward(case, path):
+    N, H, W, C0, C1, Cout, ks = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x0 = bf16_round(torch.randn(N, C0, H, W, generator=g))
+    x1 = bf16_round(torch.randn(N, C1, H, W, generator=g)) if C1 else None
+    w = torch.randn(Cout, C0 + C1, ks, ks, generator=g) / np.sqrt((C0 + C1) * ks * ks)
+    b = torch.randn(Cout, generator=g) * 0.1
+    xin = torch.cat([x0, x1], 1) if C1 else x0
+    pk = _pack(w.to(DEV), [C0, C1] if C1 else [C0])
+    CoutP = pk["CoutP"]
+    bias = torch.zeros(CoutP, device=DEV)
+    bias[:Cout] = b.to(DEV)
+    s0 = nhwc(x0).to(DEV)
+    s1 = nhwc(x1).to(DEV) if C1 else None
+    fp32_out = Cout == 4
+    out = torch.zeros((N, Cout, H, W), device=DEV) if fp32_out else torch.zeros((N, H, W, Cout), device=DEV, dtype=BF)
+    if path == "tc":
+        call("wsl_conv_tc", s0, C0, s1, C1, pk["bf"], bias, out, 1 if fp32_out else 0, N, H, W, CoutP, Cout, ks)
+        wref = bf16_round(w)   # tensor-core path multiplies bf16 weights
+    else:
+        call("wsl_conv_direct", s0, C0, s1, C1, 0, pk["wf"], bias, out, 1 if fp32_out else 0, N, H, W, pk["CinP"], CoutP, Cout, ks)
+        wref = w
+    torch.cuda.synchronize()
+    ref = F.conv2d(xin.double(), wref.double(), b.double(), padding=ks // 2).float()
+    got = out.cpu() if fp32_out else nchw(out.cpu())
+    tol = 1e-4 if fp32_out else 2 ** -7
+    err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-9)
+    assert err < tol, (case, path, err)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 16, 16, 16, 3), (1, 16, 16, 128, 128, 128, 3), (1, 8, 16, 256, 0, 128, 1),
+                                  (1, 16, 32, 16, 0, 4, 3), (2, 16, 16, 32, 0, 64, 3)])
+@pytest.mark.parametrize("path", ["direct", "tc"])
+def test_conv_dgrad(case, path):
+    N, H, W, C0, C1, Cout, ks = case
+    g = torch.Generator().manual_seed(11)
+    Cin = C0 + C1
+    w = torch.randn(Cout, Cin, ks, ks, generator=g) / np.sqrt(Cin * ks * ks)
+    CoutP = (Cout + 15) // 16 * 16
+    dy = torch.zeros(N, CoutP, H, W)
+    dy[:, :Cout] = bf16_round(torch.randn(N, Cout, H, W, generator=g))
+    pk = _pack(w.to(DEV), [C0, C1] if C1 else [C0])
+    dyd = nhwc(dy).to(DEV)
+    wr = bf16_round(w) if path == "tc" else w
+    ref = F.conv_transpose2d(dy[:, :Cout].double(), wr.double(), padding=ks // 2).float()
+    beg = 0
+    for i, c in enumerate([C0, C1] if C1 else [C0]):
+        sp = (c + 15) // 16 * 16
+        out = torch.zeros((N, H, W, c), device=DEV, dtype=BF)
+        if path == "tc":
+            call("wsl_conv_tc", dyd, CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, c, ks)
+        else:
+            call("wsl_conv_direct", dyd, CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, CoutP, sp, c, ks)
+        torch.cuda.synchronize()
+        r = ref[:, beg:beg + c]
+        err = (nchw(out.cpu()) - r).abs().max().item() / (r.abs().max().item() + 1e-9)
+        assert err < 2 ** -7, (case, path, i, err)
+        beg += c
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 16, 16, 16, 3), (1, 16, 16, 64, 0, 64, 3), (2, 8, 16, 32, 0, 16, 1),
+                                  (2, 32, 32, 16, 0, 4, 3), (3, 24, 40, 1, 0, 16, 3)])
+def test_wgrad_direct(case):
+    N, H, W, C0, C1, Cout, ks = case
+    g = torch.Generator().manual_seed(5)
+    Cin = C0 + C1
+    f32src = C0 == 1
+    x = torch.randn(N, Cin, H, W, generator=g)
+    if not f32src:
+        x = bf16_round(x)
+    CoutP = (Cout + 15) // 16 * 16
+    dy = torch.zeros(N, CoutP, H, W)
+    dy[:, :Cout] = bf16_round(torch.randn(N, Cout, H, W, generator=g))
+    dw = torch.zeros(Cout, Cin, ks, ks, device=DEV)
+    db = torch.zeros(Cout, device=DEV)
+    if f32src:
+        s0, s1 = x.to(DEV).contiguous(), None
+    else:
+        s0 = nhwc(x[:, :C0]).to(DEV)
+        s1 = nhwc(x[:, C0:]).to(DEV) if C1 else None
+    call("wsl_wgrad_direct", s0, C0, s1, C1, 1 if f32src else 0, nhwc(dy).to(DEV), CoutP, dw, db, N, H, W, Cout, ks)
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(False)
+    wz = torch.zeros(Cout, Cin, ks, ks, dtype=torch.double, requires_grad=True)
+    bz = torch.zeros(Cout, dtype=torch.double, requires_grad=True)
+    out = F.conv2d(xr, wz, bz, padding=ks // 2)
+    gw, gb = torch.autograd.grad(out, [wz, bz], dy[:, :Cout].double())
+    assert rel_l2(dw.cpu(), gw.float()) < 1e-5
+    assert rel_l2(db.cpu(), gb.float()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 16), (3, 8, 24, 64), (1, 4, 4, 256), (2, 32, 32, 32)])
+def test_bn_stats_and_act(shape):
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(2)
+    y = bf16_round(torch.randn(N, C, H, W, generator=g) * 1.7 + 0.3)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    yd = nhwc(y).to(DEV)
+    save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
+    rmd, rvd = rm.to(DEV), rv.to(DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    call("wsl_bn_stats", yd, N * H * W, C, gamma.to(DEV), beta.to(DEV), rmd, rvd, nbt, 0.1, 1e-5, save, ss, workspace("bn"))
+    rm2, rv2 = rm.clone(), rv.clone()
+    ref = F.batch_norm(y, rm2, rv2, gamma, beta, True, 0.1, 1e-5)
+    torch.cuda.synchronize()
+    assert nbt.item() == 1
+    assert torch.allclose(rmd.cpu(), rm2, atol=1e-5) and torch.allclose(rvd.cpu(), rv2, rtol=1e-4, atol=1e-5)
+    mean = y.mean((0, 2, 3))
+    assert torch.allclose(save[:C].cpu(), mean, atol=1e-5)
+    # activation + dropout mask + pool
+    p = 0.3
+    mask = (torch.rand(N, C, H, W, generator=g) >= p)
+    act = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
+    pooled = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=BF)
+    pidx = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=torch.uint8)
+    mk = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
+    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, mk, 0, None, act, pooled, pidx)
+    torch.cuda.synchronize()
+    ra = F.leaky_relu(ref, 0.01) * mask / (1 - p)
+    assert (nchw(act.cpu()) - ra).abs().max().item() <= 2 ** -8 * ra.abs().max().item() + 1e-6
+    rp, ri = F.max_pool2d(nchw(act.cpu()), 2, return_indices=True)
+    assert torch.equal(nchw(pooled.cpu()), rp)
+    # pool index k = 2*dy+dx inside the window must point at a maximal element
+    a = nchw(act.cpu())
+    k = pidx.cpu().permute(0, 3, 1, 2).long()
+    yy = torch.arange(H // 2).view(1, 1, -1, 1) * 2 + (k >> 1)
+    xx = torch.arange(W // 2).view(1, 1, 1, -1) * 2 + (k & 1)
+    picked = a.flatten(2).gather(2, (yy * W + xx).flatten(2)).view_as(rp)
+    assert torch.equal(picked, rp)
+    # counter-RNG dropout keeps ~ (1-p) of the elements and is reproduced by the same seed
+    a1 = torch.zeros_like(act)
+    a2 = torch.zeros_like(act)
+    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, None, 1234, None, a1, None, None)
+    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, None, 1234, None, a2, None, None)
+    torch.cuda.synchronize()
+    assert torch.equal(a1, a2)
+    frac = (a1 != 0).float().mean().item()
+    assert abs(frac - (1 - p)) < 0.05
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 16), (2, 8, 24, 64), (2, 32, 32, 32)])
+def test_bn_backward_chain(shape):
+    """dY, dgamma, dbeta of conv-out -> BN(train) -> LeakyReLU -> dropout -> {identity, channel-scale, maxpool}."""
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(9)
+    y = bf16_round(torch.randn(N, C, H, W, generator=g) * 1.3 + 0.2)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    p = 0.2
+    mask = (torch.rand(N, C, H, W, generator=g) >= p)
+    cs = (torch.rand(N, C, generator=g) >= 0.5).float() * 2
+    g0 = bf16_round(torch.randn(N, C, H, W, generator=g))
+    g1 = bf16_round(torch.randn(N, C, H, W, generator=g))
+    gp = bf16_round(torch.randn(N, C, H // 2, W // 2, generator=g))
+    # reference with autograd (fp64)
+    yr = y.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    z = F.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5)
+    a = F.leaky_relu(z, 0.01) * mask / (1 - p)
+    a_bf = a.detach().float().to(BF).double()           # the stored activation the pool sees
+    _, idx = F.max_pool2d(a_bf, 2, return_indices=True)
+    pool_grad = torch.zeros(N, C, H * W, dtype=torch.double).scatter_(2, idx.flatten(2), gp.double().flatten(2)).view(N, C, H, W)
+    upstream = g0.double() + g1.double() * cs.double()[:, :, None, None] + pool_grad
+    dyr, dgr, dbr = torch.autograd.grad(a, [yr, gr, br], upstream)
+    # kernels
+    yd = nhwc(y).to(DEV)
+    save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
+    call("wsl_bn_stats", yd, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
+    act = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
+    pooled = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=BF)
+    pidx = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=torch.uint8)
+    mk = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
+    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, mk, 0, None, act, pooled, pidx)
+    dgam, dbet, coef = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2 * C, device=DEV)
+    dy = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
+    call("wsl_bn_bwd", yd, ss, save, nhwc(g0).to(DEV), nhwc(g1).to(DEV), cs.to(DEV), nhwc(gp).to(DEV), pidx, mk, 0, None, p,
+         0.01, N, H, W, C, dgam, dbet, coef, dy, workspace("bn"))
+    torch.cuda.synchronize()
+    assert rel_l2(dgam.cpu(), dgr.float()) < 1e-4
+    assert rel_l2(dbet.cpu(), dbr.float()) < 1e-4
+    assert rel_l2(nchw(dy.cpu()), dyr.float()) < 2 ** -8
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 4, 16), (1, 16, 8, 32), (2, 2, 2, 128)])
+def test_upsample(shape):
+    N, h, w, C = shape
+    g = torch.Generator().manual_seed(4)
+    t = bf16_round(torch.randn(N, C, h, w, generator=g))
+    u = torch.zeros((N, 2 * h, 2 * w, C), device=DEV, dtype=BF)
+    call("wsl_upsample2x_fwd", nhwc(t).to(DEV), N, h, w, C, u)
+    tr = t.clone().requires_grad_(True)
+    ref = F.interpolate(tr, scale_factor=2, mode="bilinear", align_corners=True)
+    torch.cuda.synchronize()
+    assert (nchw(u.cpu()) - ref.detach()).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    du = bf16_round(torch.randn(N, C, 2 * h, 2 * w, generator=g))
+    (gt,) = torch.autograd.grad(ref, tr, du)
+    dt = torch.zeros((N, h, w, C), device=DEV, dtype=BF)
+    call("wsl_upsample2x_bwd", nhwc(du).to(DEV), N, h, w, C, dt)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dt.cpu()), gt) < 2 ** -8
+
+
+def test_sgd_matches_torch():
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(10007, generator=g)
+    ref = torch.nn.Parameter(w.clone())
+    opt = torch.optim.SGD([ref], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    p, m = w.to(DEV), torch.zeros(10007, device=DEV)
+    lr_dev = torch.tensor([0.01], device=DEV)
+    for it in range(3):
+        gr = torch.randn(10007, generator=g)
+        ref.grad = gr.clone()
+        opt.step()
+        call("wsl_sgd_step", p, gr.to(DEV), m, 10007, lr_dev if it % 2 else None, 0.01, 0.9, 1e-4, 1.0)
+    torch.cuda.synchronize()
+    assert torch.allclose(p.cpu(), ref.data, atol=2e-7)
+
+
+def test_chan_dropout():
+    N, H, W, C = 3, 8, 8, 32
+    cs = torch.zeros(N * C, device=DEV)
+    call("wsl_chan_mask_gen", 42, None, N * C, 0.5, cs)
+    torch.cuda.synchronize()
+    vals = set(cs.cpu().unique().tolist())
+    assert vals <= {0.0, 2.0} and len(vals) == 2
+    a = bf16_round(torch.randn(N, C, H, W))
+    d = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
+    call("wsl_chan_scale", nhwc(a).to(DEV), cs, N, H, W, C, d)
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(d.cpu()), a * cs.cpu().view(N, C, 1, 1))

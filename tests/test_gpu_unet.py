@@ -1,0 +1,171 @@
+"""Whole-network parity: UNet / UNet_CCT on the fused executor vs the reference-generated golden fixtures
+and vs the CPU oracle on the same seeded inputs and weights.
+
+The reference computes in fp32; the executor stores activations in bf16 (8-bit mantissa) with fp32
+accumulation, statistics and master weights.  Tolerances are therefore stated relative to the logit /
+gradient scale and were chosen from the measured error (see DESIGN.md 'Precision'), not from the 1e-3
+north-star target, which bf16 storage cannot meet (reported, not hidden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import wsl_oracle as O
+from _gpu_util import chan_masks, cosine, elem_masks_nchw, rel_l2, ENC_MASK_KEYS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+if torch.cuda.is_available():
+    from wsl4mis_b200 import functional as Fn
+    from wsl4mis_b200.networks.net_factory import net_factory
+    from wsl4mis_b200.networks.unet import UNet, UNet_CCT
+    from wsl4mis_b200.utils import losses as L
+    from wsl4mis_b200.utils.gate_crf_loss import ModelLossSemsegGatedCRF
+
+LOGIT_TOL = 0.04      # max |logit error| / max |logit|   (bf16 activations, 23 layers; measured ~0.01-0.02)
+GRAD_COS = 0.985      # cosine similarity of every weight gradient with the fp32 reference
+
+
+def _model(cct, g, use_tc=True):
+    decs = ("main_decoder", "aux_decoder1") if cct else ("decoder",)
+    p = O.synth_params(1, 4, decs, int(g["pseed"]))
+    m = (UNet_CCT if cct else UNet)(1, 4)
+    m.load_state_dict(p)
+    m = m.to(DEV)
+    m.executor.use_tc = use_tc
+    return m, p
+
+
+def _set_masks(m, g, cct):
+    n, hw = int(g["n"]), int(g["hw"])
+    em = elem_masks_nchw(int(g["mseed"]), n, hw, hw)
+    m.dropout_masks = {i: e.permute(0, 2, 3, 1).contiguous().to(DEV) for i, e in enumerate(em)}
+    ck = None
+    if cct:
+        ck = chan_masks(int(g["cseed"]), n)
+        m.channel_keep = [c.to(DEV) for c in ck]
+    return {k: e for k, e in zip(ENC_MASK_KEYS, em)}, ck
+
+
+@pytest.mark.parametrize("use_tc", [True, False])
+@pytest.mark.parametrize("cct", [False, True])
+def test_forward_matches_golden(golden_dir, cct, use_tc):
+    g = np.load(os.path.join(golden_dir, "unet_cct_dmpls.npz" if cct else "unet_pce_gatedcrf.npz"))
+    m, _ = _model(cct, g, use_tc)
+    _set_masks(m, g, cct)
+    x = torch.from_numpy(g["image"]).to(DEV)
+    m.eval()
+    with torch.no_grad():
+        o = m(x)
+    main = o[0] if cct else o
+    ref = torch.from_numpy(g["eval_main"])
+    err = (main.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < LOGIT_TOL, ("eval", err)
+    if cct:
+        ra = torch.from_numpy(g["eval_aux"])
+        assert (o[1].cpu() - ra).abs().max().item() / ra.abs().max().item() < LOGIT_TOL
+    m.train()
+    with torch.no_grad():
+        o = m(x)
+    main = o[0] if cct else o
+    ref = torch.from_numpy(g["train_main"])
+    err = (main.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < LOGIT_TOL, ("train", err)
+    # label maps: bit-exact wherever the reference's top-2 margin exceeds the logit tolerance
+    top2 = ref.topk(2, dim=1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_TOL * ref.abs().max()
+    assert torch.equal(main.cpu().argmax(1)[sure], ref.argmax(1)[sure])
+    assert sure.float().mean().item() > 0.5
+
+
+@pytest.mark.parametrize("cct", [False, True])
+def test_backward_matches_oracle_and_golden(golden_dir, cct):
+    g = np.load(os.path.join(golden_dir, "unet_cct_dmpls.npz" if cct else "unet_pce_gatedcrf.npz"))
+    m, p = _model(cct, g)
+    om, ock = _set_masks(m, g, cct)
+    x = torch.from_numpy(g["image"]).to(DEV)
+    lab = torch.from_numpy(g["label"]).to(DEV)
+    m.train()
+    if cct:
+        beta = float(g["beta"])
+        o1, o2 = m(x)
+        ce1, s1 = Fn.softmax_pce(o1, lab)
+        ce2, s2 = Fn.softmax_pce(o2, lab)
+        pseudo = Fn.mix_argmax(s1, s2, beta)
+        pdl = L.pDLoss(4, 4)
+        loss = 0.5 * (ce1 + ce2) + 0.5 * 0.5 * (pdl(s1, pseudo.unsqueeze(1)) + pdl(s2, pseudo.unsqueeze(1)))
+    else:
+        o = m(x)
+        ce, s = Fn.softmax_pce(o, lab)
+        loss = ce + 0.1 * ModelLossSemsegGatedCRF()(s, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, x, 32, 32)["loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss = float(g["loss"])
+    assert abs(loss.item() - ref_loss) < 0.02 * abs(ref_loss), (loss.item(), ref_loss)
+    # oracle gradients on the same inputs (fp32 CPU)
+    _, grads, _ = O.full_step(p, torch.from_numpy(g["image"]), torch.from_numpy(g["label"]),
+                              "dmpls" if cct else "pce_gatedcrf", cct, om, ock, float(g["beta"]) if cct else 0.5)
+    keys = [str(k) for k in g["grad_keys"]]
+    stats = g["grad_stats"]
+    named = dict(m.named_parameters())
+    worst = 1.0
+    for k, (_, _, l2) in zip(keys, stats):
+        mine = named[k].grad.detach().cpu()
+        ref = grads[k]
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            # conv bias directly before BatchNorm: the true gradient is 0, both sides hold rounding noise
+            assert mine.abs().max().item() < 1e-3 * max(1.0, stats[:, 1].max())
+            continue
+        c = cosine(mine, ref)
+        worst = min(worst, c)
+        assert c > GRAD_COS, (k, c)
+        assert abs(mine.double().norm().item() - l2) < 0.08 * l2 + 1e-6, (k, mine.norm().item(), l2)
+    print("worst gradient cosine", worst)
+    # running statistics were updated in place like nn.BatchNorm2d does
+    if not cct:
+        sd = m.state_dict()
+        for k in [f for f in g.files if f.startswith("stat:")]:
+            assert np.allclose(sd[k[5:]].cpu().numpy(), g[k], rtol=2e-2, atol=2e-3), k
+        assert int(sd["encoder.in_conv.conv_conv.1.num_batches_tracked"]) == 1
+
+
+def test_script_style_step_with_torch_optimizer():
+    """The per-step body of train_weakly_supervised_pCE_GatedCRFLoss_2D.py:111-126 written exactly as the
+    script does (torch CrossEntropyLoss, torch.softmax, optim.SGD) on net_factory's model: loss decreases."""
+    torch.manual_seed(2022)
+    model = net_factory("unet", in_chns=1, class_num=4)
+    assert net_factory("nope") is None
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    ce_loss = torch.nn.CrossEntropyLoss(ignore_index=4)
+    crf = ModelLossSemsegGatedCRF()
+    img, lab = O.synth_batch(4, 64, 64, seed=1, frac=0.05)
+    img, lab = img.to(DEV), lab.to(DEV)
+    model.train()
+    hist = []
+    for it in range(12):
+        out = model(img)
+        soft = torch.softmax(out, dim=1)
+        l_ce = ce_loss(out, lab[:].long())
+        l_crf = crf(soft, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 64, 64)["loss"]
+        loss = l_ce + 0.1 * l_crf
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        hist.append(l_ce.item())
+    assert hist[-1] < hist[0] * 0.8, hist
+
+
+def test_rng_dropout_is_fresh_each_step_and_eval_is_deterministic():
+    torch.manual_seed(0)
+    m = UNet(1, 4).to(DEV)
+    x = torch.rand(2, 1, 32, 32, device=DEV)
+    m.train()
+    with torch.no_grad():
+        a, b = m(x), m(x)
+    assert not torch.equal(a, b)
+    m.eval()
+    with torch.no_grad():
+        c, d = m(x), m(x)
+    assert torch.equal(c, d)

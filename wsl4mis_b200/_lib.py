@@ -94,10 +94,47 @@ def call(name, *args):
         raise TypeError(f"{name}: expected {len(proto)} arguments ({[n for _, n in proto]}), got {len(args)}")
     for (ty, _), a in zip(proto, args):
         vals.append(_ptr(a) if ty is ctypes.c_void_p else a)
+    COUNTERS["launch_calls"] += 1
+    if PROFILE is not None:
+        PROFILE.record(name, getattr(dll, name), vals)
+        return 0
     rc = getattr(dll, name)(*vals)
     if ret is ctypes.c_int and rc != 0 and name not in ("wsl_abi_version", "wsl_workspace_floats", "wsl_tc_available"):
         raise RuntimeError(f"{name} failed ({rc}): {LIB.last_error()}")
     return rc
+
+
+COUNTERS = {"launch_calls": 0}
+PROFILE = None   # set to a _Profiler by bench.py to time every C-ABI call with CUDA events
+
+
+class Profiler:
+    """Per-call CUDA-event timing of the C-ABI launches (used by bench.py for the roofline table)."""
+
+    def __init__(self):
+        self.rows = []   # (name, start_event, stop_event, meta)
+        self.meta = None
+
+    def record(self, name, fn, vals):
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*vals)
+        e.record()
+        if rc != 0:
+            raise RuntimeError(f"{name} failed ({rc}): {LIB.last_error()}")
+        self.rows.append((name, s, e, self.meta))
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, s, e, meta in self.rows:
+            key = (name, meta)
+            ms = s.elapsed_time(e)
+            a = agg.setdefault(key, [0, 0.0])
+            a[0] += 1
+            a[1] += ms
+        return agg
 
 
 _WS = {}

@@ -639,10 +639,10 @@ __global__ void __launch_bounds__(TPB) pack_weights_kernel(const float* __restri
 // torch.optim.SGD(momentum, weight_decay), dampening 0, no nesterov: g += wd*p; buf = mu*buf + g; p -= lr*buf
 // (zero-initialised buf reproduces torch's first-step "buf = g").
 __global__ void __launch_bounds__(TPB) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                  long long n, const float* lr_ptr, float lr, float mu, float wd) {
+                                                  long long n, const float* lr_ptr, float lr, float mu, float wd, float gscale) {
   const float l = lr_ptr ? *lr_ptr : lr;
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
-    const float gg = fmaf(wd, p[i], g[i]);
+    const float gg = fmaf(wd, p[i], g[i] * gscale);
     const float b = fmaf(mu, m[i], gg);
     m[i] = b;
     p[i] = p[i] - l * b;
@@ -800,7 +800,7 @@ WSL_API int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, 
 }
 
 WSL_API int wsl_sgd_step(float* param, const float* grad, float* mom, long long n, const float* lr_ptr, float lr,
-                         float momentum, float weight_decay, cudaStream_t stream) {
-  sgd_kernel<<<grid_for(n), TPB, 0, stream>>>(param, grad, mom, n, lr_ptr, lr, momentum, weight_decay);
+                         float momentum, float weight_decay, float grad_scale, cudaStream_t stream) {
+  sgd_kernel<<<grid_for(n), TPB, 0, stream>>>(param, grad, mom, n, lr_ptr, lr, momentum, weight_decay, grad_scale);
   return wsl_check_launch("sgd_step");
 }

@@ -22,6 +22,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 import torch.nn as nn
 
+from .. import _lib
 from .._lib import LIB, call, workspace
 
 BF16 = torch.bfloat16
@@ -150,6 +151,20 @@ class UNetExecutor:
         return workspace(tag, self.dev)
 
     # ---------------------------------------------------------------- primitive launches
+    def _tag(self, kind, L, N, H, W, cin, cout):
+        """Label the next C-ABI call for bench.py's per-kernel table: algorithmic FLOPs and ideal bytes."""
+        if _lib.PROFILE is not None:
+            flops = 2.0 * cin * cout * L.T * H * W * N
+            if kind == "wgrad":
+                byts = 2.0 * (cin + cout) * H * W * N
+            else:
+                byts = 2.0 * (cin + cout) * H * W * N
+            _lib.PROFILE.meta = (kind, L.name, flops, byts)
+
+    def _untag(self):
+        if _lib.PROFILE is not None:
+            _lib.PROFILE.meta = None
+
     def _tc_ok(self, layer_cin_list, H, W):
         return (self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
 
@@ -159,28 +174,34 @@ class UNetExecutor:
         s1 = srcs[1] if len(srcs) > 1 else None
         c0 = L.srcC[0]
         c1 = L.srcC[1] if len(L.srcC) > 1 else 0
+        self._tag("fwd", L, N, H, W, L.Cin, L.Cout)
         if not src_f32 and self._tc_ok(L.srcC, H, W):
             call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         else:
             call("wsl_conv_direct", s0, c0, s1, c1, 1 if src_f32 else 0, pk["wf"], pk["bias"], out, out_mode, N, H, W,
                  L.CinP, L.CoutP, cout_store, L.ks)
+        self._untag()
 
     def conv_dgrad(self, L: ConvLayer, i, dy, out, N, H, W):
         pk = L.packs(self.dev)
         ci = L.srcC[i]
         sp = _ceil16(ci)
+        self._tag("dgrad", L, N, H, W, ci, L.Cout)
         if self._tc_ok([L.CoutP], H, W):
             call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
         else:
             call("wsl_conv_direct", dy, L.CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, L.CoutP, sp, ci, L.ks)
+        self._untag()
 
     def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False):
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
         c0 = L.srcC[0]
         c1 = L.srcC[1] if len(L.srcC) > 1 else 0
+        self._tag("wgrad", L, N, H, W, L.Cin, L.Cout)
         call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if src_f32 else 0, dy, L.CoutP, self.gview(L.conv.weight),
              self.gview(L.conv.bias), N, H, W, L.Cout, L.ks)
+        self._untag()
 
     def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None):
         bn = L.bn
