@@ -97,6 +97,13 @@ int wsl_tc_available(void);
 int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
                 void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
                 cudaStream_t stream);
+/* tcgen05 weight gradient (conv_tc.cu): dw (fp32, torch layout [CoutReal][C0+C1][k][k]) += dY^T * X over all pixels.
+ * Bias gradients are NOT produced here (see wsl_channel_sum). */
+int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                 int W, int CoutReal, int ksize, cudaStream_t stream);
+/* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
+int wsl_channel_sum(const void* x, long long P, int C, int Creal, float* out, cudaStream_t stream);
+
 /* nn.BatchNorm2d training statistics (unet.py:20,24): save = {mean[C], invstd[C]}, ss = {scale[C], shift[C]};
  * running stats / num_batches_tracked updated in place when non-NULL. */
 int wsl_bn_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,

@@ -139,6 +139,44 @@ def test_wgrad_direct(case):
     assert rel_l2(db.cpu(), gb.float()) < 1e-5
 
 
+WGRAD_TC_CASES = [
+    (2, 16, 16, 16, 0, 16, 3), (2, 16, 32, 16, 0, 32, 3), (1, 32, 32, 32, 0, 32, 3), (2, 16, 16, 64, 0, 64, 3),
+    (1, 16, 16, 128, 0, 128, 3), (1, 8, 16, 256, 0, 256, 3), (1, 16, 16, 128, 128, 128, 3), (2, 16, 16, 16, 16, 16, 3),
+    (1, 16, 32, 32, 32, 32, 3), (2, 16, 16, 64, 64, 64, 3), (1, 8, 16, 256, 0, 128, 1), (2, 16, 16, 32, 0, 16, 1),
+    (2, 16, 16, 64, 0, 32, 1), (1, 32, 32, 16, 0, 4, 3), (3, 8, 16, 32, 0, 64, 3), (2, 16, 16, 64, 0, 128, 3),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_wgrad_tc(case):
+    """tcgen05 weight gradient vs fp64 autograd on the same bf16 inputs; fp32 accumulation -> 1e-4 relative."""
+    N, H, W, C0, C1, Cout, ks = case
+    g = torch.Generator().manual_seed(17)
+    Cin = C0 + C1
+    x = bf16_round(torch.randn(N, Cin, H, W, generator=g))
+    CoutP = (Cout + 15) // 16 * 16
+    dy = torch.zeros(N, CoutP, H, W)
+    dy[:, :Cout] = bf16_round(torch.randn(N, Cout, H, W, generator=g))
+    dw = torch.zeros(Cout, Cin, ks, ks, device=DEV)
+    s0 = nhwc(x[:, :C0]).to(DEV)
+    s1 = nhwc(x[:, C0:]).to(DEV) if C1 else None
+    dyd = nhwc(dy).to(DEV)
+    call("wsl_wgrad_tc", s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
+    db = torch.zeros(Cout, device=DEV)
+    call("wsl_channel_sum", dyd, N * H * W, CoutP, Cout, db)
+    torch.cuda.synchronize()
+    wz = torch.zeros(Cout, Cin, ks, ks, dtype=torch.double, requires_grad=True)
+    bz = torch.zeros(Cout, dtype=torch.double, requires_grad=True)
+    out = F.conv2d(x.double(), wz, bz, padding=ks // 2)
+    gw, gb = torch.autograd.grad(out, [wz, bz], dy[:, :Cout].double())
+    assert rel_l2(dw.cpu(), gw.float()) < 1e-4, (case, rel_l2(dw.cpu(), gw.float()))
+    assert rel_l2(db.cpu(), gb.float()) < 1e-5
+    # accumulation semantics: a second call doubles the result
+    call("wsl_wgrad_tc", s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu(), 2 * gw.float()) < 1e-4
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 16, 16), (3, 8, 24, 64), (1, 4, 4, 256), (2, 32, 32, 32)])
 def test_bn_stats_and_act(shape):
     N, H, W, C = shape

@@ -364,6 +364,231 @@ int dispatch_nt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   return -1;
 }
 
+
+// ================================================================================================
+// tcgen05 weight gradient:  dW[co][ci][t] += sum_{pixels} dY[p][co] * X[p + tap_t][ci]
+//
+//   D_t[M = 128 couts, N = CWB cins] (fp32, TMEM) += A^T[K = 128 pixels x M] * B_t[K = 128 pixels x N]
+//
+// Both operands are "MN-major" for the tensor core: K (pixels) indexes shared-memory rows, the channel (M or N)
+// is contiguous inside a row -- exactly what a channels-last TMA box (channels x 16 w x 8 h) produces.  A (dY) is
+// loaded once per 128-pixel chunk, B (the tap-shifted X box, TMA zero fill = padding) once per tap of the CTA's
+// tap group; each CTA owns (Cout tile of 128) x (Cin block of CWB) x (TG taps), loops over its share of the
+// N*H*W/128 pixel chunks (split-K), keeps TG accumulators in TMEM and finally adds them into the fp32
+// torch-layout gradient with red.global.add.f32.
+//   CWA/CWB = channels per A/B box (16/32/64 -> swizzle 32/64/128 B), NA = A boxes per stage (1 or 2).
+// When Cout < 128 the MMA still runs M = 128 (same tensor-pipe cost as M = 64): the missing row groups alias
+// whatever shared memory follows the A box; those accumulator rows are never read.
+// ================================================================================================
+template <int SW>
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  constexpr uint64_t layout = (SW == 128) ? 2 : (SW == 64) ? 4 : 6;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;   // stride between SW-byte wide channel groups
+  d |= (uint64_t)((8 * SW) >> 4) << 32;                // stride between 8-pixel row groups
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+struct WgradTcParams {
+  int N, H, W;
+  int C0, C1;          // source channels
+  int CoutP, CoutReal;
+  int taps, ks;
+  int tiles_x, tiles_y, nchunks;
+  int n_tiles0, n_tiles1;   // Cin blocks in source 0 / 1
+  int tap_groups;
+  float* dw;
+};
+
+template <int CWA, int NA, int CWB, int TG, int STAGES>
+struct WgradSmem {
+  static constexpr int A_BOX = TILE_M * CWA * 2;
+  static constexpr int B_BOX = TILE_M * CWB * 2;
+  static constexpr int STAGE_BYTES = ((NA * A_BOX + TG * B_BOX + 1023) / 1024) * 1024;
+  static constexpr int SLACK = (128 / CWA) * A_BOX;   // aliased row groups of the last stage stay inside the allocation
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + SLACK + 1024 + 256;
+};
+
+template <int CWA, int NA, int CWB, int TG, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                                  const __grid_constant__ CUtensorMap map_x0,
+                                                                  const __grid_constant__ CUtensorMap map_x1, const WgradTcParams p) {
+  using S = WgradSmem<CWA, NA, CWB, TG, STAGES>;
+  constexpr int SWA = CWA * 2, SWB = CWB * 2;
+  constexpr uint32_t TMEM_COLS = (TG * CWB <= 32) ? 32 : (TG * CWB <= 64) ? 64 : (TG * CWB <= 128) ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::SLACK);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.y -> (m tile, n tile, tap group)
+  int by = blockIdx.y;
+  const int tg = by % p.tap_groups; by /= p.tap_groups;
+  const int n_tiles = p.n_tiles0 + p.n_tiles1;
+  const int nt = by % n_tiles;
+  const int mt = by / n_tiles;
+  const int m0 = mt * 128;
+  const bool src1 = nt >= p.n_tiles0;
+  const int cb0 = (src1 ? nt - p.n_tiles0 : nt) * CWB;             // channel offset inside the source tensor
+  const int ci_global = (src1 ? p.C0 : 0) + cb0;                   // channel offset in the concatenated input
+  const int pad = p.ks >> 1;
+  const int my_chunks = (p.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_dy);
+    prefetch_tmap(src1 ? &map_x1 : &map_x0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mx = src1 ? &map_x1 : &map_x0;
+      for (int it = 0; it < my_chunks; ++it) {
+        const int chunk = blockIdx.x + it * gridDim.x;
+        const int n = chunk / (p.tiles_x * p.tiles_y);
+        const int tr = chunk - n * p.tiles_x * p.tiles_y;
+        const int y0 = (tr / p.tiles_x) * TILE_H, x0 = (tr % p.tiles_x) * TILE_W;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + NA * S::A_BOX;
+        mbar_expect_tx(&full_bar[s], NA * S::A_BOX + TG * S::B_BOX);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) tma_load_4d(&map_dy, &full_bar[s], a_dst + i * S::A_BOX, m0 + i * CWA, x0, y0, n);
+#pragma unroll
+        for (int tl = 0; tl < TG; ++tl) {
+          const int t = tg * TG + tl;
+          const int dy = t / p.ks - pad, dx = t % p.ks - pad;
+          tma_load_4d(mx, &full_bar[s], b_dst + tl * S::B_BOX, cb0, x0 + dx, y0 + dy, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(CWB, /*a_mn_major=*/1, /*b_mn_major=*/1, 128);
+    for (int it = 0; it < my_chunks; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + NA * S::A_BOX;
+        const uint64_t adesc = make_mnmajor_desc<SWA>(a_addr, S::A_BOX);
+#pragma unroll
+        for (int tl = 0; tl < TG; ++tl) {
+          const uint64_t bdesc = make_mnmajor_desc<SWB>(b_addr + tl * S::B_BOX, S::B_BOX);
+#pragma unroll
+          for (int k = 0; k < TILE_M / 16; ++k) {
+            // 16 pixels (rows) per MMA: advance both operands by 16 rows
+            umma_f16(tmem_base + tl * CWB, adesc + (uint64_t)((k * 16 * SWA) >> 4), bdesc + (uint64_t)((k * 16 * SWB) >> 4), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == my_chunks - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  } else if (my_chunks > 0) {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int CinTot = p.C0 + p.C1;
+#pragma unroll 1
+    for (int tl = 0; tl < TG; ++tl) {
+      const int t = tg * TG + tl;
+#pragma unroll 1
+      for (int c = 0; c < CWB; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * CWB + c), v);
+        if (row < p.CoutReal && q * 32 + lane < 128) {
+          float* dst = p.dw + ((size_t)row * CinTot + ci_global + c) * p.taps + t;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + (size_t)j * p.taps, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int CWA, int NA, int CWB, int TG>
+int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const WgradTcParams& p, int m_tiles,
+                 cudaStream_t stream) {
+  constexpr int per_stage = NA * TILE_M * CWA * 2 + TG * TILE_M * CWB * 2;
+  constexpr int STAGES = per_stage >= 80 * 1024 ? 2 : per_stage >= 48 * 1024 ? 3 : 4;
+  using S = WgradSmem<CWA, NA, CWB, TG, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<CWA, NA, CWB, TG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { wsl_set_error("wgrad_tc: cudaFuncSetAttribute(%d bytes): %s", S::TOTAL, cudaGetErrorString(e)); return -5; }
+    attr = true;
+  }
+  const int gy = m_tiles * (p.n_tiles0 + p.n_tiles1) * p.tap_groups;
+  int splits = (148 * 2 + gy - 1) / gy;
+  if (splits > p.nchunks) splits = p.nchunks;
+  if (splits < 1) splits = 1;
+  dim3 grid(splits, gy);
+  wgrad_tc_kernel<CWA, NA, CWB, TG, STAGES><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
+  return wsl_check_launch("wgrad_tc");
+}
+
+template <int CWA, int NA, int CWB>
+int wgrad_dispatch_tg(const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const WgradTcParams& p, int m_tiles, cudaStream_t st) {
+  if (p.ks == 3) return launch_wgrad<CWA, NA, CWB, 3>(a, b0, b1, p, m_tiles, st);
+  return launch_wgrad<CWA, NA, CWB, 1>(a, b0, b1, p, m_tiles, st);
+}
+template <int CWA, int NA>
+int wgrad_dispatch_b(int cwb, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const WgradTcParams& p, int m_tiles, cudaStream_t st) {
+  switch (cwb) {
+    case 64: return wgrad_dispatch_tg<CWA, NA, 64>(a, b0, b1, p, m_tiles, st);
+    case 32: return wgrad_dispatch_tg<CWA, NA, 32>(a, b0, b1, p, m_tiles, st);
+    default: return wgrad_dispatch_tg<CWA, NA, 16>(a, b0, b1, p, m_tiles, st);
+  }
+}
+
+// per-channel sum of a channels-last bf16 tensor, added into out[C] (bias gradients of conv1x1 / out_conv)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int Creal,
+                                                          float* __restrict__ out) {
+  extern __shared__ float s_red[];
+  const int cg = C >> 3, rows = 256 / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  float sum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+  for (long long q = (long long)blockIdx.x * rows + r; q < P; q += (long long)gridDim.x * rows) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + q * C + g * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_red[threadIdx.x * 8 + j] = sum[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < Creal; c += 256) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += s_red[(rr * cg + (c >> 3)) * 8 + (c & 7)];
+    atomicAdd(out + c, a);
+  }
+}
+
 }  // namespace
 
 WSL_API int wsl_tc_available(void) { return get_encode() != nullptr ? 1 : 0; }
@@ -409,4 +634,58 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
     case 32: return dispatch_nt<32>(a0, a1, b, p, nt, stream);
     default: return dispatch_nt<16>(a0, a1, b, p, nt, stream);
   }
+}
+
+WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                         int W, int CoutReal, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_wgrad_tc: ksize must be 1 or 3");
+  WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc: source channels must be multiples of 16 (got %d,%d)", C0, C1);
+  WSL_REQUIRE(CoutP % 16 == 0, "wsl_wgrad_tc: CoutP must be a multiple of 16");
+  WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_wgrad_tc: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
+  const int cwa = CoutP >= 64 ? 64 : CoutP;       // 16 / 32 / 64
+  WSL_REQUIRE(cwa == 16 || cwa == 32 || cwa == 64, "wsl_wgrad_tc: unsupported CoutP %d", CoutP);
+  WSL_REQUIRE(CoutP < 128 || CoutP % 128 == 0, "wsl_wgrad_tc: CoutP >= 128 must be a multiple of 128");
+  int cwb = 64;
+  while (cwb > 16 && (C0 % cwb != 0 || (C1 > 0 && C1 % cwb != 0))) cwb >>= 1;
+  const int na = CoutP >= 128 ? 2 : 1;
+  const int m_tiles = CoutP >= 128 ? CoutP / 128 : 1;
+  CUtensorMap mdy, mx0, mx1;
+  {
+    long long d[4] = {CoutP, W, H, N};
+    int bx[4] = {cwa, TILE_W, TILE_H, 1};
+    int rc = get_map(dy, 4, d, bx, cwa, &mdy);
+    if (rc) return rc;
+  }
+  {
+    long long d[4] = {C0, W, H, N};
+    int bx[4] = {cwb, TILE_W, TILE_H, 1};
+    int rc = get_map(src0, 4, d, bx, cwb, &mx0);
+    if (rc) return rc;
+  }
+  if (C1 > 0) {
+    long long d[4] = {C1, W, H, N};
+    int bx[4] = {cwb, TILE_W, TILE_H, 1};
+    int rc = get_map(src1, 4, d, bx, cwb, &mx1);
+    if (rc) return rc;
+  } else {
+    mx1 = mx0;
+  }
+  WgradTcParams p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = ksize * ksize; p.ks = ksize;
+  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.nchunks = N * p.tiles_x * p.tiles_y;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dw = dw;
+  if (cwa == 64 && na == 2) return wgrad_dispatch_b<64, 2>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
+  if (cwa == 64) return wgrad_dispatch_b<64, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
+  if (cwa == 32) return wgrad_dispatch_b<32, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
+  return wgrad_dispatch_b<16, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
+}
+
+WSL_API int wsl_channel_sum(const void* x, long long P, int C, int Creal, float* out, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && Creal <= C, "wsl_channel_sum: unsupported channel count %d", C);
+  const int rows = 256 / (C / 8);
+  long long b = (P + rows * 16 - 1) / (rows * 16);
+  if (b > 148 * 2) b = 148 * 2;
+  if (b < 1) b = 1;
+  channel_sum_kernel<<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
+  return wsl_check_launch("channel_sum");
 }

@@ -122,6 +122,7 @@ class UNetExecutor:
         self._live: List[int] = []
         self._seed_host = 0x5EED
         self.use_tc = os.environ.get("WSL4MIS_NO_TC", "0") != "1"
+        self.use_tc_wgrad = os.environ.get("WSL4MIS_NO_TC_WGRAD", "0") != "1"
         self.stats = {"launches": 0}
 
     # ---------------------------------------------------------------- buffers
@@ -199,9 +200,18 @@ class UNetExecutor:
         c0 = L.srcC[0]
         c1 = L.srcC[1] if len(L.srcC) > 1 else 0
         self._tag("wgrad", L, N, H, W, L.Cin, L.Cout)
-        call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if src_f32 else 0, dy, L.CoutP, self.gview(L.conv.weight),
-             self.gview(L.conv.bias), N, H, W, L.Cout, L.ks)
+        tc = (not src_f32 and self.use_tc_wgrad and self._tc_ok(L.srcC, H, W)
+              and (L.CoutP < 128 or L.CoutP % 128 == 0))
+        if tc:
+            call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
+        else:
+            call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if src_f32 else 0, dy, L.CoutP, self.gview(L.conv.weight),
+                 self.gview(L.conv.bias) if L.bn is None else None, N, H, W, L.Cout, L.ks)
         self._untag()
+        # Bias gradient.  A conv bias that feeds training-mode BatchNorm has an exactly-zero gradient (BN removes the
+        # per-channel mean); the reference holds ~1e-8 rounding noise there.  We leave the zero-filled bucket as is.
+        if tc and L.bn is None:
+            call("wsl_channel_sum", dy, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias))
 
     def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None):
         bn = L.bn

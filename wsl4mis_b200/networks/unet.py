@@ -108,9 +108,8 @@ class _NetFn(torch.autograd.Function):
     """Whole-network autograd node: forward = executor.forward, backward = executor.backward."""
 
     @staticmethod
-    def forward(ctx, x, holder, training, masks, chan_keep, *params):
+    def forward(ctx, x, holder, training, need, masks, chan_keep, *params):
         ex = holder.executor
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         outs, slot = ex.forward(x, training, need, masks, chan_keep)
         ctx.ex, ctx.slot, ctx.nparams = ex, slot, len(params)
         return tuple(outs)
@@ -120,7 +119,7 @@ class _NetFn(torch.autograd.Function):
         ex = ctx.ex
         ex.backward(ctx.slot, list(gouts))
         views = ex.grads()[1]
-        return (None, None, None, None, None) + tuple(views[id(p)].clone() for p in ex.params)
+        return (None, None, None, None, None, None) + tuple(views[id(p)].clone() for p in ex.params)
 
 
 class _Holder:
@@ -151,7 +150,8 @@ class _PlannedNet(nn.Module):
     def _run(self, x):
         self.executor  # build lazily
         params = list(self.parameters())
-        return _NetFn.apply(x, self._holder, self.training, self.dropout_masks, self.channel_keep, *params)
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # (grad mode is off inside Function.forward)
+        return _NetFn.apply(x, self._holder, self.training, need, self.dropout_masks, self.channel_keep, *params)
 
 
 class UNet(_PlannedNet):
