@@ -91,6 +91,12 @@ int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, int src_
 int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int CoutP,
                      float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
 
+/* first layer (Cin = 1 -> 16, unet.py:81): x fp32 [N,H,W], w fp32 torch layout [16][1][3][3], y bf16 NHWC; and its
+ * weight gradient (dw accumulated, zero-filled by the caller; the bias feeds BatchNorm -> zero gradient). */
+int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+                   cudaStream_t stream);
+int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, cudaStream_t stream);
+
 /* tcgen05 implicit-GEMM convolution (conv_tc.cu): same contract as wsl_conv_direct for bf16 NHWC sources with
  * channel counts that are multiples of 16.  wpk_bf16: [taps][CoutP][CinP] (K-major).  Requires wsl_tc_available(). */
 int wsl_tc_available(void);

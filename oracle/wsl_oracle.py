@@ -95,6 +95,38 @@ def synth_params(in_chns: int, class_num: int, decoders: Sequence[str], seed: in
 
 
 # ----------------------------------------------------------------------------------------------
+# optional storage-precision emulation (used by the GPU parity tests to separate "kernel is wrong" from
+# "bf16 storage costs precision"): QUANT rounds forward values AND the gradients flowing back through the
+# same point to bf16, at exactly the tensors the executor stores in bf16 (conv outputs Y, activations A,
+# conv1x1 output T, upsample output U, channel-dropped features) and rounds the weights of the convolutions
+# that run on the tensor cores.  QUANT = None (default) is the plain fp32 restatement of the reference.
+# ----------------------------------------------------------------------------------------------
+QUANT = None
+
+
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _q(x):
+    return x if QUANT is None else _RoundBoth.apply(x)
+
+
+def _qw(w, x):
+    """weights are bf16 on the tcgen05 path: Cin % 16 == 0 and the map is a multiple of the 8x16 pixel tile"""
+    if QUANT is None:
+        return w
+    tc = (w.shape[1] % 16 == 0) and (x.shape[-1] % 16 == 0) and (x.shape[-2] % 8 == 0)
+    return w.to(torch.bfloat16).to(w.dtype) if tc else w
+
+
+# ----------------------------------------------------------------------------------------------
 # network forward (functional)
 # ----------------------------------------------------------------------------------------------
 def _apply_elem_dropout(x, p, training, mask):
@@ -112,7 +144,7 @@ def conv_block(p, prefix, x, training, drop_p, masks=None, new_stats=None):
     -> LeakyReLU.  Running statistics are not mutated in ``p``; updated values are written to
     ``new_stats`` (dict) when given."""
     for idx, bnidx, dp in ((0, 1, drop_p), (4, 5, 0.0)):
-        x = F.conv2d(x, p[f"{prefix}.{idx}.weight"], p[f"{prefix}.{idx}.bias"], padding=1)
+        x = _q(F.conv2d(x, _qw(p[f"{prefix}.{idx}.weight"], x), p[f"{prefix}.{idx}.bias"], padding=1))
         rm = p[f"{prefix}.{bnidx}.running_mean"].clone()
         rv = p[f"{prefix}.{bnidx}.running_var"].clone()
         x = F.batch_norm(x, rm, rv, p[f"{prefix}.{bnidx}.weight"], p[f"{prefix}.{bnidx}.bias"],
@@ -123,6 +155,7 @@ def conv_block(p, prefix, x, training, drop_p, masks=None, new_stats=None):
         x = F.leaky_relu(x, LRELU)
         if dp > 0.0:
             x = _apply_elem_dropout(x, dp, training, None if masks is None else masks.get(f"{prefix}.3"))
+        x = _q(x)
     return x
 
 
@@ -141,11 +174,11 @@ def decoder_forward(p, dname, feats, training, new_stats=None):
     conv1x1 -> bilinear x2 (align_corners=True) -> cat([skip, up]) -> ConvBlock(p=0)."""
     x = feats[4]
     for j, skip in enumerate((feats[3], feats[2], feats[1], feats[0]), 1):
-        t = F.conv2d(x, p[f"{dname}.up{j}.conv1x1.weight"], p[f"{dname}.up{j}.conv1x1.bias"])
-        t = F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
+        t = _q(F.conv2d(x, _qw(p[f"{dname}.up{j}.conv1x1.weight"], x), p[f"{dname}.up{j}.conv1x1.bias"]))
+        t = _q(F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True))
         x = conv_block(p, f"{dname}.up{j}.conv.conv_conv", torch.cat([skip, t], 1), training, 0.0,
                        None, new_stats)
-    return F.conv2d(x, p[f"{dname}.out_conv.weight"], p[f"{dname}.out_conv.bias"], padding=1)
+    return F.conv2d(x, _qw(p[f"{dname}.out_conv.weight"], x), p[f"{dname}.out_conv.bias"], padding=1)
 
 
 def unet_forward(p, x, training=True, masks=None, new_stats=None):
@@ -158,7 +191,7 @@ def channel_dropout(x, keep):
     per-(n,c) Bernoulli keep mask, survivors scaled by 2.  ``keep`` is a [N,C] 0/1 tensor."""
     if keep is None:
         return F.dropout2d(x, 0.5)
-    return x * (keep.to(x.dtype) * 2.0)[:, :, None, None]
+    return _q(x * (keep.to(x.dtype) * 2.0)[:, :, None, None])
 
 
 def unet_cct_forward(p, x, training=True, masks=None, chan_keep=None, new_stats=None):

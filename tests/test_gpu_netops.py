@@ -177,7 +177,28 @@ def test_wgrad_tc(case):
     assert rel_l2(dw.cpu(), 2 * gw.float()) < 1e-4
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 16), (3, 8, 24, 64), (1, 4, 4, 256), (2, 32, 32, 32)])
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 24, 40), (1, 7, 9)])
+def test_first_layer_kernels(shape):
+    N, H, W = shape
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(N, 1, H, W, generator=g)
+    w = torch.randn(16, 1, 3, 3, generator=g) * 0.5
+    b = torch.randn(16, generator=g) * 0.1
+    y = torch.zeros((N, H, W, 16), device=DEV, dtype=BF)
+    call("wsl_conv_first", x.to(DEV), w.to(DEV), b.to(DEV), y, N, H, W, 16)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, b, padding=1)
+    assert (nchw(y.cpu()) - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    dy = bf16_round(torch.randn(N, 16, H, W, generator=g))
+    dw = torch.zeros(16, 1, 3, 3, device=DEV)
+    call("wsl_wgrad_first", x.to(DEV), nhwc(dy).to(DEV), dw, N, H, W, 16)
+    torch.cuda.synchronize()
+    wz = torch.zeros(16, 1, 3, 3, dtype=torch.double, requires_grad=True)
+    (gw,) = torch.autograd.grad(F.conv2d(x.double(), wz, None, padding=1), wz, dy.double())
+    assert rel_l2(dw.cpu(), gw.float()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 16), (3, 8, 24, 64), (1, 4, 4, 256), (2, 32, 32, 32), (8, 64, 64, 16)])
 def test_bn_stats_and_act(shape):
     N, H, W, C = shape
     g = torch.Generator().manual_seed(2)

@@ -17,7 +17,7 @@ int  wsl_check_launch(const char* what);
   } while (0)
 
 constexpr int WSL_MAX_PARTIAL_BLOCKS = 2048;   // every reduction kernel launches <= this many CTAs
-constexpr int WSL_WS_FLOATS = 1 << 18;  // per-call workspace (floats, 1 MiB), zero-initialised once; [0,64) tickets, rest partials
+constexpr int WSL_WS_FLOATS = 1 << 20;  // per-call workspace (floats, 4 MiB), zero-initialised once; [0,64) tickets, rest partials
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

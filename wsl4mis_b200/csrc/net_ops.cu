@@ -114,6 +114,75 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
   }
 }
 
+
+// ================================================================================================
+// first layer (Cin = 1, unet.py:81 in_conv): x fp32 [N,H,W] -> y bf16 [N,H,W,16]; HBM-bound (36 B/pixel)
+// ================================================================================================
+__global__ void __launch_bounds__(TPB) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][9]*/,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                         int N, int H, int W) {
+  __shared__ float s_w[9][16];
+  __shared__ float s_b[16];
+  if (threadIdx.x < 144) s_w[threadIdx.x % 9][threadIdx.x / 9] = w[threadIdx.x];
+  if (threadIdx.x < 16) s_b[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int xx = (int)(i % W), yy = (int)((i / W) % H);
+    const float* base = x + (i - (long long)yy * W - xx);
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
+      v[t] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
+    }
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = s_b[c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[c] = fmaf(v[t], s_w[t][c], o[c]);
+    float lo[8], hi[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { lo[c] = o[c]; hi[c] = o[8 + c]; }
+    uint4* dst = reinterpret_cast<uint4*>(y + i * 16);
+    dst[0] = pack8(lo);
+    dst[1] = pack8(hi);
+  }
+}
+
+// dW[co][t] += sum_p dY[p][co] * x[p + tap_t]; block = 16 co x 16 pixel lanes, 9 accumulators per thread
+__global__ void __launch_bounds__(TPB) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                          float* __restrict__ dw /*[16][9]*/, int N, int H, int W) {
+  const int co = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const long long total = (long long)N * H * W;
+  for (long long i = (long long)blockIdx.x * 16 + pl; i < total; i += (long long)gridDim.x * 16) {
+    const int xx = (int)(i % W), yy = (int)((i / W) % H);
+    const float* base = x + (i - (long long)yy * W - xx);
+    const float g = __bfloat162float(dy[i * 16 + co]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
+      const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
+      acc[t] = fmaf(g, v, acc[t]);
+    }
+  }
+  __shared__ float s_a[16][16][9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) s_a[pl][co][t] = acc[t];
+  __syncthreads();
+  if (threadIdx.x < 144) {
+    const int c = threadIdx.x / 9, t = threadIdx.x % 9;
+    float r = 0.f;
+    for (int q = 0; q < 16; ++q) r += s_a[q][c][t];
+    atomicAdd(dw + c * 9 + t, r);
+  }
+}
+
 // ================================================================================================
 // direct weight gradient:  dW[co][ci][dy][dx] = sum_{n,y,x} dY[n,y,x,co] * X[n,y+dy-P,x+dx-P,ci]
 // CTA = 16 co x 16 ci x all taps, 256 threads (co = t%16, ci = t/16); loops over 8x16 pixel tiles of its split,
@@ -193,6 +262,37 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(
   if (dbias != nullptr && cib == 0 && ci == 0 && cob + co < CoutReal) atomicAdd(dbias + cob + co, bsum);
 }
 
+
+// Fixed-order sum of per-block partials [nblocks][2][C] for all channels with all 256 threads:
+// thread t handles channel t % CP (CP = C rounded up to a power of two <= 256) and block subset t / CP.
+// Results (double) land in s_fin[2][C].
+__device__ __forceinline__ void bn_finalize_partials(const float* partials, int nblocks, int C, double* s_fin /*[2*C]*/,
+                                                     double* s_part /*[TPB*2]*/) {
+  for (int cbase = 0; cbase < C; cbase += TPB) {
+    const int cw = min(C - cbase, TPB);
+    int parts = TPB / cw;                       // threads per channel
+    const int c = cbase + (int)(threadIdx.x % cw);
+    const int part = threadIdx.x / cw;
+    double a = 0.0, b = 0.0;
+    if (part < parts) {
+      for (int bl = part; bl < nblocks; bl += parts) {
+        a += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
+        b += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
+      }
+    }
+    s_part[threadIdx.x * 2 + 0] = a;
+    s_part[threadIdx.x * 2 + 1] = b;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      double x = 0.0, y = 0.0;
+      for (int q = 0; q < parts; ++q) { x += s_part[(q * cw + threadIdx.x) * 2]; y += s_part[(q * cw + threadIdx.x) * 2 + 1]; }
+      s_fin[c] = x;
+      s_fin[C + c] = y;
+    }
+    __syncthreads();
+  }
+}
+
 // ================================================================================================
 // BatchNorm (training): per-channel statistics over N*H*W of a channels-last bf16 tensor
 // ================================================================================================
@@ -235,12 +335,11 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  __shared__ double s_fin[2 * 256];
+  __shared__ double s_part[TPB * 2];
+  bn_finalize_partials(partials, gridDim.x, C, s_fin, s_part);
   for (int c = threadIdx.x; c < C; c += TPB) {
-    double a = 0.0, b = 0.0;
-    for (int bl = 0; bl < (int)gridDim.x; ++bl) {
-      a += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
-      b += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
-    }
+    const double a = s_fin[c], b = s_fin[C + c];
     const double mean = a / (double)P;
     double var = b / (double)P - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -450,12 +549,11 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  __shared__ double s_fin[2 * 256];
+  __shared__ double s_part[TPB * 2];
+  bn_finalize_partials(partials, gridDim.x, C, s_fin, s_part);
   for (int c = threadIdx.x; c < C; c += TPB) {
-    double x = 0.0, y = 0.0;
-    for (int bl = 0; bl < (int)gridDim.x; ++bl) {
-      x += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
-      y += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
-    }
+    const double x = s_fin[c], y = s_fin[C + c];
     dbeta[c] = (float)x;
     dgamma[c] = (float)y;
     coef[c] = (float)(x / (double)P);
@@ -658,9 +756,9 @@ inline int grid_for(long long items) {
 
 inline int bn_grid(long long P, int C) {
   const int rows = TPB / (C / 8);
-  long long b = (P + (long long)rows * 8 - 1) / ((long long)rows * 8);
+  long long b = (P + (long long)rows * 4 - 1) / ((long long)rows * 4);
   if (b < 1) b = 1;
-  if (b > 296) b = 296;
+  if (b > 148 * 6) b = 148 * 6;
   return (int)b;
 }
 
@@ -706,7 +804,7 @@ WSL_API int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1,
 WSL_API int wsl_bn_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
                          float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
                          float* ss, float* ws, cudaStream_t stream) {
-  WSL_REQUIRE(C % 8 == 0 && C <= 2048 && TPB % (C / 8) == 0, "wsl_bn_stats: unsupported channel count %d", C);
+  WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_stats: unsupported channel count %d", C);
   const int grid = bn_grid(P, C);
   WSL_REQUIRE((long long)grid * 2 * C + 64 <= WSL_WS_FLOATS, "wsl_bn_stats: workspace too small");
   bn_stats_kernel<<<grid, TPB, TPB * 16 * sizeof(float), stream>>>((const __nv_bfloat16*)y, P, C, gamma, beta, running_mean,
@@ -736,7 +834,7 @@ WSL_API int wsl_bn_bwd(const void* y, const float* ss, const float* save, const 
                        const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                        const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
                        cudaStream_t stream) {
-  WSL_REQUIRE(C % 8 == 0 && TPB % (C / 8) == 0, "wsl_bn_bwd: unsupported channel count %d", C);
+  WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_bwd: unsupported channel count %d", C);
   BnBwdArgs a;
   a.y = (const __nv_bfloat16*)y; a.ss = ss; a.save = save; a.g0 = (const __nv_bfloat16*)g0; a.g1 = (const __nv_bfloat16*)g1;
   a.cs1 = cs1; a.gp = (const __nv_bfloat16*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
@@ -803,4 +901,20 @@ WSL_API int wsl_sgd_step(float* param, const float* grad, float* mom, long long 
                          float momentum, float weight_decay, float grad_scale, cudaStream_t stream) {
   sgd_kernel<<<grid_for(n), TPB, 0, stream>>>(param, grad, mom, n, lr_ptr, lr, momentum, weight_decay, grad_scale);
   return wsl_check_launch("sgd_step");
+}
+
+WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+                           cudaStream_t stream) {
+  WSL_REQUIRE(Cout == 16, "wsl_conv_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
+  conv_first_kernel<<<grid_for((long long)N * H * W), TPB, 0, stream>>>(x, w, bias, (__nv_bfloat16*)y, N, H, W);
+  return wsl_check_launch("conv_first");
+}
+
+WSL_API int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, cudaStream_t stream) {
+  WSL_REQUIRE(Cout == 16, "wsl_wgrad_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
+  long long b = ((long long)N * H * W + 16 * 64 - 1) / (16 * 64);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  wgrad_first_kernel<<<(int)b, TPB, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
+  return wsl_check_launch("wgrad_first");
 }

@@ -176,7 +176,9 @@ class UNetExecutor:
         c0 = L.srcC[0]
         c1 = L.srcC[1] if len(L.srcC) > 1 else 0
         self._tag("fwd", L, N, H, W, L.Cin, L.Cout)
-        if not src_f32 and self._tc_ok(L.srcC, H, W):
+        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode == 0:
+            call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, N, H, W, L.Cout)
+        elif not src_f32 and self._tc_ok(L.srcC, H, W):
             call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         else:
             call("wsl_conv_direct", s0, c0, s1, c1, 1 if src_f32 else 0, pk["wf"], pk["bias"], out, out_mode, N, H, W,
@@ -202,7 +204,9 @@ class UNetExecutor:
         self._tag("wgrad", L, N, H, W, L.Cin, L.Cout)
         tc = (not src_f32 and self.use_tc_wgrad and self._tc_ok(L.srcC, H, W)
               and (L.CoutP < 128 or L.CoutP % 128 == 0))
-        if tc:
+        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and L.bn is not None:
+            call("wsl_wgrad_first", s0, dy, self.gview(L.conv.weight), N, H, W, L.Cout)
+        elif tc:
             call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         else:
             call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if src_f32 else 0, dy, L.CoutP, self.gview(L.conv.weight),
