@@ -57,11 +57,19 @@ def load_peaks():
 def cpu_step_time(model_name, variant, n_img, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import wsl_oracle as O
+    O.CRF_IMPL = "unfold"          # time the reference's own (materialising) GatedCRF formulation
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
+    try:  # honour a cgroup CPU quota (oversubscribing a quota-limited container is catastrophically slow)
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            cores = max(1, min(cores, int(float(q) / float(per))))
+    except Exception:
+        pass
+    cores = min(cores, 64)   # torch CPU ops stop scaling (and start thrashing) far below 128 threads on these sizes
     torch.set_num_threads(cores)
     cct = model_name == "unet_cct"
     decs = ("main_decoder", "aux_decoder1") if cct else ("decoder",)

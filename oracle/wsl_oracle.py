@@ -246,6 +246,26 @@ def gated_crf_loss(y, image, radius=5, sigma_xy=6.0, sigma_rgb=0.1, weight=1.0):
     return (ksum - pair) / (N * H * W)                                                  # :63, :97-99, :116
 
 
+def gated_crf_loss_unfold(y, image, radius=5, sigma_xy=6.0, sigma_rgb=0.1, weight=1.0):
+    """Same quantity as ``gated_crf_loss`` computed the way the reference does it (utils/gate_crf_loss.py:59-99,
+    134-188): im2col (F.unfold, zero padded) of the scaled features and of the predictions, Gaussian of the
+    feature differences with the centre tap zeroed, Potts shortcut.  This is the formulation timed as the CPU
+    baseline (it is the reference's own algorithm and memory behaviour: the (2r+1)^2-fold unfold is materialised)."""
+    N, C, H, W = y.shape
+    d = 2 * radius + 1
+    dt = y.dtype
+    xs = torch.arange(W, dtype=dt).view(1, 1, 1, W).expand(N, 1, H, W) / sigma_xy
+    ys = torch.arange(H, dtype=dt).view(1, 1, H, 1).expand(N, 1, H, W) / sigma_xy
+    feat = torch.cat([xs, ys, F.adaptive_avg_pool2d(image.to(dt), (H, W)) / sigma_rgb], 1)
+    fu = F.unfold(feat, d, 1, radius).view(N, 3, d, d, H, W)
+    diff = fu - fu[:, :, radius, radius].view(N, 3, 1, 1, H, W)
+    k = weight * torch.exp((-0.5 * diff * diff).sum(1, keepdim=True))
+    k[:, :, radius, radius] = 0
+    yu = F.unfold(y, d, 1, radius).view(N, C, d, d, H, W)
+    prod = (k * yu).view(N, C, d * d, H, W).sum(2)
+    return (k.sum() - (prod * y).sum()) / (N * H * W)
+
+
 def mumford_shah_loss(image, prob):
     """MumfordShah_Loss.forward(image, prediction), utils/losses.py:275-309, as written: the image is
     passed as ``output`` and the softmax as ``target``."""
@@ -317,11 +337,14 @@ def softmax_mse(a_logits, b_logits):
 # ----------------------------------------------------------------------------------------------
 # step bodies (loss composition) and the optimiser
 # ----------------------------------------------------------------------------------------------
+CRF_IMPL = "loop"   # "unfold" = the reference's materialising formulation (used for CPU timing)
+
+
 def step_loss_pce_gatedcrf(logits, image, label):
     """train_weakly_supervised_pCE_GatedCRFLoss_2D.py:111-123."""
     soft = torch.softmax(logits, 1)
     ce = pce_loss(logits, label)
-    crf = gated_crf_loss(soft, image)
+    crf = gated_crf_loss_unfold(soft, image) if CRF_IMPL == "unfold" else gated_crf_loss(soft, image)
     return ce + 0.1 * crf, ce, crf
 
 
