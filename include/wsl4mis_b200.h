@@ -103,6 +103,11 @@ int wsl_tc_available(void);
 int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
                 void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
                 cudaStream_t stream);
+/* v2 of the same convolution: persistent CTAs, weights resident in shared memory, one halo load per pixel tile whose
+ * nine taps are row-shifted UMMA descriptor views (no reload).  Same contract; needs W % 8 == 0 and H % 16 == 0. */
+int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
+                 void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
+                 cudaStream_t stream);
 /* tcgen05 weight gradient (conv_tc.cu): dw (fp32, torch layout [CoutReal][C0+C1][k][k]) += dY^T * X over all pixels.
  * Bias gradients are NOT produced here (see wsl_channel_sum). */
 int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,

@@ -43,13 +43,19 @@ CONV_CASES = [
     (1, 16, 16, 128, 0, 128, 3), (1, 8, 16, 256, 0, 256, 3), (1, 16, 16, 128, 128, 128, 3), (2, 16, 16, 16, 16, 16, 3),
     (1, 32, 32, 32, 32, 32, 3), (1, 8, 16, 256, 0, 128, 1), (2, 16, 16, 32, 0, 16, 1), (1, 32, 32, 16, 0, 4, 3),
     (3, 8, 16, 64, 64, 64, 3),
+    # shapes that exercise the multi-sub-tile (MT = 2, 4) persistent v2 kernel and several tiles per CTA
+    (2, 64, 32, 16, 0, 16, 3), (1, 64, 64, 16, 16, 16, 3), (2, 32, 16, 32, 0, 64, 3), (1, 32, 32, 32, 32, 32, 3),
+    (2, 32, 32, 64, 0, 128, 3), (1, 16, 16, 256, 0, 256, 3), (1, 32, 32, 128, 128, 128, 3), (1, 64, 64, 16, 0, 4, 3),
+    (2, 16, 16, 256, 0, 128, 1), (2, 64, 64, 32, 0, 16, 1),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("path", ["direct", "tc"])
+@pytest.mark.parametrize("path", ["direct", "tc", "tc2"])
 def test_conv_forward(case, path):
     N, H, W, C0, C1, Cout, ks = case
+    if path == "tc2" and (H % 16 or W % 8):
+        pytest.skip("v2 tile is 8x16")
     g = torch.Generator().manual_seed(hash(case) % 1000)
     x0 = bf16_round(torch.randn(N, C0, H, W, generator=g))
     x1 = bf16_round(torch.randn(N, C1, H, W, generator=g)) if C1 else None
@@ -64,8 +70,9 @@ def test_conv_forward(case, path):
     s1 = nhwc(x1).to(DEV) if C1 else None
     fp32_out = Cout == 4
     out = torch.zeros((N, Cout, H, W), device=DEV) if fp32_out else torch.zeros((N, H, W, Cout), device=DEV, dtype=BF)
-    if path == "tc":
-        call("wsl_conv_tc", s0, C0, s1, C1, pk["bf"], bias, out, 1 if fp32_out else 0, N, H, W, CoutP, Cout, ks)
+    if path in ("tc", "tc2"):
+        call("wsl_conv_tc2" if path == "tc2" else "wsl_conv_tc", s0, C0, s1, C1, pk["bf"], bias, out, 1 if fp32_out else 0,
+             N, H, W, CoutP, Cout, ks)
         wref = bf16_round(w)   # tensor-core path multiplies bf16 weights
     else:
         call("wsl_conv_direct", s0, C0, s1, C1, 0, pk["wf"], bias, out, 1 if fp32_out else 0, N, H, W, pk["CinP"], CoutP, Cout, ks)
@@ -80,9 +87,11 @@ def test_conv_forward(case, path):
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 16, 16, 16, 3), (1, 16, 16, 128, 128, 128, 3), (1, 8, 16, 256, 0, 128, 1),
                                   (1, 16, 32, 16, 0, 4, 3), (2, 16, 16, 32, 0, 64, 3)])
-@pytest.mark.parametrize("path", ["direct", "tc"])
+@pytest.mark.parametrize("path", ["direct", "tc", "tc2"])
 def test_conv_dgrad(case, path):
     N, H, W, C0, C1, Cout, ks = case
+    if path == "tc2" and (H % 16 or W % 8):
+        pytest.skip("v2 tile is 8x16")
     g = torch.Generator().manual_seed(11)
     Cin = C0 + C1
     w = torch.randn(Cout, Cin, ks, ks, generator=g) / np.sqrt(Cin * ks * ks)
@@ -91,14 +100,14 @@ def test_conv_dgrad(case, path):
     dy[:, :Cout] = bf16_round(torch.randn(N, Cout, H, W, generator=g))
     pk = _pack(w.to(DEV), [C0, C1] if C1 else [C0])
     dyd = nhwc(dy).to(DEV)
-    wr = bf16_round(w) if path == "tc" else w
+    wr = bf16_round(w) if path != "direct" else w
     ref = F.conv_transpose2d(dy[:, :Cout].double(), wr.double(), padding=ks // 2).float()
     beg = 0
     for i, c in enumerate([C0, C1] if C1 else [C0]):
         sp = (c + 15) // 16 * 16
         out = torch.zeros((N, H, W, c), device=DEV, dtype=BF)
-        if path == "tc":
-            call("wsl_conv_tc", dyd, CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, c, ks)
+        if path != "direct":
+            call("wsl_conv_tc2" if path == "tc2" else "wsl_conv_tc", dyd, CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, c, ks)
         else:
             call("wsl_conv_direct", dyd, CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, CoutP, sp, c, ks)
         torch.cuda.synchronize()

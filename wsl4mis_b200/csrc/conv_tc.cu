@@ -20,6 +20,7 @@
 #include <unordered_map>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -366,6 +367,204 @@ int dispatch_nt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
 
 
 // ================================================================================================
+// conv_tc v2: persistent, weights resident in shared memory, ONE halo load per (tile, k-block)
+//
+//   * pixel tile = 8 w x (16*MT) h  (MT accumulators of M = 128 rows, row m = h*8 + w);
+//   * A: one TMA box (KBLK channels x 10 w x (16*MT+2) h) per k-block -- the 3x3 halo.  The nine taps are NOT
+//     reloaded: tap (dy,dx) of sub-tile j is the same shared-memory tile viewed through a UMMA descriptor whose
+//     start address is shifted by ((16*j+dy)*10 + dx) rows and whose 8-row-group stride (SBO) is one halo row
+//     (10 pixels).  The 128B/64B/32B swizzle is a function of the absolute shared-memory address (TMA writes and
+//     tcgen05 reads agree), so a row-shifted start keeps the pattern consistent.
+//   * B: the CTA's whole weight slice [taps][k-blocks][NT x KBLK] is loaded once (it fits: NT is chosen on the
+//     host so that taps*Cin*NT*2 <= ~148 KB) and stays resident while the CTA walks its pixel tiles.
+//   * TMEM: two sets of MT*NT fp32 columns; the epilogue of tile i overlaps the MMAs of tile i+1.
+// L2->SM traffic per output pixel drops from 9*(Cin + NT)*2 B (v1) to ~1.4*Cin*2 B.
+// ================================================================================================
+template <int SW>
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
+  constexpr uint64_t layout = (SW == 128) ? 2 : (SW == 64) ? 4 : 6;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= layout << 61;
+  return d;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct ConvV2Params {
+  int N, H, W;
+  int C0, C1;
+  int CoutP, CoutStore;
+  int tiles_x, tiles_y, ntiles;
+  int out_mode;
+  int desc_mode;
+  const float* bias;
+  void* out;
+};
+
+template <int KS, int KBLK, int NT, int MT>
+struct ConvV2Cfg {
+  static constexpr int PAD = KS / 2;
+  static constexpr int TW = 8, TH = 16 * MT;
+  static constexpr int HW_ = TW + 2 * PAD, HH_ = TH + 2 * PAD;
+  static constexpr int ROWB = KBLK * 2;
+  static constexpr int HALO_BYTES = HW_ * HH_ * ROWB;
+  static constexpr int A_STAGE = ((HALO_BYTES + 1023) / 1024) * 1024;
+  static constexpr int W_SUB = NT * ROWB;                  // one (tap, k-block) weight tile
+  static constexpr uint32_t TMEM_COLS = (2 * MT * NT <= 32) ? 32 : (2 * MT * NT <= 64) ? 64 : (2 * MT * NT <= 128) ? 128
+                                        : (2 * MT * NT <= 256) ? 256 : 512;
+};
+
+template <int KS, int KBLK, int NT, int MT, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0,
+                                                               const __grid_constant__ CUtensorMap map_a1,
+                                                               const __grid_constant__ CUtensorMap map_b, const ConvV2Params p,
+                                                               const int w_bytes) {
+  using Cfg = ConvV2Cfg<KS, KBLK, NT, MT>;
+  constexpr int SW = KBLK * 2, T = KS * KS;
+  static_assert(2 * MT * NT <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_smem = smem;
+  uint8_t* a_smem = smem + w_bytes;                         // w_bytes is a multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + STAGES * Cfg::A_STAGE);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;
+  uint64_t* w_bar = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * NT;
+  const int kb0 = p.C0 / KBLK, nkb = kb0 + p.C1 / KBLK;
+  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_a0);
+    prefetch_tmap(&map_b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, (uint32_t)(T * nkb * Cfg::W_SUB));
+      for (int t = 0; t < T; ++t)
+        for (int kb = 0; kb < nkb; ++kb) tma_load_3d(&map_b, w_bar, w_smem + (t * nkb + kb) * Cfg::W_SUB, kb * KBLK, n0, t);
+      int it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int n = tile / (p.tiles_x * p.tiles_y);
+        const int tr = tile - n * p.tiles_x * p.tiles_y;
+        const int y0 = (tr / p.tiles_x) * Cfg::TH, x0 = (tr % p.tiles_x) * Cfg::TW;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&a_empty[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&a_full[s], Cfg::HALO_BYTES);
+          if (kb < kb0) tma_load_4d(&map_a0, &a_full[s], a_smem + s * Cfg::A_STAGE, kb * KBLK, x0 - Cfg::PAD, y0 - Cfg::PAD, n);
+          else          tma_load_4d(&map_a1, &a_full[s], a_smem + s * Cfg::A_STAGE, (kb - kb0) * KBLK, x0 - Cfg::PAD, y0 - Cfg::PAD, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(NT);
+    mbar_wait(w_bar, 0);
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int acc = i & 1;
+      mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&a_full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(a_smem + s * Cfg::A_STAGE);
+          const uint32_t w_base = smem_u32(w_smem);
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const int dy = t / KS, dx = t % KS;
+              const uint32_t a_addr = a_base + (uint32_t)(((16 * j + dy) * Cfg::HW_ + dx) * Cfg::ROWB);
+              const uint64_t adesc = make_kmajor_desc_sbo<SW>(a_addr, Cfg::HW_ * Cfg::ROWB, p.desc_mode);
+              const uint64_t bdesc = make_kmajor_desc_sbo<SW>(w_base + (uint32_t)((t * nkb + kb) * Cfg::W_SUB), 8 * SW, 0);
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k)
+                umma_f16(tmem_base + (uint32_t)((acc * MT + j) * NT), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                         (kb > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[s]);
+          if (kb == nkb - 1) umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / (p.tiles_x * p.tiles_y);
+      const int tr = tile - n * p.tiles_x * p.tiles_y;
+      const int y0 = (tr / p.tiles_x) * Cfg::TH, x0 = (tr % p.tiles_x) * Cfg::TW;
+      const int acc = i & 1;
+      mbar_wait(&acc_full[acc], (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int gy = y0 + 16 * j + m / 8, gx = x0 + (m & 7);
+#pragma unroll 1
+        for (int c = 0; c < NT; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + j) * NT + c), v);
+          if (p.bias) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) v[jj] += p.bias[n0 + c + jj];
+          }
+          if (p.out_mode == 0) {
+            if (n0 + c < p.CoutStore) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)n * p.H + gy) * p.W + gx) * p.CoutStore + n0 + c;
+              float lo[8], hi[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) { lo[jj] = v[jj]; hi[jj] = v[8 + jj]; }
+              reinterpret_cast<uint4*>(o)[0] = pack8(lo);
+              if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              if (n0 + c + jj < p.CoutStore) o[(((long long)n * p.CoutStore + n0 + c + jj) * p.H + gy) * p.W + gx] = v[jj];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ================================================================================================
 // tcgen05 weight gradient:  dW[co][ci][t] += sum_{pixels} dY[p][co] * X[p + tap_t][ci]
 //
 //   D_t[M = 128 couts, N = CWB cins] (fp32, TMEM) += A^T[K = 128 pixels x M] * B_t[K = 128 pixels x N]
@@ -589,6 +788,48 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* _
   }
 }
 
+
+template <int KS, int KBLK, int NT, int MT>
+int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvV2Params& p, cudaStream_t stream) {
+  using Cfg = ConvV2Cfg<KS, KBLK, NT, MT>;
+  constexpr int STAGES = (Cfg::A_STAGE <= 8 * 1024) ? 4 : (Cfg::A_STAGE <= 13 * 1024) ? 3 : 2;
+  const int T = KS * KS;
+  const int nkb = (p.C0 + p.C1) / KBLK;
+  const int w_bytes = ((T * nkb * Cfg::W_SUB + 1023) / 1024) * 1024;
+  const int smem = w_bytes + STAGES * Cfg::A_STAGE + 1024 + 256;
+  if (smem > 227 * 1024) { wsl_set_error("conv_tc2: %d bytes of shared memory needed", smem); return -6; }
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<KS, KBLK, NT, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { wsl_set_error("conv_tc2: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return -5; }
+    attr_bytes = smem;
+  }
+  const int n_tiles = p.CoutP / NT;
+  int occ = (220 * 1024) / smem;
+  const int occ_tmem = 512 / (int)Cfg::TMEM_COLS;
+  if (occ > occ_tmem) occ = occ_tmem;
+  if (occ > 4) occ = 4;
+  if (occ < 1) occ = 1;
+  int gx = (148 * occ) / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > p.ntiles) gx = p.ntiles;
+  dim3 grid(gx, n_tiles);
+  conv_tc2_kernel<KS, KBLK, NT, MT, STAGES><<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p, w_bytes);
+  return wsl_check_launch("conv_tc2");
+}
+
+template <int KS, int KBLK, int MT>
+int conv2_dispatch_nt(int nt, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvV2Params& p, cudaStream_t st) {
+  switch (nt) {
+    case 16:  return launch_conv2<KS, KBLK, 16, MT>(a0, a1, b, p, st);
+    case 32:  return launch_conv2<KS, KBLK, 32, MT>(a0, a1, b, p, st);
+    case 64:  return launch_conv2<KS, KBLK, 64, MT>(a0, a1, b, p, st);
+    case 128: if constexpr (MT <= 2) return launch_conv2<KS, KBLK, 128, MT>(a0, a1, b, p, st); else break;
+  }
+  wsl_set_error("conv_tc2: unsupported N tile %d", nt);
+  return -1;
+}
+
 }  // namespace
 
 WSL_API int wsl_tc_available(void) { return get_encode() != nullptr ? 1 : 0; }
@@ -688,4 +929,65 @@ WSL_API int wsl_channel_sum(const void* x, long long P, int C, int Creal, float*
   if (b < 1) b = 1;
   channel_sum_kernel<<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
   return wsl_check_launch("channel_sum");
+}
+
+// conv_tc v2 entry point (same contract as wsl_conv_tc; needs W % 8 == 0 and H % (16*MT) == 0)
+WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+                         int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc2: ksize must be 1 or 3");
+  WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc2: source channels must be multiples of 16 (got %d,%d)", C0, C1);
+  WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc2: CoutP must be a multiple of 16");
+  int kblk = 64;
+  while (kblk > 16 && (C0 % kblk != 0 || (C1 > 0 && C1 % kblk != 0))) kblk >>= 1;
+  int mt = kblk == 64 ? 1 : kblk == 32 ? 2 : 4;
+  while (mt > 1 && H % (16 * mt) != 0) mt >>= 1;
+  WSL_REQUIRE(W % 8 == 0 && H % (16 * mt) == 0, "wsl_conv_tc2: H,W must be multiples of the 16x8 pixel tile (got %dx%d)", H, W);
+  const int CinP = C0 + C1, T = ksize * ksize;
+  // N tile: largest of 128/64/32/16 dividing CoutP whose resident weight slice fits (~148 KB) and TMEM (2*MT*NT <= 512)
+  int nt = CoutP >= 128 ? 128 : CoutP;
+  while (nt > 16 && (CoutP % nt != 0 || (long long)T * CinP * nt * 2 > 148 * 1024 || 2 * mt * nt > 512 || (nt == 128 && mt > 2))) nt >>= 1;
+  WSL_REQUIRE(CoutP % nt == 0 && (long long)T * CinP * nt * 2 <= 152 * 1024, "wsl_conv_tc2: weights do not fit (Cin %d, NT %d)", CinP, nt);
+  static int desc_mode = -1;
+  if (desc_mode < 0) { const char* e = getenv("WSL_HALO_DESC_MODE"); desc_mode = e ? atoi(e) : 0; }
+  const int pad = ksize / 2;
+  CUtensorMap a0, a1, b;
+  {
+    long long d[4] = {C0, W, H, N};
+    int bx[4] = {kblk, 8 + 2 * pad, 16 * mt + 2 * pad, 1};
+    int rc = get_map(src0, 4, d, bx, kblk, &a0);
+    if (rc) return rc;
+  }
+  if (C1 > 0) {
+    long long d[4] = {C1, W, H, N};
+    int bx[4] = {kblk, 8 + 2 * pad, 16 * mt + 2 * pad, 1};
+    int rc = get_map(src1, 4, d, bx, kblk, &a1);
+    if (rc) return rc;
+  } else {
+    a1 = a0;
+  }
+  {
+    long long d[3] = {CinP, CoutP, T};
+    int bx[3] = {kblk, nt, 1};
+    int rc = get_map(wpk_bf16, 3, d, bx, kblk, &b);
+    if (rc) return rc;
+  }
+  ConvV2Params p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore;
+  p.tiles_x = W / 8; p.tiles_y = H / (16 * mt); p.ntiles = N * p.tiles_x * p.tiles_y;
+  p.out_mode = out_mode; p.desc_mode = desc_mode; p.bias = bias; p.out = out;
+#define WSL_C2(KS_, KB_, MT_) return conv2_dispatch_nt<KS_, KB_, MT_>(nt, a0, a1, b, p, stream)
+  if (ksize == 3) {
+    if (kblk == 64) WSL_C2(3, 64, 1);
+    if (kblk == 32) { if (mt == 2) WSL_C2(3, 32, 2); WSL_C2(3, 32, 1); }
+    if (mt == 4) WSL_C2(3, 16, 4);
+    if (mt == 2) WSL_C2(3, 16, 2);
+    WSL_C2(3, 16, 1);
+  } else {
+    if (kblk == 64) WSL_C2(1, 64, 1);
+    if (kblk == 32) { if (mt == 2) WSL_C2(1, 32, 2); WSL_C2(1, 32, 1); }
+    if (mt == 4) WSL_C2(1, 16, 4);
+    if (mt == 2) WSL_C2(1, 16, 2);
+    WSL_C2(1, 16, 1);
+  }
+#undef WSL_C2
 }
