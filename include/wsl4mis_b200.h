@@ -112,6 +112,9 @@ int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void*
  * Bias gradients are NOT produced here (see wsl_channel_sum). */
 int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                  int W, int CoutReal, int ksize, cudaStream_t stream);
+/* v2 of the 3x3 weight gradient: one halo load of X per 16x8 pixel chunk, nine row-shifted descriptor views. */
+int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                  int W, int CoutReal, int ksize, cudaStream_t stream);
 /* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
 int wsl_channel_sum(const void* x, long long P, int C, int Creal, float* out, cudaStream_t stream);
 

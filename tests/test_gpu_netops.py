@@ -156,10 +156,19 @@ WGRAD_TC_CASES = [
 ]
 
 
+WGRAD_TC_CASES += [(2, 32, 32, 16, 0, 16, 3), (1, 64, 32, 32, 32, 32, 3), (2, 32, 16, 64, 0, 128, 3), (1, 32, 32, 128, 128, 128, 3),
+                   (1, 16, 16, 256, 0, 256, 3), (2, 32, 32, 16, 0, 4, 3), (1, 48, 24, 32, 0, 64, 3)]
+
+
 @pytest.mark.parametrize("case", WGRAD_TC_CASES)
-def test_wgrad_tc(case):
+@pytest.mark.parametrize("ver", ["wsl_wgrad_tc", "wsl_wgrad_tc2"])
+def test_wgrad_tc(case, ver):
     """tcgen05 weight gradient vs fp64 autograd on the same bf16 inputs; fp32 accumulation -> 1e-4 relative."""
     N, H, W, C0, C1, Cout, ks = case
+    if ver == "wsl_wgrad_tc2" and (ks != 3 or H % 16 or W % 8):
+        pytest.skip("v2: 3x3, 8x16 chunks")
+    if ver == "wsl_wgrad_tc" and (H % 8 or W % 16):
+        pytest.skip("v1: 16x8 chunks")
     g = torch.Generator().manual_seed(17)
     Cin = C0 + C1
     x = bf16_round(torch.randn(N, Cin, H, W, generator=g))
@@ -170,7 +179,7 @@ def test_wgrad_tc(case):
     s0 = nhwc(x[:, :C0]).to(DEV)
     s1 = nhwc(x[:, C0:]).to(DEV) if C1 else None
     dyd = nhwc(dy).to(DEV)
-    call("wsl_wgrad_tc", s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
+    call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
     db = torch.zeros(Cout, device=DEV)
     call("wsl_channel_sum", dyd, N * H * W, CoutP, Cout, db)
     torch.cuda.synchronize()
@@ -181,7 +190,7 @@ def test_wgrad_tc(case):
     assert rel_l2(dw.cpu(), gw.float()) < 1e-4, (case, rel_l2(dw.cpu(), gw.float()))
     assert rel_l2(db.cpu(), gb.float()) < 1e-5
     # accumulation semantics: a second call doubles the result
-    call("wsl_wgrad_tc", s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
+    call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
     torch.cuda.synchronize()
     assert rel_l2(dw.cpu(), 2 * gw.float()) < 1e-4
 

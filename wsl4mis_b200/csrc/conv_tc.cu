@@ -728,6 +728,161 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ================================================================================================
+// wgrad v2 (3x3 only): one halo load of X per 8x16 pixel chunk; the nine tap operands are row-shifted MN-major
+// descriptor views of that halo (same absolute-address swizzle argument as conv_tc2).  CTA = (Cout tile of 128) x
+// (Cin block of CWB <= 32) x all nine taps -> nine accumulators of CWB columns in TMEM (<= 288 columns).
+// L2->SM traffic per chunk: dY tile + 1.4x X block instead of dY + 9 X boxes.
+// ================================================================================================
+template <int CWA, int NA, int CWB, int STAGES>
+struct Wgrad2Smem {
+  static constexpr int A_BOX = TILE_M * CWA * 2;
+  static constexpr int ROWB = CWB * 2;
+  static constexpr int B_HALO = ((10 * 18 * ROWB + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = ((NA * A_BOX + B_HALO + 1023) / 1024) * 1024;
+  static constexpr int SLACK = (128 / CWA) * A_BOX;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + SLACK + 1024 + 256;
+};
+
+template <int SW>
+__device__ __forceinline__ uint64_t make_mnmajor_desc_sbo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  constexpr uint64_t layout = (SW == 128) ? 2 : (SW == 64) ? 4 : 6;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+template <int CWA, int NA, int CWB, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                                   const __grid_constant__ CUtensorMap map_x0,
+                                                                   const __grid_constant__ CUtensorMap map_x1, const WgradTcParams p) {
+  using S = Wgrad2Smem<CWA, NA, CWB, STAGES>;
+  constexpr int SWA = CWA * 2, SWB = CWB * 2;
+  constexpr uint32_t TMEM_COLS = (9 * CWB <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::SLACK);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.n_tiles0 + p.n_tiles1;
+  const int nt = blockIdx.y % n_tiles;
+  const int mt = blockIdx.y / n_tiles;
+  const int m0 = mt * 128;
+  const bool src1 = nt >= p.n_tiles0;
+  const int cb0 = (src1 ? nt - p.n_tiles0 : nt) * CWB;
+  const int ci_global = (src1 ? p.C0 : 0) + cb0;
+  const int my_chunks = (p.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_dy);
+    prefetch_tmap(src1 ? &map_x1 : &map_x0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mx = src1 ? &map_x1 : &map_x0;
+      for (int it = 0; it < my_chunks; ++it) {
+        const int chunk = blockIdx.x + it * gridDim.x;
+        const int n = chunk / (p.tiles_x * p.tiles_y);
+        const int tr = chunk - n * p.tiles_x * p.tiles_y;
+        const int y0 = (tr / p.tiles_x) * 16, x0 = (tr % p.tiles_x) * 8;
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + NA * S::A_BOX;
+        mbar_expect_tx(&full_bar[s], NA * S::A_BOX + 10 * 18 * S::ROWB);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) tma_load_4d(&map_dy, &full_bar[s], a_dst + i * S::A_BOX, m0 + i * CWA, x0, y0, n);
+        tma_load_4d(mx, &full_bar[s], b_dst, cb0, x0 - 1, y0 - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(CWB, 1, 1, 128);
+    for (int it = 0; it < my_chunks; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + NA * S::A_BOX;
+        const uint64_t adesc = make_mnmajor_desc_sbo<SWA>(a_addr, S::A_BOX, 8 * SWA);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3, dx = t % 3;
+          const uint64_t bdesc = make_mnmajor_desc_sbo<SWB>(b_addr + (uint32_t)((dy * 10 + dx) * S::ROWB), S::B_HALO, 10 * S::ROWB);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // k-step = 16 pixels = image rows 2k, 2k+1 of the chunk: A advances 16 rows, B advances 2 halo rows
+            umma_f16(tmem_base + t * CWB, adesc + (uint64_t)((k * 16 * SWA) >> 4), bdesc + (uint64_t)((k * 2 * 10 * S::ROWB) >> 4), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == my_chunks - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  } else if (my_chunks > 0) {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int CinTot = p.C0 + p.C1;
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll 1
+      for (int c = 0; c < CWB; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * CWB + c), v);
+        if (row < p.CoutReal) {
+          float* dst = p.dw + ((size_t)row * CinTot + ci_global + c) * 9 + t;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + (size_t)j * 9, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int CWA, int NA, int CWB>
+int launch_wgrad2(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const WgradTcParams& p, int m_tiles,
+                  cudaStream_t stream) {
+  constexpr int per_stage = NA * TILE_M * CWA * 2 + 12 * 1024;
+  constexpr int STAGES = per_stage >= 40 * 1024 ? 3 : 4;
+  using S = Wgrad2Smem<CWA, NA, CWB, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel<CWA, NA, CWB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { wsl_set_error("wgrad_tc2: cudaFuncSetAttribute(%d bytes): %s", S::TOTAL, cudaGetErrorString(e)); return -5; }
+    attr = true;
+  }
+  const int gy = m_tiles * (p.n_tiles0 + p.n_tiles1);
+  int splits = (148 + gy - 1) / gy;
+  if (splits > p.nchunks) splits = p.nchunks;
+  if (splits < 1) splits = 1;
+  dim3 grid(splits, gy);
+  wgrad_tc2_kernel<CWA, NA, CWB, STAGES><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
+  return wsl_check_launch("wgrad_tc2");
+}
+
 template <int CWA, int NA, int CWB, int TG>
 int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const WgradTcParams& p, int m_tiles,
                  cudaStream_t stream) {
@@ -947,8 +1102,9 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
   int nt = CoutP >= 128 ? 128 : CoutP;
   while (nt > 16 && (CoutP % nt != 0 || (long long)T * CinP * nt * 2 > 148 * 1024 || 2 * mt * nt > 512 || (nt == 128 && mt > 2))) nt >>= 1;
   WSL_REQUIRE(CoutP % nt == 0 && (long long)T * CinP * nt * 2 <= 152 * 1024, "wsl_conv_tc2: weights do not fit (Cin %d, NT %d)", CinP, nt);
-  static int desc_mode = -1;
-  if (desc_mode < 0) { const char* e = getenv("WSL_HALO_DESC_MODE"); desc_mode = e ? atoi(e) : 0; }
+  // base_offset stays 0: the swizzle XOR is taken from absolute shared-memory address bits by both TMA and tcgen05
+  // (verified on B200: setting base_offset = (addr>>7)&7 for the row-shifted views breaks every case).
+  const int desc_mode = 0;
   const int pad = ksize / 2;
   CUtensorMap a0, a1, b;
   {
@@ -990,4 +1146,52 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
     WSL_C2(1, 16, 1);
   }
 #undef WSL_C2
+}
+
+// 3x3 weight gradient, v2 (halo views).  Same contract as wsl_wgrad_tc; needs W % 8 == 0 and H % 16 == 0.
+WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                          int W, int CoutReal, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3, "wsl_wgrad_tc2: 3x3 only");
+  WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc2: source channels must be multiples of 16 (got %d,%d)", C0, C1);
+  WSL_REQUIRE(CoutP % 16 == 0 && (CoutP < 128 || CoutP % 128 == 0), "wsl_wgrad_tc2: unsupported CoutP %d", CoutP);
+  WSL_REQUIRE(W % 8 == 0 && H % 16 == 0, "wsl_wgrad_tc2: H,W must be multiples of the 16x8 pixel chunk (got %dx%d)", H, W);
+  const int cwa = CoutP >= 64 ? 64 : CoutP;
+  const int cwb = (C0 % 32 == 0 && (C1 == 0 || C1 % 32 == 0)) ? 32 : 16;
+  const int na = CoutP >= 128 ? 2 : 1;
+  const int m_tiles = CoutP >= 128 ? CoutP / 128 : 1;
+  CUtensorMap mdy, mx0, mx1;
+  {
+    long long d[4] = {CoutP, W, H, N};
+    int bx[4] = {cwa, 8, 16, 1};
+    int rc = get_map(dy, 4, d, bx, cwa, &mdy);
+    if (rc) return rc;
+  }
+  {
+    long long d[4] = {C0, W, H, N};
+    int bx[4] = {cwb, 10, 18, 1};
+    int rc = get_map(src0, 4, d, bx, cwb, &mx0);
+    if (rc) return rc;
+  }
+  if (C1 > 0) {
+    long long d[4] = {C1, W, H, N};
+    int bx[4] = {cwb, 10, 18, 1};
+    int rc = get_map(src1, 4, d, bx, cwb, &mx1);
+    if (rc) return rc;
+  } else {
+    mx1 = mx0;
+  }
+  WgradTcParams p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = 9; p.ks = 3;
+  p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dw = dw;
+  if (cwb == 32) {
+    if (cwa == 64 && na == 2) return launch_wgrad2<64, 2, 32>(mdy, mx0, mx1, p, m_tiles, stream);
+    if (cwa == 64) return launch_wgrad2<64, 1, 32>(mdy, mx0, mx1, p, m_tiles, stream);
+    if (cwa == 32) return launch_wgrad2<32, 1, 32>(mdy, mx0, mx1, p, m_tiles, stream);
+    return launch_wgrad2<16, 1, 32>(mdy, mx0, mx1, p, m_tiles, stream);
+  }
+  if (cwa == 64 && na == 2) return launch_wgrad2<64, 2, 16>(mdy, mx0, mx1, p, m_tiles, stream);
+  if (cwa == 64) return launch_wgrad2<64, 1, 16>(mdy, mx0, mx1, p, m_tiles, stream);
+  if (cwa == 32) return launch_wgrad2<32, 1, 16>(mdy, mx0, mx1, p, m_tiles, stream);
+  return launch_wgrad2<16, 1, 16>(mdy, mx0, mx1, p, m_tiles, stream);
 }

@@ -152,35 +152,43 @@ __global__ void __launch_bounds__(TPB) conv_first_kernel(const float* __restrict
   }
 }
 
-// dW[co][t] += sum_p dY[p][co] * x[p + tap_t]; block = 16 co x 16 pixel lanes, 9 accumulators per thread
-__global__ void __launch_bounds__(TPB) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+// dW[co][t] += sum_p dY[p][co] * x[p + tap_t]: every thread walks pixels with a 16x9 register tile (144 FMAs per
+// 11 loads), then warp-shuffle + one atomicAdd per warp and entry.
+__global__ void __launch_bounds__(128) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                           float* __restrict__ dw /*[16][9]*/, int N, int H, int W) {
-  const int co = threadIdx.x & 15, pl = threadIdx.x >> 4;
-  float acc[9];
+  float acc[16][9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int c = 0; c < 16; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
   const long long total = (long long)N * H * W;
-  for (long long i = (long long)blockIdx.x * 16 + pl; i < total; i += (long long)gridDim.x * 16) {
+  for (long long i = blockIdx.x * 128LL + threadIdx.x; i < total; i += (long long)gridDim.x * 128) {
     const int xx = (int)(i % W), yy = (int)((i / W) % H);
     const float* base = x + (i - (long long)yy * W - xx);
-    const float g = __bfloat162float(dy[i * 16 + co]);
+    float v[9], g[16];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
-      const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
-      acc[t] = fmaf(g, v, acc[t]);
+      v[t] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
     }
-  }
-  __shared__ float s_a[16][16][9];
+    const uint4* src = reinterpret_cast<const uint4*>(dy + i * 16);
+    float lo[8], hi[8];
+    unpack8(src[0], lo);
+    unpack8(src[1], hi);
 #pragma unroll
-  for (int t = 0; t < 9; ++t) s_a[pl][co][t] = acc[t];
-  __syncthreads();
-  if (threadIdx.x < 144) {
-    const int c = threadIdx.x / 9, t = threadIdx.x % 9;
-    float r = 0.f;
-    for (int q = 0; q < 16; ++q) r += s_a[q][c][t];
-    atomicAdd(dw + c * 9 + t, r);
+    for (int c = 0; c < 8; ++c) { g[c] = lo[c]; g[8 + c] = hi[c]; }
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], v[t], acc[c][t]);
   }
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float r = warp_sum(acc[c][t]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(dw + c * 9 + t, r);
+    }
 }
 
 // ================================================================================================
@@ -275,7 +283,18 @@ __device__ __forceinline__ void bn_finalize_partials(const float* partials, int 
     const int part = threadIdx.x / cw;
     double a = 0.0, b = 0.0;
     if (part < parts) {
-      for (int bl = part; bl < nblocks; bl += parts) {
+      int bl = part;
+      for (; bl + 7 * parts < nblocks; bl += 8 * parts) {   // 16 independent loads in flight, fixed summation order
+        float va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          va[u] = __ldcg(&partials[((size_t)(bl + u * parts) * 2 + 0) * C + c]);
+          vb[u] = __ldcg(&partials[((size_t)(bl + u * parts) * 2 + 1) * C + c]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a += (double)va[u]; b += (double)vb[u]; }
+      }
+      for (; bl < nblocks; bl += parts) {
         a += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
         b += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
       }
@@ -755,10 +774,10 @@ inline int grid_for(long long items) {
 }
 
 inline int bn_grid(long long P, int C) {
-  const int rows = TPB / (C / 8);
-  long long b = (P + (long long)rows * 4 - 1) / ((long long)rows * 4);
+  // every block should stream >= ~96 KB so that the fixed-order finalize (one pass over all partials) stays negligible
+  long long b = (P * C * 2 + 96 * 1024 - 1) / (96 * 1024);
   if (b < 1) b = 1;
-  if (b > 148 * 6) b = 148 * 6;
+  if (b > 148 * 4) b = 148 * 4;
   return (int)b;
 }
 
@@ -912,9 +931,9 @@ WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, vo
 
 WSL_API int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, cudaStream_t stream) {
   WSL_REQUIRE(Cout == 16, "wsl_wgrad_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
-  long long b = ((long long)N * H * W + 16 * 64 - 1) / (16 * 64);
-  if (b > 148 * 8) b = 148 * 8;
+  long long b = ((long long)N * H * W + 128 * 16 - 1) / (128 * 16);
+  if (b > 148 * 3) b = 148 * 3;
   if (b < 1) b = 1;
-  wgrad_first_kernel<<<(int)b, TPB, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
+  wgrad_first_kernel<<<(int)b, 128, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
   return wsl_check_launch("wgrad_first");
 }

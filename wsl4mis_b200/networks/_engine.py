@@ -123,6 +123,7 @@ class UNetExecutor:
         self._seed_host = 0x5EED
         self.use_tc = os.environ.get("WSL4MIS_NO_TC", "0") != "1"
         self.use_tc_wgrad = os.environ.get("WSL4MIS_NO_TC_WGRAD", "0") != "1"
+        self.use_tc2 = os.environ.get("WSL4MIS_NO_TC2", "0") != "1"
         self.stats = {"launches": 0}
 
     # ---------------------------------------------------------------- buffers
@@ -166,6 +167,10 @@ class UNetExecutor:
         if _lib.PROFILE is not None:
             _lib.PROFILE.meta = None
 
+    def _tc2_ok(self, layer_cin_list, H, W):
+        """persistent / resident-weight / halo-view kernels: 8 x 16 pixel tiles"""
+        return (self.use_tc and self.use_tc2 and all(c % 16 == 0 for c in layer_cin_list) and W % 8 == 0 and H % 16 == 0)
+
     def _tc_ok(self, layer_cin_list, H, W):
         return (self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
 
@@ -178,6 +183,8 @@ class UNetExecutor:
         self._tag("fwd", L, N, H, W, L.Cin, L.Cout)
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode == 0:
             call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, N, H, W, L.Cout)
+        elif not src_f32 and self._tc2_ok(L.srcC, H, W):
+            call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         elif not src_f32 and self._tc_ok(L.srcC, H, W):
             call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         else:
@@ -190,7 +197,9 @@ class UNetExecutor:
         ci = L.srcC[i]
         sp = _ceil16(ci)
         self._tag("dgrad", L, N, H, W, ci, L.Cout)
-        if self._tc_ok([L.CoutP], H, W):
+        if self._tc2_ok([L.CoutP], H, W):
+            call("wsl_conv_tc2", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
+        elif self._tc_ok([L.CoutP], H, W):
             call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
         else:
             call("wsl_conv_direct", dy, L.CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, L.CoutP, sp, ci, L.ks)
@@ -206,6 +215,8 @@ class UNetExecutor:
               and (L.CoutP < 128 or L.CoutP % 128 == 0))
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and L.bn is not None:
             call("wsl_wgrad_first", s0, dy, self.gview(L.conv.weight), N, H, W, L.Cout)
+        elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W):
+            call("wsl_wgrad_tc2", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         elif tc:
             call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         else:
