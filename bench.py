@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     return ap.parse_args()
 
 
@@ -212,7 +214,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(K):
+    for _ in range(0 if args.skip_e2e else K):
         si, sl = step.static_inputs() if step.static_inputs() is not None else (img_d, lab_d)
         si.copy_(img_h, non_blocking=True)
         sl.copy_(lab_h, non_blocking=True)
@@ -220,7 +222,9 @@ def main():
         lv = loss.item()                      # D2H of the step's result
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = max(e0.elapsed_time(e1), 1e-6)
+    if args.skip_e2e:
+        lv = loss.item()
     clocks = sampler.stop() if sampler is not None else None
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -278,7 +282,7 @@ def main():
                     "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["src"]}
 
     if rank == 0:
-        cb, _ = cpu_step_time(args.model, args.variant, args.cpu_sample, 2, 1)
+        cb = None if args.skip_cpu else cpu_step_time(args.model, args.variant, args.cpu_sample, 2, 1)[0]
         imgs = N * world * K
         line = {
             "metric": METRIC, "value": imgs / (ms_dev * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
