@@ -107,13 +107,22 @@ int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* 
  * nine taps are row-shifted UMMA descriptor views (no reload).  Same contract; needs W % 8 == 0 and H % 16 == 0. */
 int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
                  void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
-                 cudaStream_t stream);
+                 float* stat_partials, int* stat_rows_host, cudaStream_t stream);
+/* stat_partials (optional, device, >= 592*2*CoutP floats): per-CTA sum / sum-of-squares rows of the stored outputs for the
+ * following BatchNorm; *stat_rows_host (optional, HOST int) receives the number of rows written.  wsl_bn_finalize turns
+ * the rows into {mean, invstd, scale, shift} and updates the running statistics exactly like wsl_bn_stats. */
+int wsl_bn_finalize(const float* partials, int nrows, long long P, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    float* save, float* ss, cudaStream_t stream);
 /* tcgen05 weight gradient (conv_tc.cu): dw (fp32, torch layout [CoutReal][C0+C1][k][k]) += dY^T * X over all pixels.
  * Bias gradients are NOT produced here (see wsl_channel_sum). */
 int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                  int W, int CoutReal, int ksize, cudaStream_t stream);
 /* v2 of the 3x3 weight gradient: one halo load of X per 16x8 pixel chunk, nine row-shifted descriptor views. */
 int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                  int W, int CoutReal, int ksize, cudaStream_t stream);
+/* v3: filter columns ride in the MMA's M dimension (A = X halo with one-pixel group stride, B = dY, N = Cout tile). */
+int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                   int W, int CoutReal, int ksize, cudaStream_t stream);
 /* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
 int wsl_channel_sum(const void* x, long long P, int C, int Creal, float* out, cudaStream_t stream);
@@ -155,6 +164,10 @@ int wsl_nhwc_bf16_to_nchw_f32(const void* src, int N, int C, int H, int W, float
 /* fp32 torch-layout conv weight -> packed operands (any output may be NULL), see net_ops.cu */
 int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,
                           int ci_count, float* wf, float* wd, void* bf, void* bd, cudaStream_t stream);
+
+/* all layers in one launch: table = n_entries x 13 int64 {w, wf, wd, bf, bd, Cout, Cin, T, CoutP, CinP, ci_begin,
+ * ci_count, first_item} in device memory (pointers as integers), items = T*CoutP*CinP per entry */
+int wsl_pack_conv_weights_batched(const long long* table, int n_entries, long long total_items, cudaStream_t stream);
 
 /* optim.SGD(lr, momentum, weight_decay).step() over a flat fp32 buffer (train_weakly_supervised_pCE_2D.py:79-80,104);
  * lr is read from lr_ptr (device) when non-NULL so a captured CUDA graph follows the poly schedule (:106-108);

@@ -71,9 +71,21 @@ def test_conv_forward(case, path):
     fp32_out = Cout == 4
     out = torch.zeros((N, Cout, H, W), device=DEV) if fp32_out else torch.zeros((N, H, W, Cout), device=DEV, dtype=BF)
     if path in ("tc", "tc2"):
+        import ctypes
+        rows = ctypes.c_int(0)
+        parts = torch.zeros(592 * 2 * CoutP, device=DEV)
+        extra = (parts, ctypes.addressof(rows)) if path == "tc2" else ()
         call("wsl_conv_tc2" if path == "tc2" else "wsl_conv_tc", s0, C0, s1, C1, pk["bf"], bias, out, 1 if fp32_out else 0,
-             N, H, W, CoutP, Cout, ks)
+             N, H, W, CoutP, Cout, ks, *extra)
         wref = bf16_round(w)   # tensor-core path multiplies bf16 weights
+        if path == "tc2" and not fp32_out:
+            # fused BatchNorm statistics: rows of per-CTA (sum, sum of squares) of the stored outputs
+            torch.cuda.synchronize()
+            st = parts[: rows.value * 2 * CoutP].view(rows.value, 2, CoutP).double().sum(0).cpu()
+            o = nchw(out.cpu()).double()
+            assert rows.value >= 1
+            assert torch.allclose(st[0, :Cout], o.sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+            assert torch.allclose(st[1, :Cout], (o * o).sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
     else:
         call("wsl_conv_direct", s0, C0, s1, C1, 0, pk["wf"], bias, out, 1 if fp32_out else 0, N, H, W, pk["CinP"], CoutP, Cout, ks)
         wref = w
@@ -107,7 +119,8 @@ def test_conv_dgrad(case, path):
         sp = (c + 15) // 16 * 16
         out = torch.zeros((N, H, W, c), device=DEV, dtype=BF)
         if path != "direct":
-            call("wsl_conv_tc2" if path == "tc2" else "wsl_conv_tc", dyd, CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, c, ks)
+            extra = (None, None) if path == "tc2" else ()
+            call("wsl_conv_tc2" if path == "tc2" else "wsl_conv_tc", dyd, CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, c, ks, *extra)
         else:
             call("wsl_conv_direct", dyd, CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, CoutP, sp, c, ks)
         torch.cuda.synchronize()
@@ -161,11 +174,11 @@ WGRAD_TC_CASES += [(2, 32, 32, 16, 0, 16, 3), (1, 64, 32, 32, 32, 32, 3), (2, 32
 
 
 @pytest.mark.parametrize("case", WGRAD_TC_CASES)
-@pytest.mark.parametrize("ver", ["wsl_wgrad_tc", "wsl_wgrad_tc2"])
+@pytest.mark.parametrize("ver", ["wsl_wgrad_tc", "wsl_wgrad_tc2", "wsl_wgrad_tc3"])
 def test_wgrad_tc(case, ver):
     """tcgen05 weight gradient vs fp64 autograd on the same bf16 inputs; fp32 accumulation -> 1e-4 relative."""
     N, H, W, C0, C1, Cout, ks = case
-    if ver == "wsl_wgrad_tc2" and (ks != 3 or H % 16 or W % 8):
+    if ver != "wsl_wgrad_tc" and (ks != 3 or H % 16 or W % 8):
         pytest.skip("v2: 3x3, 8x16 chunks")
     if ver == "wsl_wgrad_tc" and (H % 8 or W % 16):
         pytest.skip("v1: 16x8 chunks")

@@ -406,7 +406,34 @@ struct ConvV2Params {
   int desc_mode;
   const float* bias;
   void* out;
+  float* stat_partials;   // optional [gridDim.x][2][CoutP]: per-CTA sum / sum of squares of the stored (bf16-rounded) outputs
 };
+
+// Sum over the 32 lanes of a warp for 16 per-lane values with a transpose-reduction (16 shuffles instead of 80):
+// returns, on every lane, the total of value index ((lane >> 1) & 15).
+__device__ __forceinline__ float warp_transpose_sum16(const float (&x)[16], int lane) {
+  float y[8], z[4], w[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = h16 ? x[i] : x[i + 8], keep = h16 ? x[i + 8] : x[i];
+    y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h8 ? y[i] : y[i + 4], keep = h8 ? y[i + 4] : y[i];
+    z[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h4 ? z[i] : z[i + 2], keep = h4 ? z[i + 2] : z[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = h2 ? w[0] : w[1], keep = h2 ? w[1] : w[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
 
 template <int KS, int KBLK, int NT, int MT>
 struct ConvV2Cfg {
@@ -518,6 +545,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    float rs[NT / 16], rq[NT / 16];       // running per-channel sum / sum of squares (channel = chunk*16 + ((lane>>1)&15))
+#pragma unroll
+    for (int c = 0; c < NT / 16; ++c) rs[c] = rq[c] = 0.f;
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int n = tile / (p.tiles_x * p.tiles_y);
@@ -529,7 +559,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {
         const int gy = y0 + 16 * j + m / 8, gx = x0 + (m & 7);
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < NT; c += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + j) * NT + c), v);
@@ -538,13 +568,25 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
             for (int jj = 0; jj < 16; ++jj) v[jj] += p.bias[n0 + c + jj];
           }
           if (p.out_mode == 0) {
+            float lo[8], hi[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) { lo[jj] = v[jj]; hi[jj] = v[8 + jj]; }
+            const uint4 plo = pack8(lo), phi = pack8(hi);
             if (n0 + c < p.CoutStore) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)n * p.H + gy) * p.W + gx) * p.CoutStore + n0 + c;
-              float lo[8], hi[8];
+              reinterpret_cast<uint4*>(o)[0] = plo;
+              if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = phi;
+            }
+            if (p.stat_partials) {   // BatchNorm statistics of the values exactly as stored (bf16-rounded)
+              float r[16], r2[16];
+              unpack8(plo, lo);
+              unpack8(phi, hi);
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) { lo[jj] = v[jj]; hi[jj] = v[8 + jj]; }
-              reinterpret_cast<uint4*>(o)[0] = pack8(lo);
-              if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+              for (int jj = 0; jj < 8; ++jj) { r[jj] = lo[jj]; r[8 + jj] = hi[jj]; }
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) r2[jj] = r[jj] * r[jj];
+              rs[c / 16] += warp_transpose_sum16(r, lane);
+              rq[c / 16] += warp_transpose_sum16(r2, lane);
             }
           } else {
             float* o = reinterpret_cast<float*>(p.out);
@@ -557,6 +599,24 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+    if (p.stat_partials) {
+      // combine the four epilogue warps (fixed order) and write this CTA's partial row
+      __shared__ float s_stat[4][2][NT];
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int c = 0; c < NT / 16; ++c) {
+          s_stat[q][0][c * 16 + ((lane >> 1) & 15)] = rs[c];
+          s_stat[q][1][c * 16 + ((lane >> 1) & 15)] = rq[c];
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;      // 0..127 over the epilogue warps
+      for (int c = t; c < 2 * NT; c += 128) {
+        const int which = c / NT, ch = c % NT;
+        const float a = ((s_stat[0][which][ch] + s_stat[1][which][ch]) + s_stat[2][which][ch]) + s_stat[3][which][ch];
+        p.stat_partials[((size_t)blockIdx.x * 2 + which) * p.CoutP + n0 + ch] = a;
+      }
     }
   }
   tc_fence_before();
@@ -883,6 +943,164 @@ int launch_wgrad2(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensor
   return wsl_check_launch("wgrad_tc2");
 }
 
+// ================================================================================================
+// wgrad v3 (3x3): taps in the M dimension.
+//
+//   A := X halo (MN-major).  An M = 128 operand is 128/CWB channel groups spaced LBO apart; with LBO = ONE PIXEL
+//        (CWB*2 bytes) group g is the same halo viewed g pixels further right, i.e. filter column dx = g.  One MMA
+//        therefore accumulates dx = 0,1,2 of a filter row at once (groups >= 3 are don't-care rows of D).
+//   B := dY tile (MN-major), N = the Cout tile (<= 128) -> wide N keeps the tensor pipe ahead of the A smem reads.
+//   D_dy[(dx, ci)][co], dy = 0..2: three accumulators of N columns in TMEM.
+// MMAs per 128-pixel chunk and 32-channel Cin block: 3 dy x 8 k-steps = 24 (v2 issued 72 narrow ones).
+// ================================================================================================
+template <int CWB, int CWN, int NBOX, int STAGES>
+struct Wgrad3Smem {
+  static constexpr int ROWB = CWB * 2;
+  static constexpr int N_BOX = TILE_M * CWN * 2;
+  static constexpr int A_HALO = ((10 * 18 * ROWB + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = ((NBOX * N_BOX + A_HALO + 1023) / 1024) * 1024;
+  static constexpr int SLACK = 2048;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + SLACK + 1024 + 256;
+};
+
+struct Wgrad3Params {
+  int N, H, W;
+  int C0, C1;
+  int CoutReal;
+  int tiles_x, tiles_y, nchunks;
+  int k_tiles0, k_tiles1;     // Cin blocks (of CWB channels) in source 0 / 1
+  float* dw;
+};
+
+template <int CWB, int CWN, int NBOX, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                                   const __grid_constant__ CUtensorMap map_x0,
+                                                                   const __grid_constant__ CUtensorMap map_x1, const Wgrad3Params p) {
+  using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES>;
+  constexpr int NTILE = CWN * NBOX;
+  constexpr int SWX = CWB * 2, SWN = CWN * 2;
+  constexpr uint32_t TMEM_COLS = (3 * NTILE <= 64) ? 64 : (3 * NTILE <= 128) ? 128 : (3 * NTILE <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::SLACK);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_tiles = p.k_tiles0 + p.k_tiles1;
+  const int kt = blockIdx.y % k_tiles;          // Cin block
+  const int nt = blockIdx.y / k_tiles;          // Cout tile
+  const int n0 = nt * NTILE;
+  const bool src1 = kt >= p.k_tiles0;
+  const int cb0 = (src1 ? kt - p.k_tiles0 : kt) * CWB;
+  const int ci_global = (src1 ? p.C0 : 0) + cb0;
+  const int my_chunks = (p.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_dy);
+    prefetch_tmap(src1 ? &map_x1 : &map_x0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mx = src1 ? &map_x1 : &map_x0;
+      for (int it = 0; it < my_chunks; ++it) {
+        const int chunk = blockIdx.x + it * gridDim.x;
+        const int n = chunk / (p.tiles_x * p.tiles_y);
+        const int tr = chunk - n * p.tiles_x * p.tiles_y;
+        const int y0 = (tr / p.tiles_x) * 16, x0 = (tr % p.tiles_x) * 8;
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        uint8_t* b_dst = smem + s * S::STAGE_BYTES;          // dY boxes
+        uint8_t* a_dst = b_dst + NBOX * S::N_BOX;            // X halo
+        mbar_expect_tx(&full_bar[s], NBOX * S::N_BOX + 10 * 18 * S::ROWB);
+#pragma unroll
+        for (int i = 0; i < NBOX; ++i) tma_load_4d(&map_dy, &full_bar[s], b_dst + i * S::N_BOX, n0 + i * CWN, x0, y0, n);
+        tma_load_4d(mx, &full_bar[s], a_dst, cb0, x0 - 1, y0 - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(NTILE, 1, 1, 128);
+    for (int it = 0; it < my_chunks; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t b_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t a_addr = b_addr + NBOX * S::N_BOX;
+        const uint64_t bdesc = make_mnmajor_desc_sbo<SWN>(b_addr, S::N_BOX, 8 * SWN);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          // channel-group stride (LBO) = one pixel: group g == filter column dx = g
+          const uint64_t adesc = make_mnmajor_desc_sbo<SWX>(a_addr + (uint32_t)(dy * 10 * S::ROWB), S::ROWB, 10 * S::ROWB);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16(tmem_base + dy * NTILE, adesc + (uint64_t)((k * 2 * 10 * S::ROWB) >> 4), bdesc + (uint64_t)((k * 16 * SWN) >> 4), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == my_chunks - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  } else if (my_chunks > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int g = m / CWB, ci = m % CWB;        // filter column dx, input channel inside the block
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int CinTot = p.C0 + p.C1;
+#pragma unroll 1
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+      for (int c = 0; c < NTILE; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dy * NTILE + c), v);
+        if (g < 3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = n0 + c + j;
+            if (co < p.CoutReal) atomicAdd(p.dw + ((size_t)co * CinTot + ci_global + ci) * 9 + dy * 3 + g, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int CWB, int CWN, int NBOX>
+int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const Wgrad3Params& p, int n_tiles,
+                  cudaStream_t stream) {
+  constexpr int per_stage = NBOX * TILE_M * CWN * 2 + 12 * 1024;
+  constexpr int STAGES = per_stage >= 40 * 1024 ? 3 : 4;
+  using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { wsl_set_error("wgrad_tc3: cudaFuncSetAttribute(%d bytes): %s", S::TOTAL, cudaGetErrorString(e)); return -5; }
+    attr = true;
+  }
+  const int gy = n_tiles * (p.k_tiles0 + p.k_tiles1);
+  int splits = (148 + gy - 1) / gy;
+  if (splits > p.nchunks) splits = p.nchunks;
+  if (splits < 1) splits = 1;
+  dim3 grid(splits, gy);
+  wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
+  return wsl_check_launch("wgrad_tc3");
+}
+
 template <int CWA, int NA, int CWB, int TG>
 int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const WgradTcParams& p, int m_tiles,
                  cudaStream_t stream) {
@@ -944,6 +1162,8 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* _
 }
 
 
+static int g_conv2_last_rows = 0;   // gridDim.x of the most recent conv_tc2 launch (rows of stat_partials)
+
 template <int KS, int KBLK, int NT, int MT>
 int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvV2Params& p, cudaStream_t stream) {
   using Cfg = ConvV2Cfg<KS, KBLK, NT, MT>;
@@ -969,6 +1189,7 @@ int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid(gx, n_tiles);
+  g_conv2_last_rows = gx;
   conv_tc2_kernel<KS, KBLK, NT, MT, STAGES><<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p, w_bytes);
   return wsl_check_launch("conv_tc2");
 }
@@ -1088,7 +1309,8 @@ WSL_API int wsl_channel_sum(const void* x, long long P, int C, int Creal, float*
 
 // conv_tc v2 entry point (same contract as wsl_conv_tc; needs W % 8 == 0 and H % (16*MT) == 0)
 WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                         int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream) {
+                         int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, float* stat_partials,
+                         int* stat_rows_host, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc2: ksize must be 1 or 3");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc2: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc2: CoutP must be a multiple of 16");
@@ -1131,7 +1353,13 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore;
   p.tiles_x = W / 8; p.tiles_y = H / (16 * mt); p.ntiles = N * p.tiles_x * p.tiles_y;
   p.out_mode = out_mode; p.desc_mode = desc_mode; p.bias = bias; p.out = out;
-#define WSL_C2(KS_, KB_, MT_) return conv2_dispatch_nt<KS_, KB_, MT_>(nt, a0, a1, b, p, stream)
+  p.stat_partials = (out_mode == 0) ? stat_partials : nullptr;
+#define WSL_C2(KS_, KB_, MT_)                                                   \
+  do {                                                                         \
+    int rc_ = conv2_dispatch_nt<KS_, KB_, MT_>(nt, a0, a1, b, p, stream);      \
+    if (stat_rows_host) *stat_rows_host = g_conv2_last_rows;                   \
+    return rc_;                                                                \
+  } while (0)
   if (ksize == 3) {
     if (kblk == 64) WSL_C2(3, 64, 1);
     if (kblk == 32) { if (mt == 2) WSL_C2(3, 32, 2); WSL_C2(3, 32, 1); }
@@ -1194,4 +1422,51 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
   if (cwa == 64) return launch_wgrad2<64, 1, 16>(mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 32) return launch_wgrad2<32, 1, 16>(mdy, mx0, mx1, p, m_tiles, stream);
   return launch_wgrad2<16, 1, 16>(mdy, mx0, mx1, p, m_tiles, stream);
+}
+
+// 3x3 weight gradient, v3 (filter columns in the MMA's M dimension).  Same contract as wsl_wgrad_tc2.
+WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                          int W, int CoutReal, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3, "wsl_wgrad_tc3: 3x3 only");
+  WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc3: source channels must be multiples of 16 (got %d,%d)", C0, C1);
+  WSL_REQUIRE(CoutP % 16 == 0 && (CoutP <= 64 || CoutP % 128 == 0), "wsl_wgrad_tc3: unsupported CoutP %d", CoutP);
+  WSL_REQUIRE(CoutP == 16 || CoutP == 32 || CoutP >= 64, "wsl_wgrad_tc3: unsupported CoutP %d", CoutP);
+  WSL_REQUIRE(W % 8 == 0 && H % 16 == 0, "wsl_wgrad_tc3: H,W must be multiples of the 16x8 pixel chunk (got %dx%d)", H, W);
+  const int cwb = (C0 % 32 == 0 && (C1 == 0 || C1 % 32 == 0)) ? 32 : 16;
+  const int cwn = CoutP >= 64 ? 64 : CoutP;
+  const int ntile = CoutP >= 128 ? 128 : CoutP;
+  const int n_tiles = CoutP / ntile;
+  CUtensorMap mdy, mx0, mx1;
+  {
+    long long d[4] = {CoutP, W, H, N};
+    int bx[4] = {cwn, 8, 16, 1};
+    int rc = get_map(dy, 4, d, bx, cwn, &mdy);
+    if (rc) return rc;
+  }
+  {
+    long long d[4] = {C0, W, H, N};
+    int bx[4] = {cwb, 10, 18, 1};
+    int rc = get_map(src0, 4, d, bx, cwb, &mx0);
+    if (rc) return rc;
+  }
+  if (C1 > 0) {
+    long long d[4] = {C1, W, H, N};
+    int bx[4] = {cwb, 10, 18, 1};
+    int rc = get_map(src1, 4, d, bx, cwb, &mx1);
+    if (rc) return rc;
+  } else {
+    mx1 = mx0;
+  }
+  Wgrad3Params p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutReal = CoutReal;
+  p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
+  p.k_tiles0 = C0 / cwb; p.k_tiles1 = C1 / cwb; p.dw = dw;
+#define WSL_W3(CWB_) \
+  if (ntile == 128) return launch_wgrad3<CWB_, 64, 2>(mdy, mx0, mx1, p, n_tiles, stream); \
+  if (ntile == 64) return launch_wgrad3<CWB_, 64, 1>(mdy, mx0, mx1, p, n_tiles, stream);  \
+  if (ntile == 32) return launch_wgrad3<CWB_, 32, 1>(mdy, mx0, mx1, p, n_tiles, stream);  \
+  return launch_wgrad3<CWB_, 16, 1>(mdy, mx0, mx1, p, n_tiles, stream);
+  if (cwb == 32) { WSL_W3(32) }
+  WSL_W3(16)
+#undef WSL_W3
 }

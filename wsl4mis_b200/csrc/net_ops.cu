@@ -380,6 +380,33 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(
   }
 }
 
+// finalize-only variant: partial rows [nrows][2][C] produced by the convolution epilogue (conv_tc.cu)
+__global__ void __launch_bounds__(TPB) bn_finalize_kernel(const float* __restrict__ partials, int nrows, long long P, int C,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* running_mean, float* running_var, long long* nbt, float momentum,
+                                                          float eps, float* __restrict__ save, float* __restrict__ ss) {
+  __shared__ double s_fin[2 * 256];
+  __shared__ double s_part[TPB * 2];
+  bn_finalize_partials(partials, nrows, C, s_fin, s_part);
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    const double mean = s_fin[c] / (double)P;
+    double var = s_fin[C + c] / (double)P - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    save[c] = (float)mean;
+    save[C + c] = invstd;
+    const float sc = gamma[c] * invstd;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - (float)mean * sc;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      const double unb = (P > 1) ? var * (double)P / (double)(P - 1) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  }
+  if (threadIdx.x == 0 && nbt) *nbt += 1;
+}
+
 // eval mode: scale/shift from running statistics
 __global__ void bn_eval_prepare_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
                                        float eps, int C, float* ss) {
@@ -753,6 +780,41 @@ __global__ void __launch_bounds__(TPB) pack_weights_kernel(const float* __restri
   }
 }
 
+// Batched form: ONE launch packs every layer.  table[e] = 13 int64: {w, wf, wd, bf, bd, Cout, Cin, T, CoutP, CinP, ci_begin,
+// ci_count, first_item}; items of entry e are [first_item(e), first_item(e+1)).
+__global__ void __launch_bounds__(TPB) pack_weights_batched_kernel(const long long* __restrict__ table, int n_entries, long long total) {
+  __shared__ long long s_first[129];
+  for (int e = threadIdx.x; e <= n_entries; e += TPB) s_first[e] = (e < n_entries) ? table[e * 13 + 12] : total;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {                     // last entry whose first_item <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_first[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const long long* t = table + lo * 13;
+    const float* w = reinterpret_cast<const float*>(t[0]);
+    float* wf = reinterpret_cast<float*>(t[1]);
+    float* wd = reinterpret_cast<float*>(t[2]);
+    __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(t[3]);
+    __nv_bfloat16* bd = reinterpret_cast<__nv_bfloat16*>(t[4]);
+    const int Cout = (int)t[5], Cin = (int)t[6], T = (int)t[7], CoutP = (int)t[8], CinP = (int)t[9], ci_begin = (int)t[10],
+              ci_count = (int)t[11];
+    const long long j = i - s_first[lo];
+    const int SliceP = (ci_count + 15) & ~15;
+    const int ci = (int)(j % CinP), co = (int)((j / CinP) % CoutP), tt = (int)(j / ((long long)CinP * CoutP));
+    const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * T + tt] : 0.f;
+    if (wf) wf[((size_t)tt * CinP + ci) * CoutP + co] = v;
+    if (bf) bf[((size_t)tt * CoutP + co) * CinP + ci] = __float2bfloat16(v);
+    const int cs = ci - ci_begin;
+    if (cs >= 0 && cs < SliceP) {
+      const float vs = (cs < ci_count) ? v : 0.f;
+      if (wd) wd[((size_t)(T - 1 - tt) * CoutP + co) * SliceP + cs] = vs;
+      if (bd) bd[((size_t)(T - 1 - tt) * SliceP + cs) * CoutP + co] = __float2bfloat16(vs);
+    }
+  }
+}
+
 // torch.optim.SGD(momentum, weight_decay), dampening 0, no nesterov: g += wd*p; buf = mu*buf + g; p -= lr*buf
 // (zero-initialised buf reproduces torch's first-step "buf = g").
 __global__ void __launch_bounds__(TPB) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -936,4 +998,19 @@ WSL_API int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, in
   if (b < 1) b = 1;
   wgrad_first_kernel<<<(int)b, 128, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
   return wsl_check_launch("wgrad_first");
+}
+
+WSL_API int wsl_pack_conv_weights_batched(const long long* table, int n_entries, long long total_items, cudaStream_t stream) {
+  WSL_REQUIRE(n_entries >= 1 && n_entries <= 128, "wsl_pack_conv_weights_batched: 1..128 entries (got %d)", n_entries);
+  pack_weights_batched_kernel<<<grid_for(total_items), TPB, 0, stream>>>(table, n_entries, total_items);
+  return wsl_check_launch("pack_conv_weights_batched");
+}
+
+WSL_API int wsl_bn_finalize(const float* partials, int nrows, long long P, int C, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                            float* save, float* ss, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0 && C <= 256, "wsl_bn_finalize: unsupported channel count %d", C);
+  bn_finalize_kernel<<<1, TPB, 0, stream>>>(partials, nrows, P, C, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                            momentum, eps, save, ss);
+  return wsl_check_launch("bn_finalize");
 }

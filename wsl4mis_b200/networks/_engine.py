@@ -16,6 +16,7 @@ All launches go to torch's current stream, never allocate or synchronise, and ar
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Dict, List, Optional, Sequence
 
@@ -124,6 +125,8 @@ class UNetExecutor:
         self.use_tc = os.environ.get("WSL4MIS_NO_TC", "0") != "1"
         self.use_tc_wgrad = os.environ.get("WSL4MIS_NO_TC_WGRAD", "0") != "1"
         self.use_tc2 = os.environ.get("WSL4MIS_NO_TC2", "0") != "1"
+        self.wgrad_version = int(os.environ.get("WSL4MIS_WGRAD", "3"))
+        self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
         self.stats = {"launches": 0}
 
     # ---------------------------------------------------------------- buffers
@@ -174,8 +177,10 @@ class UNetExecutor:
     def _tc_ok(self, layer_cin_list, H, W):
         return (self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
 
-    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False):
+    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, want_stats=False):
+        """Returns the number of BatchNorm partial-statistics rows the conv epilogue produced (0 = none)."""
         pk = L.packs(self.dev)
+        rows = 0
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
         c0 = L.srcC[0]
@@ -184,13 +189,22 @@ class UNetExecutor:
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode == 0:
             call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, N, H, W, L.Cout)
         elif not src_f32 and self._tc2_ok(L.srcC, H, W):
-            call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
+            if want_stats and self.fuse_bn_stats:
+                if getattr(self, "_stat_buf", None) is None or self._stat_buf.device != self.dev:
+                    self._stat_buf = torch.zeros(592 * 2 * 256, dtype=torch.float32, device=self.dev)
+                    self._stat_rows = ctypes.c_int(0)
+                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks,
+                     self._stat_buf, ctypes.addressof(self._stat_rows))
+                rows = self._stat_rows.value
+            else:
+                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks, None, None)
         elif not src_f32 and self._tc_ok(L.srcC, H, W):
             call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         else:
             call("wsl_conv_direct", s0, c0, s1, c1, 1 if src_f32 else 0, pk["wf"], pk["bias"], out, out_mode, N, H, W,
                  L.CinP, L.CoutP, cout_store, L.ks)
         self._untag()
+        return rows
 
     def conv_dgrad(self, L: ConvLayer, i, dy, out, N, H, W):
         pk = L.packs(self.dev)
@@ -198,7 +212,7 @@ class UNetExecutor:
         sp = _ceil16(ci)
         self._tag("dgrad", L, N, H, W, ci, L.Cout)
         if self._tc2_ok([L.CoutP], H, W):
-            call("wsl_conv_tc2", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
+            call("wsl_conv_tc2", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks, None, None)
         elif self._tc_ok([L.CoutP], H, W):
             call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
         else:
@@ -215,6 +229,8 @@ class UNetExecutor:
               and (L.CoutP < 128 or L.CoutP % 128 == 0))
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and L.bn is not None:
             call("wsl_wgrad_first", s0, dy, self.gview(L.conv.weight), N, H, W, L.Cout)
+        elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W) and self.wgrad_version == 3 and (L.CoutP <= 64 or L.CoutP % 128 == 0):
+            call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W):
             call("wsl_wgrad_tc2", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         elif tc:
@@ -228,13 +244,16 @@ class UNetExecutor:
         if tc and L.bn is None:
             call("wsl_channel_sum", dy, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias))
 
-    def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None):
+    def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None, stat_rows=0):
         bn = L.bn
         C = L.Cout
         pk = L.packs(self.dev)
         save = self.buf(slot, tag + ".save", (2 * C,), torch.float32)
         ss = self.buf(slot, tag + ".ss", (2 * C,), torch.float32)
-        if training:
+        if training and stat_rows > 0:
+            call("wsl_bn_finalize", self._stat_buf, stat_rows, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss)
+        elif training:
             call("wsl_bn_stats", y, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                  bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"))
         else:
@@ -259,8 +278,30 @@ class UNetExecutor:
 
     # ---------------------------------------------------------------- forward
     def pack_all(self):
-        for L in self.layers:
-            L.pack(self.dev)
+        """fp32 master weights -> packed bf16/fp32 operands of every layer, ONE launch (table of pointers on device)."""
+        ptrs = tuple(L.conv.weight.data_ptr() for L in self.layers)
+        if getattr(self, "_pack_key", None) != (ptrs, str(self.dev)):
+            rows, first = [], 0
+            for L in self.layers:
+                pk = L.packs(self.dev)
+                beg = 0
+                for i, c in enumerate(L.srcC):
+                    rows.append([L.conv.weight.data_ptr(), pk["wf"].data_ptr() if i == 0 else 0, pk["wd"][i].data_ptr(),
+                                 pk["bf"].data_ptr() if i == 0 else 0, pk["bd"][i].data_ptr(), L.Cout, L.Cin, L.T, L.CoutP, L.CinP,
+                                 beg, c, first])
+                    first += L.T * L.CoutP * L.CinP
+                    beg += c
+            self._pack_table = torch.tensor(rows, dtype=torch.int64).to(self.dev)
+            self._pack_total = first
+            self._pack_n = len(rows)
+            self._pack_key = (ptrs, str(self.dev))
+        call("wsl_pack_conv_weights_batched", self._pack_table, self._pack_n, self._pack_total)
+        for L in self.layers:                      # biases: share the parameter storage (or copy into the 16-padded buffer)
+            pk = L.packs(self.dev)
+            if L.Cout == L.CoutP:
+                pk["bias"] = L.conv.bias.detach()
+            else:
+                pk["bias"][: L.Cout].copy_(L.conv.bias.detach())
 
     def forward(self, x: torch.Tensor, training: bool, need_grad: bool, masks: Optional[dict] = None,
                 chan_keep: Optional[list] = None):
@@ -287,14 +328,14 @@ class UNetExecutor:
             a1 = self.buf(slot, tag + ".a1", (N, h, w, C))
             y2 = self.buf(slot, tag + ".y2", (N, h, w, C))
             a2 = self.buf(slot, tag + ".a2", (N, h, w, C))
-            self.conv_fwd(l1, srcs, y1, 0, N, h, w, C, src_f32)
-            sv1, ss1 = self.bn_fwd(l1, y1, a1, N, h, w, training, slot, tag + ".bn1", mask)
-            self.conv_fwd(l2, [a1], y2, 0, N, h, w, C)
+            r1 = self.conv_fwd(l1, srcs, y1, 0, N, h, w, C, src_f32, want_stats=training)
+            sv1, ss1 = self.bn_fwd(l1, y1, a1, N, h, w, training, slot, tag + ".bn1", mask, stat_rows=r1)
+            r2 = self.conv_fwd(l2, [a1], y2, 0, N, h, w, C, want_stats=training)
             pooled = idx = None
             if pool:
                 pooled = self.buf(slot, tag + ".pool", (N, h // 2, w // 2, C))
                 idx = self.buf(slot, tag + ".pidx", (N, h // 2, w // 2, C), torch.uint8)
-            sv2, ss2 = self.bn_fwd(l2, y2, a2, N, h, w, training, slot, tag + ".bn2", None, pooled, idx)
+            sv2, ss2 = self.bn_fwd(l2, y2, a2, N, h, w, training, slot, tag + ".bn2", None, pooled, idx, stat_rows=r2)
             return {"srcs": srcs, "y1": y1, "a1": a1, "y2": y2, "a2": a2, "sv1": sv1, "ss1": ss1, "sv2": sv2, "ss2": ss2,
                     "pool": pooled, "pidx": idx, "mask": mask, "h": h, "w": w, "src_f32": src_f32}
 
