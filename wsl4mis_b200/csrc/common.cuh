@@ -106,3 +106,16 @@ __device__ __forceinline__ uint32_t wsl_hash32(uint64_t x) {
 __device__ __forceinline__ float wsl_uniform(uint64_t seed, uint64_t idx) {
   return (wsl_hash32(seed * 0x9E3779B97F4A7C15ULL + idx) >> 8) * (1.0f / 16777216.0f);
 }
+
+// 8 x 16 random bits for one 8-element vector (two splitmix64 rounds): dropout keeps element j when r16_j >= p*65536.
+__device__ __forceinline__ uint64_t wsl_splitmix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ void wsl_rand8x16(uint64_t seed, uint32_t vec, uint32_t (&r)[8]) {
+  const uint64_t a = wsl_splitmix64(seed + (uint64_t)vec * 0x9E3779B97F4A7C15ULL);
+  const uint64_t b = wsl_splitmix64(a + 0xD1B54A32D192ED03ULL);
+  r[0] = (uint32_t)(a & 0xffff); r[1] = (uint32_t)((a >> 16) & 0xffff); r[2] = (uint32_t)((a >> 32) & 0xffff); r[3] = (uint32_t)(a >> 48);
+  r[4] = (uint32_t)(b & 0xffff); r[5] = (uint32_t)((b >> 16) & 0xffff); r[6] = (uint32_t)((b >> 32) & 0xffff); r[7] = (uint32_t)(b >> 48);
+}

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
 // ================================================================================================
 // first layer (Cin = 1, unet.py:81 in_conv): x fp32 [N,H,W] -> y bf16 [N,H,W,16]; HBM-bound (36 B/pixel)
 // ================================================================================================
-__global__ void __launch_bounds__(TPB) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][9]*/,
+__global__ void __launch_bounds__(TPB, 4) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][9]*/,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                          int N, int H, int W) {
   __shared__ float s_w[9][16];
@@ -152,42 +152,38 @@ __global__ void __launch_bounds__(TPB) conv_first_kernel(const float* __restrict
   }
 }
 
-// dW[co][t] += sum_p dY[p][co] * x[p + tap_t]: every thread walks pixels with a 16x9 register tile (144 FMAs per
-// 11 loads), then warp-shuffle + one atomicAdd per warp and entry.
-__global__ void __launch_bounds__(128) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                          float* __restrict__ dw /*[16][9]*/, int N, int H, int W) {
-  float acc[16][9];
+// dW[co][t] += sum_p dY[p][co] * x[p + tap_t]: every thread walks pixels with an 8x9 register tile (blockIdx.y picks
+// the channel half; 72 FMAs per 10 loads), then warp-shuffle + one atomicAdd per warp and entry.
+__global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                             float* __restrict__ dw /*[16][9]*/, int N, int H, int W) {
+  float acc[8][9];
 #pragma unroll
-  for (int c = 0; c < 16; ++c)
+  for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+  const int half = blockIdx.y;
   const long long total = (long long)N * H * W;
   for (long long i = blockIdx.x * 128LL + threadIdx.x; i < total; i += (long long)gridDim.x * 128) {
     const int xx = (int)(i % W), yy = (int)((i / W) % H);
     const float* base = x + (i - (long long)yy * W - xx);
-    float v[9], g[16];
+    float v[9], g[8];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
       v[t] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
     }
-    const uint4* src = reinterpret_cast<const uint4*>(dy + i * 16);
-    float lo[8], hi[8];
-    unpack8(src[0], lo);
-    unpack8(src[1], hi);
+    unpack8(reinterpret_cast<const uint4*>(dy + i * 16)[half], g);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { g[c] = lo[c]; g[8 + c] = hi[c]; }
-#pragma unroll
-    for (int c = 0; c < 16; ++c)
+    for (int c = 0; c < 8; ++c)
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], v[t], acc[c][t]);
   }
 #pragma unroll
-  for (int c = 0; c < 16; ++c)
+  for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float r = warp_sum(acc[c][t]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(dw + c * 9 + t, r);
+      if ((threadIdx.x & 31) == 0) atomicAdd(dw + (half * 8 + c) * 9 + t, r);
     }
 }
 
@@ -418,73 +414,96 @@ __global__ void bn_eval_prepare_kernel(const float* gamma, const float* beta, co
   }
 }
 
-// A = dropout(leaky_relu(y*scale + shift)); optional fused 2x2 max-pool of A (DownBlock, unet.py:38).
-// mask: optional uint8 keep-mask (tests / parity); otherwise counter-based RNG keyed on (seed, element index).
-__device__ __forceinline__ void bn_act8(const uint4& raw, const float* __restrict__ ss, int C, int c0, float slope,
-                                        float drop_p, float inv_keep, const uint8_t* mask, unsigned long long seed,
-                                        long long eidx, float (&o)[8]) {
-  float v[8];
-  unpack8(raw, v);
-  uint2 mk = make_uint2(0x01010101u, 0x01010101u);
-  if (drop_p > 0.f && mask) mk = *reinterpret_cast<const uint2*>(mask + eidx);
+// ---- shared per-thread machinery of the BN forward/backward elementwise kernels ---------------------------------
+// Thread t owns channel group g = t % (C/8) for its whole life (per-channel constants live in registers) and walks
+// pixels p = block*rows + t/(C/8), p += grid*rows: a warp reads 512 contiguous bytes per tensor and iteration.
+struct DropCtx {
+  const uint8_t* mask;      // optional explicit keep mask (NHWC uint8)
+  unsigned long long seed;
+  uint32_t thresh;          // drop when r16 < thresh
+  float inv_keep;
+  bool on;
+};
+
+__device__ __forceinline__ uint32_t keep_bits8(const DropCtx& d, long long eidx, uint32_t vec) {
+  // bit j set -> element j is kept
+  if (!d.on) return 0xffu;
+  uint32_t bits = 0;
+  if (d.mask) {
+    const uint2 mk = *reinterpret_cast<const uint2*>(d.mask + eidx);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float z = fmaf(v[j], ss[c0 + j], ss[C + c0 + j]);
-    z = z > 0.f ? z : z * slope;
-    if (drop_p > 0.f) {
-      bool keep;
-      if (mask) keep = ((j < 4 ? (mk.x >> (8 * j)) : (mk.y >> (8 * (j - 4)))) & 0xffu) != 0;
-      else keep = wsl_uniform(seed, (unsigned long long)(eidx + j)) >= drop_p;
-      z = keep ? z * inv_keep : 0.f;
-    }
-    o[j] = z;
+    for (int j = 0; j < 8; ++j) bits |= ((((j < 4 ? (mk.x >> (8 * j)) : (mk.y >> (8 * (j - 4)))) & 0xffu) != 0) ? 1u : 0u) << j;
+  } else {
+    uint32_t r[8];
+    wsl_rand8x16(d.seed, vec, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bits |= (r[j] >= d.thresh ? 1u : 0u) << j;
   }
+  return bits;
 }
 
+__device__ __forceinline__ DropCtx make_drop(float p, const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr) {
+  DropCtx d;
+  d.on = p > 0.f;
+  d.mask = mask;
+  d.seed = seed + (seed_ptr ? *seed_ptr : 0ULL);
+  d.thresh = (uint32_t)(p * 65536.0f);
+  d.inv_keep = d.on ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+
+// A = dropout(leaky_relu(y*scale + shift)); optional fused 2x2 max-pool of A (DownBlock, unet.py:38).
 __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ y, const float* __restrict__ ss, int N, int H, int W, int C, float slope,
     float drop_p, const uint8_t* __restrict__ mask, unsigned long long seed, const unsigned long long* seed_ptr,
     __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ pooled, uint8_t* __restrict__ pool_idx) {
-  const int cg = C >> 3;
-  if (seed_ptr) seed += *seed_ptr;
-  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int cg = C >> 3, rows = TPB / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg, c0 = g * 8;
+  const DropCtx dc = make_drop(drop_p, mask, seed, seed_ptr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = ss[c0 + j]; sh[j] = ss[C + c0 + j]; }
+  auto act8 = [&](int p, float (&o)[8]) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + (long long)p * C + c0), v);
+    const uint32_t kb = keep_bits8(dc, (long long)p * C + c0, (uint32_t)p * cg + g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = fmaf(v[j], sc[j], sh[j]);
+      z = z > 0.f ? z : z * slope;
+      o[j] = ((kb >> j) & 1u) ? z * dc.inv_keep : 0.f;
+    }
+  };
   if (pooled == nullptr) {
-    const long long total = (long long)N * H * W * cg;
-    for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-      const long long p = i / cg;
-      const int c0 = (int)(i - p * cg) * 8;
+    const int P = N * H * W;
+    for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
       float o[8];
-      bn_act8(*reinterpret_cast<const uint4*>(y + p * C + c0), ss, C, c0, slope, drop_p, inv_keep, mask, seed, p * C + c0, o);
-      *reinterpret_cast<uint4*>(act + p * C + c0) = pack8(o);
+      act8(p, o);
+      *reinterpret_cast<uint4*>(act + (long long)p * C + c0) = pack8(o);
     }
   } else {
-    const int Hp = H >> 1, Wp = W >> 1;
-    const long long total = (long long)N * Hp * Wp * cg;
-    for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-      const long long q = i / cg;
-      const int c0 = (int)(i - q * cg) * 8;
-      const int xp = (int)(q % Wp), yp = (int)((q / Wp) % Hp);
-      const long long n = q / ((long long)Wp * Hp);
+    const int Hp = H >> 1, Wp = W >> 1, Q = N * Hp * Wp;
+    for (int q = blockIdx.x * rows + r; q < Q; q += gridDim.x * rows) {
+      const int xp = q % Wp, t = q / Wp, yp = t % Hp, n = t / Hp;
       float best[8];
       int arg[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const long long p = (n * H + yp * 2 + (k >> 1)) * W + xp * 2 + (k & 1);
-        float o[8];
-        bn_act8(*reinterpret_cast<const uint4*>(y + p * C + c0), ss, C, c0, slope, drop_p, inv_keep, mask, seed, p * C + c0, o);
+        const int p = (n * H + yp * 2 + (k >> 1)) * W + xp * 2 + (k & 1);
+        float o[8], ob[8];
+        act8(p, o);
         const uint4 pk = pack8(o);
-        *reinterpret_cast<uint4*>(act + p * C + c0) = pk;
-        float ob[8];
+        *reinterpret_cast<uint4*>(act + (long long)p * C + c0) = pk;
         unpack8(pk, ob);  // pool over the stored (bf16-rounded) activations
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (k == 0 || ob[j] > best[j]) { best[j] = ob[j]; arg[j] = k; }  // first maximum wins (torch)
       }
-      *reinterpret_cast<uint4*>(pooled + q * C + c0) = pack8(best);
+      *reinterpret_cast<uint4*>(pooled + (long long)q * C + c0) = pack8(best);
       uint2 ai;
       ai.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
       ai.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
-      *reinterpret_cast<uint2*>(pool_idx + q * C + c0) = ai;
+      *reinterpret_cast<uint2*>(pool_idx + (long long)q * C + c0) = ai;
     }
   }
 }
@@ -510,52 +529,73 @@ struct BnBwdArgs {
   int N, H, W, C;
 };
 
-__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, long long p, int c0, float (&dz)[8], float (&xh)[8]) {
-  float yv[8], g[8];
-  unpack8(*reinterpret_cast<const uint4*>(a.y + p * a.C + c0), yv);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  const int x = (int)(p % a.W), yy = (int)((p / a.W) % a.H);
-  const long long n = p / ((long long)a.W * a.H);
-  if (a.g0) {
-    float t[8];
-    unpack8(*reinterpret_cast<const uint4*>(a.g0 + p * a.C + c0), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += t[j];
-  }
-  if (a.g1) {
-    float t[8];
-    unpack8(*reinterpret_cast<const uint4*>(a.g1 + p * a.C + c0), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += t[j] * (a.cs1 ? a.cs1[n * a.C + c0 + j] : 1.f);
-  }
-  if (a.gp) {
-    const long long q = (n * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (x >> 1);
-    const int k = ((yy & 1) << 1) | (x & 1);
-    const uint2 ai = *reinterpret_cast<const uint2*>(a.pool_idx + q * a.C + c0);
-    float t[8];
-    unpack8(*reinterpret_cast<const uint4*>(a.gp + q * a.C + c0), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int aj = (j < 4 ? (ai.x >> (8 * j)) : (ai.y >> (8 * (j - 4)))) & 0xff;
-      if (aj == k) g[j] += t[j];
-    }
-  }
-  const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-  uint2 mk = make_uint2(0x01010101u, 0x01010101u);
-  if (a.drop_p > 0.f && a.mask) mk = *reinterpret_cast<const uint2*>(a.mask + p * a.C + c0);
+struct BnBwdThread {
+  float sc[8], sh[8], mean[8], istd[8];
+  int c0, g, cg;
+  DropCtx dc;
+};
+
+__device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs& a) {
+  BnBwdThread t;
+  t.cg = a.C >> 3;
+  t.g = threadIdx.x % t.cg;
+  t.c0 = t.g * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float z = fmaf(yv[j], a.ss[c0 + j], a.ss[a.C + c0 + j]);
-    float d = g[j] * (z > 0.f ? 1.f : a.slope);
-    if (a.drop_p > 0.f) {
-      bool keep;
-      if (a.mask) keep = ((j < 4 ? (mk.x >> (8 * j)) : (mk.y >> (8 * (j - 4)))) & 0xffu) != 0;
-      else keep = wsl_uniform(a.seed, (unsigned long long)(p * a.C + c0 + j)) >= a.drop_p;
-      d = keep ? d * inv_keep : 0.f;
+    t.sc[j] = a.ss[t.c0 + j]; t.sh[j] = a.ss[a.C + t.c0 + j];
+    t.mean[j] = a.save[t.c0 + j]; t.istd[j] = a.save[a.C + t.c0 + j];
+  }
+  t.dc = make_drop(a.drop_p, a.mask, a.seed, a.seed_ptr);
+  return t;
+}
+
+__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread& t, int p, float (&dz)[8], float (&xh)[8]) {
+  float yv[8], g[8];
+  const long long off = (long long)p * a.C + t.c0;
+  unpack8(*reinterpret_cast<const uint4*>(a.y + off), yv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (a.g0) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(a.g0 + off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += v[j];
+  }
+  if (a.g1 || a.gp) {
+    const int x = p % a.W, r = p / a.W, yy = r % a.H, n = r / a.H;
+    if (a.g1) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(a.g1 + off), v);
+      if (a.cs1) {
+        const float4 s0 = *reinterpret_cast<const float4*>(a.cs1 + (long long)n * a.C + t.c0);
+        const float4 s1 = *reinterpret_cast<const float4*>(a.cs1 + (long long)n * a.C + t.c0 + 4);
+        g[0] = fmaf(v[0], s0.x, g[0]); g[1] = fmaf(v[1], s0.y, g[1]); g[2] = fmaf(v[2], s0.z, g[2]); g[3] = fmaf(v[3], s0.w, g[3]);
+        g[4] = fmaf(v[4], s1.x, g[4]); g[5] = fmaf(v[5], s1.y, g[5]); g[6] = fmaf(v[6], s1.z, g[6]); g[7] = fmaf(v[7], s1.w, g[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += v[j];
+      }
     }
-    dz[j] = d;
-    xh[j] = (yv[j] - a.save[c0 + j]) * a.save[a.C + c0 + j];
+    if (a.gp) {
+      const long long q = ((long long)(n * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (x >> 1)) * a.C + t.c0;
+      const int k = ((yy & 1) << 1) | (x & 1);
+      const uint2 ai = *reinterpret_cast<const uint2*>(a.pool_idx + q);
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(a.gp + q), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int aj = (j < 4 ? (ai.x >> (8 * j)) : (ai.y >> (8 * (j - 4)))) & 0xff;
+        if (aj == k) g[j] += v[j];
+      }
+    }
+  }
+  const uint32_t kb = keep_bits8(t.dc, off, (uint32_t)p * t.cg + t.g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z = fmaf(yv[j], t.sc[j], t.sh[j]);
+    const float d = g[j] * (z > 0.f ? 1.f : a.slope);
+    dz[j] = ((kb >> j) & 1u) ? d * t.dc.inv_keep : 0.f;
+    xh[j] = (yv[j] - t.mean[j]) * t.istd[j];
   }
 }
 
@@ -563,20 +603,18 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
                                                             float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
                                                             float* partials, unsigned* ticket) {
   extern __shared__ float s_red[];
-  if (a.seed_ptr) a.seed += *a.seed_ptr;
-  const int C = a.C, cg = C >> 3, rows = TPB / cg;
-  const long long P = (long long)a.N * a.H * a.W;
-  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const BnBwdThread t = bn_bwd_thread(a);
+  const int C = a.C, cg = t.cg, rows = TPB / cg;
+  const int P = a.N * a.H * a.W;
+  const int r = threadIdx.x / cg;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  if (r < rows) {
-    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-      float dz[8], xh[8];
-      bn_bwd_dz8(a, p, g * 8, dz, xh);
+  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+    float dz[8], xh[8];
+    bn_bwd_dz8(a, t, p, dz, xh);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], xh[j], s2[j]); }
-    }
+    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], xh[j], s2[j]); }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
@@ -610,17 +648,19 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
 
 __global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
                                                            __nv_bfloat16* __restrict__ dy) {
-  const int C = a.C, cg = C >> 3;
-  if (a.seed_ptr) a.seed += *a.seed_ptr;
-  const long long total = (long long)a.N * a.H * a.W * cg;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-    const long long p = i / cg;
-    const int c0 = (int)(i - p * cg) * 8;
-    float dz[8], xh[8], o[8];
-    bn_bwd_dz8(a, p, c0, dz, xh);
+  const BnBwdThread t = bn_bwd_thread(a);
+  const int C = a.C, rows = TPB / t.cg;
+  const int P = a.N * a.H * a.W;
+  const int r = threadIdx.x / t.cg;
+  float k1[8], k2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = a.ss[c0 + j] * (dz[j] - coef[c0 + j] - xh[j] * coef[C + c0 + j]);
-    *reinterpret_cast<uint4*>(dy + p * C + c0) = pack8(o);
+  for (int j = 0; j < 8; ++j) { k1[j] = coef[t.c0 + j]; k2[j] = coef[C + t.c0 + j]; }
+  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+    float dz[8], xh[8], o[8];
+    bn_bwd_dz8(a, t, p, dz, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = t.sc[j] * (dz[j] - k1[j] - xh[j] * k2[j]);
+    *reinterpret_cast<uint4*>(dy + (long long)p * C + t.c0) = pack8(o);
   }
 }
 
@@ -905,8 +945,9 @@ WSL_API int wsl_bn_act_fwd(const void* y, const float* ss, int N, int H, int W, 
                            void* pooled, uint8_t* pool_idx, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_bn_act_fwd: C %% 8 != 0");
   WSL_REQUIRE(pooled == nullptr || (H % 2 == 0 && W % 2 == 0), "wsl_bn_act_fwd: pooling needs even H, W");
+  WSL_REQUIRE(TPB % (C / 8) == 0 && (long long)N * H * W < (1LL << 31), "wsl_bn_act_fwd: unsupported C=%d or too many pixels", C);
   const long long items = (long long)N * H * W * (C / 8) / (pooled ? 4 : 1);
-  bn_act_fwd_kernel<<<grid_for(items), TPB, 0, stream>>>((const __nv_bfloat16*)y, ss, N, H, W, C, slope, drop_p, mask, seed,
+  bn_act_fwd_kernel<<<grid_for((items + 1) / 2), TPB, 0, stream>>>((const __nv_bfloat16*)y, ss, N, H, W, C, slope, drop_p, mask, seed,
                                                          seed_ptr, (__nv_bfloat16*)act, (__nv_bfloat16*)pooled, pool_idx);
   return wsl_check_launch("bn_act_fwd");
 }
@@ -926,7 +967,7 @@ WSL_API int wsl_bn_bwd(const void* y, const float* ss, const float* save, const 
   bn_bwd_reduce_kernel<<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws));
   int rc = wsl_check_launch("bn_bwd_reduce");
   if (rc) return rc;
-  bn_bwd_apply_kernel<<<grid_for(P * (C / 8)), TPB, 0, stream>>>(a, coef, (__nv_bfloat16*)dy);
+  bn_bwd_apply_kernel<<<grid_for(P * (C / 8) / 2), TPB, 0, stream>>>(a, coef, (__nv_bfloat16*)dy);
   return wsl_check_launch("bn_bwd_apply");
 }
 
@@ -994,9 +1035,9 @@ WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, vo
 WSL_API int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, cudaStream_t stream) {
   WSL_REQUIRE(Cout == 16, "wsl_wgrad_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
   long long b = ((long long)N * H * W + 128 * 16 - 1) / (128 * 16);
-  if (b > 148 * 3) b = 148 * 3;
+  if (b > 148 * 4) b = 148 * 4;
   if (b < 1) b = 1;
-  wgrad_first_kernel<<<(int)b, 128, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
+  wgrad_first_kernel<<<dim3((int)b, 2), 128, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
   return wsl_check_launch("wgrad_first");
 }
 
