@@ -1,0 +1,106 @@
+"""The fused per-step body (wsl4mis_b200.engine.TrainStep) against the CPU oracle's step for every hot-path script
+variant: loss value, and the SGD update direction of every parameter; CUDA-graph replay == eager launch sequence."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import wsl_oracle as O
+from _gpu_util import chan_masks, cosine, elem_masks_nchw, ENC_MASK_KEYS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+if torch.cuda.is_available():
+    from wsl4mis_b200.engine import TrainStep
+    from wsl4mis_b200.networks.unet import UNet, UNet_CCT
+
+
+def _setup(cct, n, hw, seed=3):
+    torch.manual_seed(seed)
+    m = (UNet_CCT if cct else UNet)(1, 4)          # reference default init (bit-identical to the reference's)
+    p = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    em = elem_masks_nchw(5, n, hw, hw)
+    m.dropout_masks = {i: e.permute(0, 2, 3, 1).contiguous().to(DEV) for i, e in enumerate(em)}
+    ck = None
+    if cct:
+        ck = chan_masks(9, n)
+        m.channel_keep = [c.to(DEV) for c in ck]
+    image, label = O.synth_batch(n, hw, hw, seed=11, frac=0.05)
+    return m, p, {k: e for k, e in zip(ENC_MASK_KEYS, em)}, ck, image, label
+
+
+@pytest.mark.parametrize("variant,cct", [("pce", False), ("pce_gatedcrf", False), ("pce_gatedcrf", True), ("pce_ms", False),
+                                         ("pce_tv", False), ("dmpls", True)])
+def test_step_matches_oracle(variant, cct):
+    n, hw = 4, 64
+    m, p, om, ock, image, label = _setup(cct, n, hw)
+    step = TrainStep(m, variant, base_lr=0.01, graph=False)
+    import random
+    random.seed(123)
+    loss = step(image.to(DEV), label.to(DEV))
+    torch.cuda.synchronize()
+    beta = getattr(step, "beta", 0.5)
+    O.QUANT = True                                        # oracle emulating bf16 storage (see test_gpu_unet.py)
+    try:
+        if variant == "pce_gatedcrf" and cct:
+            # single-head script on a two-head model: loss on main_seg only
+            leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+            main, _ = O.unet_cct_forward(leaves, image, True, om, ock)
+            ref_loss = O.step_loss_pce_gatedcrf(main, image, label)[0]
+            names = [k for k, v in leaves.items() if v.requires_grad]
+            gs = torch.autograd.grad(ref_loss, [leaves[k] for k in names], allow_unused=True)
+            grads = {k: g for k, g in zip(names, gs)}
+        else:
+            ref_loss, grads, _ = O.full_step(p, image, label, variant, cct, om, ock, beta)
+    finally:
+        O.QUANT = None
+    assert abs(loss.item() - ref_loss.item()) < 0.02 * abs(ref_loss.item()) + 1e-4, (loss.item(), ref_loss.item())
+    # SGD first step: delta = -lr * (g + wd*w); compare directions parameter by parameter
+    named = dict(m.named_parameters())
+    worst = 1.0
+    for k, g in grads.items():
+        new = named[k].detach().cpu()
+        if g is None:                                      # untouched aux decoder: skipped by the optimiser
+            assert torch.equal(new, p[k]), k
+            continue
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue                                       # zero-gradient biases in front of BatchNorm
+        delta, ref_delta = new - p[k], -0.01 * (g + 1e-4 * p[k])
+        c = cosine(delta, ref_delta)
+        worst = min(worst, c)
+        assert c > 0.9, (variant, k, c)
+        assert abs(delta.norm().item() - ref_delta.norm().item()) < 0.35 * ref_delta.norm().item() + 1e-9, k
+    print(f"[{variant} cct={cct}] loss {loss.item():.5f} (oracle {ref_loss.item():.5f}), worst update cosine {worst:.4f}")
+
+
+def test_graph_replay_equals_eager():
+    n, hw = 4, 64
+    img, lab = O.synth_batch(n, hw, hw, seed=5, frac=0.05)
+    img, lab = img.to(DEV), lab.to(DEV)
+    losses = {}
+    finals = {}
+    for graph in (False, True):
+        torch.manual_seed(7)
+        m = UNet_CCT(1, 4).to(DEV)
+        step = TrainStep(m, "pce_gatedcrf", graph=graph)
+        ls = [step(img, lab).item() for _ in range(6)]
+        torch.cuda.synchronize()
+        losses[graph] = ls
+        finals[graph] = step.flat.clone()
+        assert step.iter_num == 6
+    assert np.allclose(losses[False], losses[True], rtol=2e-3), (losses[False], losses[True])
+    assert cosine(finals[False], finals[True]) > 0.999999
+    assert losses[True][-1] < losses[True][0]
+
+
+def test_lr_schedule_follows_the_script():
+    torch.manual_seed(0)
+    m = UNet(1, 4).to(DEV)
+    step = TrainStep(m, "pce", base_lr=0.03, max_iterations=100, graph=False)
+    img, lab = O.synth_batch(2, 32, 32, seed=1, frac=0.1)
+    for it in range(3):
+        step(img.to(DEV), lab.to(DEV))
+        assert abs(step.lr_dev.item() - O.poly_lr(0.03, it, 100)) < 1e-8

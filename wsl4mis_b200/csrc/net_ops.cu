@@ -599,7 +599,7 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread
   }
 }
 
-__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ dgamma,
+__global__ void __launch_bounds__(TPB, 2) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
                                                             float* partials, unsigned* ticket) {
   extern __shared__ float s_red[];
@@ -610,7 +610,18 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + stride < P; p += 2 * stride) {   // two independent pixels per iteration: twice the loads in flight
+    float dz[8], xh[8], dz2[8], xh2[8];
+    bn_bwd_dz8(a, t, p, dz, xh);
+    bn_bwd_dz8(a, t, p + stride, dz2, xh2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], xh[j], s2[j]); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += dz2[j]; s2[j] = fmaf(dz2[j], xh2[j], s2[j]); }
+  }
+  for (; p < P; p += stride) {
     float dz[8], xh[8];
     bn_bwd_dz8(a, t, p, dz, xh);
 #pragma unroll
@@ -646,7 +657,7 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-__global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
+__global__ void __launch_bounds__(TPB, 2) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
                                                            __nv_bfloat16* __restrict__ dy) {
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, rows = TPB / t.cg;
@@ -655,7 +666,20 @@ __global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(BnBwdArgs a, const fl
   float k1[8], k2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { k1[j] = coef[t.c0 + j]; k2[j] = coef[C + t.c0 + j]; }
-  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + stride < P; p += 2 * stride) {
+    float dz[8], xh[8], dz2[8], xh2[8], o[8];
+    bn_bwd_dz8(a, t, p, dz, xh);
+    bn_bwd_dz8(a, t, p + stride, dz2, xh2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = t.sc[j] * (dz[j] - k1[j] - xh[j] * k2[j]);
+    *reinterpret_cast<uint4*>(dy + (long long)p * C + t.c0) = pack8(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = t.sc[j] * (dz2[j] - k1[j] - xh2[j] * k2[j]);
+    *reinterpret_cast<uint4*>(dy + (long long)(p + stride) * C + t.c0) = pack8(o);
+  }
+  for (; p < P; p += stride) {
     float dz[8], xh[8], o[8];
     bn_bwd_dz8(a, t, p, dz, xh);
 #pragma unroll
@@ -678,27 +702,27 @@ __device__ __forceinline__ void up_src(int d, int in, int out, int& i0, int& i1,
 
 __global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ t, int N, int h, int w, int C,
                                                              __nv_bfloat16* __restrict__ u) {
-  const int cg = C >> 3, H = 2 * h, W = 2 * w;
-  const long long total = (long long)N * H * W * cg;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-    const long long p = i / cg;
-    const int c0 = (int)(i - p * cg) * 8;
-    const int x = (int)(p % W), y = (int)((p / W) % H);
-    const long long n = p / ((long long)W * H);
-    int y0, y1, x0, x1;
-    float ly, lx;
-    up_src(y, h, H, y0, y1, ly);
-    up_src(x, w, W, x0, x1, lx);
+  // thread t owns channel group g = t % (C/8); rows of the block walk output pixels (32-bit indexing)
+  const int cg = C >> 3, rows = TPB / cg, H = 2 * h, W = 2 * w;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg, c0 = g * 8;
+  const int P = N * H * W;
+  const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+    const int x = p % W, q = p / W, y = q % H, n = q / H;
+    const float sy = ry * (float)y, sx = rx * (float)x;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
     float a[8], b[8], c[8], d[8], o[8];
-    const __nv_bfloat16* base = t + n * (long long)h * w * C + c0;
-    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x0) * C), a);
-    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x1) * C), b);
-    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x0) * C), c);
-    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x1) * C), d);
+    const __nv_bfloat16* base = t + (long long)n * h * w * C + c0;
+    unpack8(*reinterpret_cast<const uint4*>(base + (y0 * w + x0) * C), a);
+    unpack8(*reinterpret_cast<const uint4*>(base + (y0 * w + x1) * C), b);
+    unpack8(*reinterpret_cast<const uint4*>(base + (y1 * w + x0) * C), c);
+    unpack8(*reinterpret_cast<const uint4*>(base + (y1 * w + x1) * C), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
-    *reinterpret_cast<uint4*>(u + p * C + c0) = pack8(o);
+    *reinterpret_cast<uint4*>(u + (long long)p * C + c0) = pack8(o);
   }
 }
 
@@ -973,7 +997,8 @@ WSL_API int wsl_bn_bwd(const void* y, const float* ss, const float* save, const 
 
 WSL_API int wsl_upsample2x_fwd(const void* t, int N, int h, int w, int C, void* u, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_fwd: C %% 8 != 0");
-  upsample2x_fwd_kernel<<<grid_for((long long)N * 4 * h * w * (C / 8)), TPB, 0, stream>>>((const __nv_bfloat16*)t, N, h, w, C, (__nv_bfloat16*)u);
+  WSL_REQUIRE(TPB % (C / 8) == 0, "wsl_upsample2x_fwd: unsupported C=%d", C);
+  upsample2x_fwd_kernel<<<grid_for((long long)N * 4 * h * w * (C / 8) / 2), TPB, 0, stream>>>((const __nv_bfloat16*)t, N, h, w, C, (__nv_bfloat16*)u);
   return wsl_check_launch("upsample2x_fwd");
 }
 

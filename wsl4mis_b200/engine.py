@@ -21,6 +21,7 @@ import random
 
 import torch
 
+from . import ddp
 from ._lib import call, workspace
 
 VARIANTS = ("pce", "pce_gatedcrf", "pce_ms", "pce_tv", "dmpls")
@@ -54,6 +55,8 @@ class TrainStep:
             p.data = self.flat[off:off + p.numel()].view_as(p)
             self.offsets[id(p)] = (off, p.numel())
             off += p.numel()
+        if self.world_size > 1:
+            ddp.broadcast_flat(self.flat, 0, self.pg)     # identical replicas (DDP does the same at construction)
         self.mom = torch.zeros_like(self.flat)
         self.lr_dev = torch.full((1,), self.base_lr, dtype=torch.float32, device=dev)
         self.two_heads = len(self.ex.dec) == 2
@@ -157,8 +160,7 @@ class TrainStep:
 
     def _allreduce(self, gflat):
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(gflat[: self.n_trained], group=self.pg)
+            ddp.allreduce_flat(gflat[: self.n_trained], self.pg)
 
     # ------------------------------------------------------------------
     def __call__(self, image, label):
