@@ -530,7 +530,7 @@ struct BnBwdArgs {
 };
 
 struct BnBwdThread {
-  float sc[8], sh[8], mean[8], istd[8];
+  float sc[8], sh[8];    // z = y*sc + sh (only its sign is needed)
   int c0, g, cg;
   DropCtx dc;
 };
@@ -541,16 +541,14 @@ __device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs& a) {
   t.g = threadIdx.x % t.cg;
   t.c0 = t.g * 8;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    t.sc[j] = a.ss[t.c0 + j]; t.sh[j] = a.ss[a.C + t.c0 + j];
-    t.mean[j] = a.save[t.c0 + j]; t.istd[j] = a.save[a.C + t.c0 + j];
-  }
+  for (int j = 0; j < 8; ++j) { t.sc[j] = a.ss[t.c0 + j]; t.sh[j] = a.ss[a.C + t.c0 + j]; }
   t.dc = make_drop(a.drop_p, a.mask, a.seed, a.seed_ptr);
   return t;
 }
 
-__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread& t, int p, float (&dz)[8], float (&xh)[8]) {
-  float yv[8], g[8];
+// dz (gradient w.r.t. the BN output z) and the raw conv output y of 8 channels of pixel p
+__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread& t, int p, float (&dz)[8], float (&yv)[8]) {
+  float g[8];
   const long long off = (long long)p * a.C + t.c0;
   unpack8(*reinterpret_cast<const uint4*>(a.y + off), yv);
 #pragma unroll
@@ -595,37 +593,28 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread
     const float z = fmaf(yv[j], t.sc[j], t.sh[j]);
     const float d = g[j] * (z > 0.f ? 1.f : a.slope);
     dz[j] = ((kb >> j) & 1u) ? d * t.dc.inv_keep : 0.f;
-    xh[j] = (yv[j] - t.mean[j]) * t.istd[j];
   }
 }
 
-__global__ void __launch_bounds__(TPB, 2) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
-                                                            float* partials, unsigned* ticket) {
+__global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
+                                                               float* partials, unsigned* ticket) {
   extern __shared__ float s_red[];
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, cg = t.cg, rows = TPB / cg;
   const int P = a.N * a.H * a.W;
   const int r = threadIdx.x / cg;
+  float xa[8], xb[8];     // xhat = y*xa + xb
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { xa[j] = a.save[C + t.c0 + j]; xb[j] = -a.save[t.c0 + j] * xa[j]; }
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  const int stride = gridDim.x * rows;
-  int p = blockIdx.x * rows + r;
-  for (; p + stride < P; p += 2 * stride) {   // two independent pixels per iteration: twice the loads in flight
-    float dz[8], xh[8], dz2[8], xh2[8];
-    bn_bwd_dz8(a, t, p, dz, xh);
-    bn_bwd_dz8(a, t, p + stride, dz2, xh2);
+  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+    float dz[8], yv[8];
+    bn_bwd_dz8(a, t, p, dz, yv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], xh[j], s2[j]); }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] += dz2[j]; s2[j] = fmaf(dz2[j], xh2[j], s2[j]); }
-  }
-  for (; p < P; p += stride) {
-    float dz[8], xh[8];
-    bn_bwd_dz8(a, t, p, dz, xh);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], xh[j], s2[j]); }
+    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], fmaf(yv[j], xa[j], xb[j]), s2[j]); }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
@@ -651,39 +640,29 @@ __global__ void __launch_bounds__(TPB, 2) bn_bwd_reduce_kernel(BnBwdArgs a, floa
     const double x = s_fin[c], y = s_fin[C + c];
     dbeta[c] = (float)x;
     dgamma[c] = (float)y;
-    coef[c] = (float)(x / (double)P);
-    coef[C + c] = (float)(y / (double)P);
+    // apply-pass constants: dY = dz*A + y*B + D with A = scale, B = -scale*c2*invstd, D = -scale*c1 + scale*c2*mean*invstd
+    const double c1 = x / (double)P, c2 = y / (double)P;
+    const double sc = (double)a.ss[c], istd = (double)a.save[C + c], mean = (double)a.save[c];
+    coef[c] = (float)(-sc * c2 * istd);
+    coef[C + c] = (float)(-sc * c1 + sc * c2 * mean * istd);
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-__global__ void __launch_bounds__(TPB, 2) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
-                                                           __nv_bfloat16* __restrict__ dy) {
+__global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
+                                                              __nv_bfloat16* __restrict__ dy) {
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, rows = TPB / t.cg;
   const int P = a.N * a.H * a.W;
   const int r = threadIdx.x / t.cg;
-  float k1[8], k2[8];
+  float kb_[8], kd_[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { k1[j] = coef[t.c0 + j]; k2[j] = coef[C + t.c0 + j]; }
-  const int stride = gridDim.x * rows;
-  int p = blockIdx.x * rows + r;
-  for (; p + stride < P; p += 2 * stride) {
-    float dz[8], xh[8], dz2[8], xh2[8], o[8];
-    bn_bwd_dz8(a, t, p, dz, xh);
-    bn_bwd_dz8(a, t, p + stride, dz2, xh2);
+  for (int j = 0; j < 8; ++j) { kb_[j] = coef[t.c0 + j]; kd_[j] = coef[C + t.c0 + j]; }
+  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+    float dz[8], yv[8], o[8];
+    bn_bwd_dz8(a, t, p, dz, yv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = t.sc[j] * (dz[j] - k1[j] - xh[j] * k2[j]);
-    *reinterpret_cast<uint4*>(dy + (long long)p * C + t.c0) = pack8(o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = t.sc[j] * (dz2[j] - k1[j] - xh2[j] * k2[j]);
-    *reinterpret_cast<uint4*>(dy + (long long)(p + stride) * C + t.c0) = pack8(o);
-  }
-  for (; p < P; p += stride) {
-    float dz[8], xh[8], o[8];
-    bn_bwd_dz8(a, t, p, dz, xh);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = t.sc[j] * (dz[j] - k1[j] - xh[j] * k2[j]);
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(dz[j], t.sc[j], fmaf(yv[j], kb_[j], kd_[j]));
     *reinterpret_cast<uint4*>(dy + (long long)p * C + t.c0) = pack8(o);
   }
 }

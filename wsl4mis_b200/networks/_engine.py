@@ -16,6 +16,7 @@ All launches go to torch's current stream, never allocate or synchronise, and ar
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from typing import Dict, List, Optional, Sequence
@@ -127,6 +128,12 @@ class UNetExecutor:
         self.use_tc2 = os.environ.get("WSL4MIS_NO_TC2", "0") != "1"
         self.wgrad_version = int(os.environ.get("WSL4MIS_WGRAD", "3"))
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
+        self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
+        self._side = None
+        self._on_side = False
+        self._side_dirty = False
+        self._stat_bufs = {}
+        self._stat_rows = ctypes.c_int(0)
         self.stats = {"launches": 0}
 
     # ---------------------------------------------------------------- buffers
@@ -153,7 +160,48 @@ class UNetExecutor:
         return self.grads()[1][id(p)]
 
     def _ws(self, tag):
-        return workspace(tag, self.dev)
+        return workspace(tag + ("" if not self._on_side else ".side"), self.dev)
+
+    def _stat_scratch(self):
+        """per-stream scratch for the conv-epilogue BatchNorm partial rows"""
+        key = "side" if self._on_side else "main"
+        if key not in self._stat_bufs or self._stat_bufs[key].device != self.dev:
+            self._stat_bufs[key] = torch.zeros(592 * 2 * 256, dtype=torch.float32, device=self.dev)
+        return self._stat_bufs[key]
+
+    # ---------------------------------------------------------------- two-stream scheduling
+    # Independent work is issued on a side stream so that HBM-bound elementwise kernels of one chain overlap the
+    # tensor-core kernels of the other: (a) the aux decoder's forward runs beside the main decoder's, (b) every
+    # weight-gradient kernel runs beside the data-gradient -> BatchNorm-backward chain.  Inside a captured CUDA
+    # graph the fork/join events become graph edges.
+    def _side_stream(self):
+        if self._side is None or self._side.device != self.dev:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
+
+    @contextlib.contextmanager
+    def on_side(self):
+        if not self.multi_stream:
+            yield
+            return
+        side = self._side_stream()
+        ev = torch.cuda.Event()
+        ev.record()                      # everything issued so far on the main stream ...
+        side.wait_event(ev)              # ... is visible to the side stream
+        self._on_side = True
+        try:
+            with torch.cuda.stream(side):
+                yield
+        finally:
+            self._on_side = False
+            self._side_dirty = True
+
+    def join_side(self):
+        if self.multi_stream and self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream())
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_dirty = False
 
     # ---------------------------------------------------------------- primitive launches
     def _tag(self, kind, L, N, H, W, cin, cout):
@@ -190,11 +238,9 @@ class UNetExecutor:
             call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, N, H, W, L.Cout)
         elif not src_f32 and self._tc2_ok(L.srcC, H, W):
             if want_stats and self.fuse_bn_stats:
-                if getattr(self, "_stat_buf", None) is None or self._stat_buf.device != self.dev:
-                    self._stat_buf = torch.zeros(592 * 2 * 256, dtype=torch.float32, device=self.dev)
-                    self._stat_rows = ctypes.c_int(0)
+                sb = self._stat_scratch()
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks,
-                     self._stat_buf, ctypes.addressof(self._stat_rows))
+                     sb, ctypes.addressof(self._stat_rows))
                 rows = self._stat_rows.value
             else:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks, None, None)
@@ -251,7 +297,7 @@ class UNetExecutor:
         save = self.buf(slot, tag + ".save", (2 * C,), torch.float32)
         ss = self.buf(slot, tag + ".ss", (2 * C,), torch.float32)
         if training and stat_rows > 0:
-            call("wsl_bn_finalize", self._stat_buf, stat_rows, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+            call("wsl_bn_finalize", self._stat_scratch(), stat_rows, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                  bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss)
         elif training:
             call("wsl_bn_stats", y, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
@@ -354,8 +400,9 @@ class UNetExecutor:
         feats = [r["a2"] for r in rec["enc"]]
 
         # ---- decoders (unet.py:123-135; aux branch sees channel-dropped features, :344) ----
-        outs = []
-        for di, (ups, oc) in enumerate(self.dec):
+        outs = [torch.empty((N, self.n_class, H, W), dtype=torch.float32, device=self.dev) for _ in self.dec]
+
+        def run_decoder(di, ups, oc):
             drec = {"ups": [], "cs": None}
             fe = feats
             if self.aux[di]:
@@ -385,11 +432,17 @@ class UNetExecutor:
                 r["xlow"] = xlow
                 drec["ups"].append(r)
                 xlow = r["a2"]
-            logits = torch.empty((N, self.n_class, H, W), dtype=torch.float32, device=self.dev)
-            self.conv_fwd(oc, [xlow], logits, 1, N, H, W, self.n_class)
+            self.conv_fwd(oc, [xlow], outs[di], 1, N, H, W, self.n_class)
             drec["xlast"] = xlow
-            rec["dec"].append(drec)
-            outs.append(logits)
+            return drec
+
+        drecs = [None] * len(self.dec)
+        for di in range(len(self.dec) - 1, 0, -1):          # aux decoders first, on the side stream
+            with self.on_side():
+                drecs[di] = run_decoder(di, *self.dec[di])
+        drecs[0] = run_decoder(0, *self.dec[0])
+        self.join_side()
+        rec["dec"] = drecs
         if need_grad:
             self._recs[slot] = rec
         return outs, slot
@@ -425,13 +478,15 @@ class UNetExecutor:
             dy2 = B(tag + ".dy2", (N, h, w, C))
             self.bn_bwd(l2, r["y2"], r["ss2"], r["sv2"], g0, g1, cs1, gpool, r["pidx"] if gpool is not None else None,
                         None, dy2, N, h, w, slot, tag + ".bn2")
-            self.conv_wgrad(l2, [r["a1"]], dy2, N, h, w)
+            with self.on_side():
+                self.conv_wgrad(l2, [r["a1"]], dy2, N, h, w)
             da1 = B(tag + ".da1", (N, h, w, C))
             self.conv_dgrad(l2, 0, dy2, da1, N, h, w)
             dy1 = B(tag + ".dy1", (N, h, w, C))
             self.bn_bwd(l1, r["y1"], r["ss1"], r["sv1"], da1, None, None, None, None, r["mask"], dy1, N, h, w, slot,
                         tag + ".bn1")
-            self.conv_wgrad(l1, r["srcs"], dy1, N, h, w, r["src_f32"])
+            with self.on_side():
+                self.conv_wgrad(l1, r["srcs"], dy1, N, h, w, r["src_f32"])
             outs = []
             if need_dsrc:
                 for i, c in enumerate(l1.srcC):
@@ -450,7 +505,8 @@ class UNetExecutor:
             g = g.contiguous()
             dl = B(f"dec{di}.dl", (N, H, W, 16))
             call("wsl_nchw_f32_to_nhwc_bf16", g, N, self.n_class, H, W, 16, dl)
-            self.conv_wgrad(oc, [drec["xlast"]], dl, N, H, W)
+            with self.on_side():
+                self.conv_wgrad(oc, [drec["xlast"]], dl, N, H, W)
             da = B(f"dec{di}.dlast", (N, H, W, ft[0]))
             self.conv_dgrad(oc, 0, dl, da, N, H, W)
             for j in range(3, -1, -1):
@@ -462,7 +518,8 @@ class UNetExecutor:
                 hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
                 dt = B(f"dec{di}.up{j}.dt", (N, hh, ww, C2))
                 call("wsl_upsample2x_bwd", du, N, hh, ww, C2, dt)
-                self.conv_wgrad(c1, [r["xlow"]], dt, N, hh, ww)
+                with self.on_side():
+                    self.conv_wgrad(c1, [r["xlow"]], dt, N, hh, ww)
                 da = B(f"dec{di}.up{j}.dxlow", (N, hh, ww, c1.Cin))
                 self.conv_dgrad(c1, 0, dt, da, N, hh, ww)
             skip_grads[4].append((da, drec["cs"][4] if drec["cs"] else None))
@@ -479,4 +536,5 @@ class UNetExecutor:
             g1, cs1 = scaled[0] if scaled else (None, None)
             d = block_bwd(f"enc{i}", self.enc_blocks[i], r, g0, g1, cs1, gpool, need_dsrc=(i > 0))
             gpool = d[0] if i > 0 else None
+        self.join_side()
         return gflat
