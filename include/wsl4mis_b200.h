@@ -11,7 +11,9 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*-compatible handle), never
  *     allocates, never synchronises; the caller owns all buffers;
  *   - return 0 on success, negative on error; wsl_last_error() returns a thread-local message;
- *   - "act" tensors are channels-last (NHWC) bf16; logits / probabilities / losses are fp32 NCHW;
+ *   - "act" tensors are channels-last (NHWC); their storage type is bf16 (`dtype` 0, the fast tensor-core path) or
+ *     fp32 (`dtype` 1, the reference-accurate parity mode on the CUDA-core kernels); logits / probabilities /
+ *     losses are fp32 NCHW;
  *   - `ws` is a caller-provided workspace of wsl_workspace_floats() floats, zero-initialised ONCE by the
  *     caller (kernels leave its ticket words zero again); one workspace must not be shared by two kernels
  *     that may run concurrently.
@@ -82,20 +84,22 @@ int wsl_tv_loss(const float* probs, int planes, int H, int W, float grad_scale, 
 
 /* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the
  * data gradient.  Two channels-last sources model torch.cat([x2,x1],1) (unet.py:67).
- * out_mode 0: bf16 NHWC with CoutStore channels; 1: fp32 NCHW with CoutStore channels. */
+ * out_mode 0: bf16 NHWC with CoutStore channels; 1: fp32 NCHW with CoutStore channels; 2: fp32 NHWC.
+ * src_f32: sources are fp32 (a single-channel image, or fp32 NHWC activations with C %% 8 == 0). */
 int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const float* wpk,
                     const float* bias, void* out, int out_mode, int N, int H, int W, int CinP, int CoutP,
                     int CoutStore, int ksize, cudaStream_t stream);
 
 /* weight (+bias) gradient of the same convolutions, accumulated into zero-filled fp32 torch-layout grads. */
-int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int CoutP,
-                     float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
+int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int dy_f32,
+                     int CoutP, float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
 
 /* first layer (Cin = 1 -> 16, unet.py:81): x fp32 [N,H,W], w fp32 torch layout [16][1][3][3], y bf16 NHWC; and its
  * weight gradient (dw accumulated, zero-filled by the caller; the bias feeds BatchNorm -> zero gradient). */
-int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout,
                    cudaStream_t stream);
-int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, cudaStream_t stream);
+int wsl_wgrad_first(const float* x, const void* dy, int dtype, float* dw, int N, int H, int W, int Cout,
+                    cudaStream_t stream);
 
 /* tcgen05 implicit-GEMM convolution (conv_tc.cu): same contract as wsl_conv_direct for bf16 NHWC sources with
  * channel counts that are multiples of 16.  wpk_bf16: [taps][CoutP][CinP] (K-major).  Requires wsl_tc_available(). */
@@ -125,11 +129,11 @@ int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void
 int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                   int W, int CoutReal, int ksize, cudaStream_t stream);
 /* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
-int wsl_channel_sum(const void* x, long long P, int C, int Creal, float* out, cudaStream_t stream);
+int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, cudaStream_t stream);
 
 /* nn.BatchNorm2d training statistics (unet.py:20,24): save = {mean[C], invstd[C]}, ss = {scale[C], shift[C]};
  * running stats / num_batches_tracked updated in place when non-NULL. */
-int wsl_bn_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
+int wsl_bn_stats(const void* y, int dtype, long long P, int C, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
                  float* ss, float* ws, cudaStream_t stream);
 int wsl_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
@@ -138,28 +142,28 @@ int wsl_bn_eval_prepare(const float* gamma, const float* beta, const float* runn
 /* BN-affine + LeakyReLU(slope) + Dropout(p) (unet.py:20-22) and, when pooled != NULL, MaxPool2d(2) (unet.py:38)
  * of the result.  mask: optional uint8 keep mask (NHWC); NULL -> counter RNG on `seed` (+ *seed_ptr when non-NULL, so a
  * captured CUDA graph draws fresh masks every replay). */
-int wsl_bn_act_fwd(const void* y, const float* ss, int N, int H, int W, int C, float slope, float drop_p,
+int wsl_bn_act_fwd(const void* y, int dtype, const float* ss, int N, int H, int W, int C, float slope, float drop_p,
                    const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr, void* act,
                    void* pooled, uint8_t* pool_idx, cudaStream_t stream);
 
 /* backward of the same chain: dA = g0 + cs1*g1 + maxpool-routed gpool (each optional) -> dY (bf16), dgamma, dbeta. */
-int wsl_bn_bwd(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
                const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
                cudaStream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:56-57) and its transpose. */
-int wsl_upsample2x_fwd(const void* t, int N, int h, int w, int C, void* u, cudaStream_t stream);
-int wsl_upsample2x_bwd(const void* du, int N, int h, int w, int C, void* dt, cudaStream_t stream);
+int wsl_upsample2x_fwd(const void* t, int dtype, int N, int h, int w, int C, void* u, cudaStream_t stream);
+int wsl_upsample2x_bwd(const void* du, int dtype, int N, int h, int w, int C, void* dt, cudaStream_t stream);
 
 /* F.dropout2d(x, 0.5) of the aux branch (unet.py:254-256,344): cs[N*C] in {0, 1/(1-p)}. */
 int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long* seed_ptr, int n, float p, float* cs,
                       cudaStream_t stream);
-int wsl_chan_scale(const void* a, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream);
+int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream);
 
 /* layout helpers at the API boundary */
-int wsl_nchw_f32_to_nhwc_bf16(const float* src, int N, int Creal, int H, int W, int CP, void* dst, cudaStream_t stream);
-int wsl_nhwc_bf16_to_nchw_f32(const void* src, int N, int C, int H, int W, float* dst, cudaStream_t stream);
+int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, cudaStream_t stream);
+int wsl_nhwc_to_nchw_f32(const void* src, int dtype, int N, int C, int H, int W, float* dst, cudaStream_t stream);
 
 /* fp32 torch-layout conv weight -> packed operands (any output may be NULL), see net_ops.cu */
 int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,

@@ -150,7 +150,7 @@ def test_wgrad_direct(case):
     else:
         s0 = nhwc(x[:, :C0]).to(DEV)
         s1 = nhwc(x[:, C0:]).to(DEV) if C1 else None
-    call("wsl_wgrad_direct", s0, C0, s1, C1, 1 if f32src else 0, nhwc(dy).to(DEV), CoutP, dw, db, N, H, W, Cout, ks)
+    call("wsl_wgrad_direct", s0, C0, s1, C1, 1 if f32src else 0, nhwc(dy).to(DEV), 0, CoutP, dw, db, N, H, W, Cout, ks)
     torch.cuda.synchronize()
     xr = x.double().requires_grad_(False)
     wz = torch.zeros(Cout, Cin, ks, ks, dtype=torch.double, requires_grad=True)
@@ -194,7 +194,7 @@ def test_wgrad_tc(case, ver):
     dyd = nhwc(dy).to(DEV)
     call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks)
     db = torch.zeros(Cout, device=DEV)
-    call("wsl_channel_sum", dyd, N * H * W, CoutP, Cout, db)
+    call("wsl_channel_sum", dyd, 0, N * H * W, CoutP, Cout, db)
     torch.cuda.synchronize()
     wz = torch.zeros(Cout, Cin, ks, ks, dtype=torch.double, requires_grad=True)
     bz = torch.zeros(Cout, dtype=torch.double, requires_grad=True)
@@ -216,13 +216,13 @@ def test_first_layer_kernels(shape):
     w = torch.randn(16, 1, 3, 3, generator=g) * 0.5
     b = torch.randn(16, generator=g) * 0.1
     y = torch.zeros((N, H, W, 16), device=DEV, dtype=BF)
-    call("wsl_conv_first", x.to(DEV), w.to(DEV), b.to(DEV), y, N, H, W, 16)
+    call("wsl_conv_first", x.to(DEV), w.to(DEV), b.to(DEV), y, 0, N, H, W, 16)
     torch.cuda.synchronize()
     ref = F.conv2d(x, w, b, padding=1)
     assert (nchw(y.cpu()) - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
     dy = bf16_round(torch.randn(N, 16, H, W, generator=g))
     dw = torch.zeros(16, 1, 3, 3, device=DEV)
-    call("wsl_wgrad_first", x.to(DEV), nhwc(dy).to(DEV), dw, N, H, W, 16)
+    call("wsl_wgrad_first", x.to(DEV), nhwc(dy).to(DEV), 0, dw, N, H, W, 16)
     torch.cuda.synchronize()
     wz = torch.zeros(16, 1, 3, 3, dtype=torch.double, requires_grad=True)
     (gw,) = torch.autograd.grad(F.conv2d(x.double(), wz, None, padding=1), wz, dy.double())
@@ -240,7 +240,7 @@ def test_bn_stats_and_act(shape):
     save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
     rmd, rvd = rm.to(DEV), rv.to(DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
-    call("wsl_bn_stats", yd, N * H * W, C, gamma.to(DEV), beta.to(DEV), rmd, rvd, nbt, 0.1, 1e-5, save, ss, workspace("bn"))
+    call("wsl_bn_stats", yd, 0, N * H * W, C, gamma.to(DEV), beta.to(DEV), rmd, rvd, nbt, 0.1, 1e-5, save, ss, workspace("bn"))
     rm2, rv2 = rm.clone(), rv.clone()
     ref = F.batch_norm(y, rm2, rv2, gamma, beta, True, 0.1, 1e-5)
     torch.cuda.synchronize()
@@ -255,7 +255,7 @@ def test_bn_stats_and_act(shape):
     pooled = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=BF)
     pidx = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=torch.uint8)
     mk = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
-    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, mk, 0, None, act, pooled, pidx)
+    call("wsl_bn_act_fwd", yd, 0, ss, N, H, W, C, 0.01, p, mk, 0, None, act, pooled, pidx)
     torch.cuda.synchronize()
     ra = F.leaky_relu(ref, 0.01) * mask / (1 - p)
     assert (nchw(act.cpu()) - ra).abs().max().item() <= 2 ** -8 * ra.abs().max().item() + 1e-6
@@ -271,8 +271,8 @@ def test_bn_stats_and_act(shape):
     # counter-RNG dropout keeps ~ (1-p) of the elements and is reproduced by the same seed
     a1 = torch.zeros_like(act)
     a2 = torch.zeros_like(act)
-    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, None, 1234, None, a1, None, None)
-    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, None, 1234, None, a2, None, None)
+    call("wsl_bn_act_fwd", yd, 0, ss, N, H, W, C, 0.01, p, None, 1234, None, a1, None, None)
+    call("wsl_bn_act_fwd", yd, 0, ss, N, H, W, C, 0.01, p, None, 1234, None, a2, None, None)
     torch.cuda.synchronize()
     assert torch.equal(a1, a2)
     frac = (a1 != 0).float().mean().item()
@@ -305,15 +305,15 @@ def test_bn_backward_chain(shape):
     # kernels
     yd = nhwc(y).to(DEV)
     save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
-    call("wsl_bn_stats", yd, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
+    call("wsl_bn_stats", yd, 0, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
     act = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
     pooled = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=BF)
     pidx = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=torch.uint8)
     mk = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
-    call("wsl_bn_act_fwd", yd, ss, N, H, W, C, 0.01, p, mk, 0, None, act, pooled, pidx)
+    call("wsl_bn_act_fwd", yd, 0, ss, N, H, W, C, 0.01, p, mk, 0, None, act, pooled, pidx)
     dgam, dbet, coef = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2 * C, device=DEV)
     dy = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
-    call("wsl_bn_bwd", yd, ss, save, nhwc(g0).to(DEV), nhwc(g1).to(DEV), cs.to(DEV), nhwc(gp).to(DEV), pidx, mk, 0, None, p,
+    call("wsl_bn_bwd", yd, 0, ss, save, nhwc(g0).to(DEV), nhwc(g1).to(DEV), cs.to(DEV), nhwc(gp).to(DEV), pidx, mk, 0, None, p,
          0.01, N, H, W, C, dgam, dbet, coef, dy, workspace("bn"))
     torch.cuda.synchronize()
     assert rel_l2(dgam.cpu(), dgr.float()) < 1e-4
@@ -327,7 +327,7 @@ def test_upsample(shape):
     g = torch.Generator().manual_seed(4)
     t = bf16_round(torch.randn(N, C, h, w, generator=g))
     u = torch.zeros((N, 2 * h, 2 * w, C), device=DEV, dtype=BF)
-    call("wsl_upsample2x_fwd", nhwc(t).to(DEV), N, h, w, C, u)
+    call("wsl_upsample2x_fwd", nhwc(t).to(DEV), 0, N, h, w, C, u)
     tr = t.clone().requires_grad_(True)
     ref = F.interpolate(tr, scale_factor=2, mode="bilinear", align_corners=True)
     torch.cuda.synchronize()
@@ -335,7 +335,7 @@ def test_upsample(shape):
     du = bf16_round(torch.randn(N, C, 2 * h, 2 * w, generator=g))
     (gt,) = torch.autograd.grad(ref, tr, du)
     dt = torch.zeros((N, h, w, C), device=DEV, dtype=BF)
-    call("wsl_upsample2x_bwd", nhwc(du).to(DEV), N, h, w, C, dt)
+    call("wsl_upsample2x_bwd", nhwc(du).to(DEV), 0, N, h, w, C, dt)
     torch.cuda.synchronize()
     assert rel_l2(nchw(dt.cpu()), gt) < 2 ** -8
 
@@ -365,6 +365,6 @@ def test_chan_dropout():
     assert vals <= {0.0, 2.0} and len(vals) == 2
     a = bf16_round(torch.randn(N, C, H, W))
     d = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
-    call("wsl_chan_scale", nhwc(a).to(DEV), cs, N, H, W, C, d)
+    call("wsl_chan_scale", nhwc(a).to(DEV), 0, cs, N, H, W, C, d)
     torch.cuda.synchronize()
     assert torch.equal(nchw(d.cpu()), a * cs.cpu().view(N, C, 1, 1))

@@ -161,6 +161,63 @@ def test_backward_matches_oracle_and_golden(golden_dir, cct):
         assert int(sd["encoder.in_conv.conv_conv.1.num_batches_tracked"]) == 1
 
 
+@pytest.mark.parametrize("cct", [False, True])
+def test_fp32_parity_mode_meets_the_north_star_tolerance(golden_dir, cct):
+    """precision='fp32' (activations and gradients stored in fp32, CUDA-core convolutions): logits within 1e-3 of the
+    reference (north_star's bar; measured ~1e-6), label maps bit-exact, every gradient within 1e-3 relative L2."""
+    g = np.load(os.path.join(golden_dir, "unet_cct_dmpls.npz" if cct else "unet_pce_gatedcrf.npz"))
+    decs = ("main_decoder", "aux_decoder1") if cct else ("decoder",)
+    p = O.synth_params(1, 4, decs, int(g["pseed"]))
+    m = (UNet_CCT if cct else UNet)(1, 4)
+    m.load_state_dict(p)
+    m = m.to(DEV).set_precision("fp32")
+    om, ock = _set_masks(m, g, cct)
+    x = torch.from_numpy(g["image"]).to(DEV)
+    lab = torch.from_numpy(g["label"]).to(DEV)
+    m.eval()
+    with torch.no_grad():
+        o = m(x)
+    for mine, key in ((o[0] if cct else o, "eval_main"),) + (((o[1], "eval_aux"),) if cct else ()):
+        ref = torch.from_numpy(g[key])
+        assert (mine.cpu() - ref).abs().max().item() / ref.abs().max().item() < 1e-3, key
+    m.train()
+    if cct:
+        beta = float(g["beta"])
+        o1, o2 = m(x)
+        ce1, s1 = Fn.softmax_pce(o1, lab)
+        ce2, s2 = Fn.softmax_pce(o2, lab)
+        pseudo = Fn.mix_argmax(s1, s2, beta)
+        assert np.array_equal(pseudo.cpu().numpy(), g["pseudo"])          # bit-exact dynamically mixed pseudo labels
+        pdl = L.pDLoss(4, 4)
+        loss = 0.5 * (ce1 + ce2) + 0.5 * 0.5 * (pdl(s1, pseudo.unsqueeze(1)) + pdl(s2, pseudo.unsqueeze(1)))
+        main = o1
+    else:
+        main = m(x)
+        ce, s = Fn.softmax_pce(main, lab)
+        loss = ce + 0.1 * ModelLossSemsegGatedCRF()(s, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, x, 32, 32)["loss"]
+    ref = torch.from_numpy(g["train_main"])
+    err = (main.detach().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-3, err
+    assert torch.equal(main.detach().cpu().argmax(1), ref.argmax(1))      # bit-exact label maps
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    _, grads, _ = O.full_step(p, torch.from_numpy(g["image"]), torch.from_numpy(g["label"]), "dmpls" if cct else "pce_gatedcrf",
+                              cct, om, ock, float(g["beta"]) if cct else 0.5)
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, (_, _, l2) in zip([str(k) for k in g["grad_keys"]], g["grad_stats"]):
+        mine = named[k].grad.detach().cpu()
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            assert mine.abs().max().item() < 1e-4          # true gradient is zero (conv bias in front of BatchNorm)
+            continue
+        e = rel_l2(mine, grads[k])
+        worst = max(worst, e)
+        assert e < 1e-3, (k, e)
+        assert abs(mine.double().norm().item() - l2) < 2e-3 * l2 + 1e-7, k
+    print(f"[fp32 cct={cct}] logits err {err:.2e} of scale, worst gradient rel-L2 {worst:.2e}")
+
+
 def test_script_style_step_with_torch_optimizer():
     """The per-step body of train_weakly_supervised_pCE_GatedCRFLoss_2D.py:111-126 written exactly as the
     script does (torch CrossEntropyLoss, torch.softmax, optim.SGD) on net_factory's model: loss decreases."""

@@ -1137,7 +1137,8 @@ int wgrad_dispatch_b(int cwb, const CUtensorMap& a, const CUtensorMap& b0, const
 }
 
 // per-channel sum of a channels-last bf16 tensor, added into out[C] (bias gradients of conv1x1 / out_conv)
-__global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int Creal,
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ x, long long P, int C, int Creal,
                                                           float* __restrict__ out) {
   extern __shared__ float s_red[];
   const int cg = C >> 3, rows = 256 / cg;
@@ -1147,7 +1148,12 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* _
   for (int j = 0; j < 8; ++j) sum[j] = 0.f;
   for (long long q = (long long)blockIdx.x * rows + r; q < P; q += (long long)gridDim.x * rows) {
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + q * C + g * 8), v);
+    if constexpr (sizeof(T) == 2) {
+      unpack8(*reinterpret_cast<const uint4*>(x + q * C + g * 8), v);
+    } else {
+      const float4 a = reinterpret_cast<const float4*>(x + q * C + g * 8)[0], b = reinterpret_cast<const float4*>(x + q * C + g * 8)[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] += v[j];
   }
@@ -1297,13 +1303,14 @@ WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, con
   return wgrad_dispatch_b<16, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
 }
 
-WSL_API int wsl_channel_sum(const void* x, long long P, int C, int Creal, float* out, cudaStream_t stream) {
+WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && Creal <= C, "wsl_channel_sum: unsupported channel count %d", C);
   const int rows = 256 / (C / 8);
   long long b = (P + rows * 16 - 1) / (rows * 16);
   if (b > 148 * 2) b = 148 * 2;
   if (b < 1) b = 1;
-  channel_sum_kernel<<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
+  if (dtype == 1) channel_sum_kernel<float><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const float*)x, P, C, Creal, out);
+  else channel_sum_kernel<__nv_bfloat16><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
   return wsl_check_launch("channel_sum");
 }
 

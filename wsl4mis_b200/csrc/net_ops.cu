@@ -11,6 +11,31 @@
 namespace {
 
 constexpr int TPB = 256;
+
+// Storage type of activations / activation gradients: bf16 (fast path, tensor cores) or fp32 (the reference-accurate
+// "parity" mode that runs the CUDA-core direct convolutions).  dtype codes in the C ABI: 0 = bf16, 1 = fp32.
+using bf16 = __nv_bfloat16;
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void ld8<bf16>(const bf16* p, float (&v)[8]) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void st8<bf16>(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+// value as it will be read back from storage
+template <typename T> __device__ __forceinline__ void round8(float (&v)[8]);
+template <> __device__ __forceinline__ void round8<bf16>(float (&v)[8]) { const uint4 u = pack8(v); unpack8(u, v); }
+template <> __device__ __forceinline__ void round8<float>(float (&v)[8]) {}
+// generic source element loader for the direct convolutions (dtype code at run time)
+__device__ __forceinline__ void ld8_dyn(const void* base, long long elem_off, int f32, float (&v)[8]) {
+  if (f32) ld8(reinterpret_cast<const float*>(base) + elem_off, v);
+  else ld8(reinterpret_cast<const bf16*>(base) + elem_off, v);
+}
 constexpr float BN_EPS_DEFAULT = 1e-5f;
 
 // ================================================================================================
@@ -52,15 +77,15 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
       if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
         const long long pix = ((long long)n * H + gy) * W + gx;
         const int c = c0 + half * 8;
-        if (src_f32) {
+        if (src_f32 && (C0 % 8) != 0) {          // single-channel image
           if (c < Cin) {
             const float* s = reinterpret_cast<const float*>(src0) + pix * C0 + c;
             for (int j = 0; j < 8 && c + j < Cin; ++j) v[j] = s[j];
           }
         } else if (c < C0) {
-          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src0) + pix * C0 + c), v);
+          ld8_dyn(src0, pix * C0 + c, src_f32, v);
         } else if (c < Cin) {
-          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src1) + pix * C1 + (c - C0)), v);
+          ld8_dyn(src1, pix * C1 + (c - C0), src_f32, v);
         }
       }
 #pragma unroll
@@ -105,6 +130,11 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
       for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi[c] = v[8 + c]; }
       if (cob + 8 <= CoutStore) reinterpret_cast<uint4*>(o)[0] = pack8(lo);
       if (cob + 16 <= CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+    } else if (out_mode == 2) {  // fp32 NHWC with CoutStore channels (parity mode activations)
+      float* o = reinterpret_cast<float*>(out) + (((long long)n * H + gy) * W + gx) * CoutStore + cob;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (cob + c < CoutStore) o[c] = v[c];
     } else {  // fp32 NCHW with CoutStore real channels
       float* o = reinterpret_cast<float*>(out);
 #pragma unroll
@@ -118,8 +148,9 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
 // ================================================================================================
 // first layer (Cin = 1, unet.py:81 in_conv): x fp32 [N,H,W] -> y bf16 [N,H,W,16]; HBM-bound (36 B/pixel)
 // ================================================================================================
+template <typename T>
 __global__ void __launch_bounds__(TPB, 4) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][9]*/,
-                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                         const float* __restrict__ bias, T* __restrict__ y,
                                                          int N, int H, int W) {
   __shared__ float s_w[9][16];
   __shared__ float s_b[16];
@@ -146,15 +177,15 @@ __global__ void __launch_bounds__(TPB, 4) conv_first_kernel(const float* __restr
     float lo[8], hi[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { lo[c] = o[c]; hi[c] = o[8 + c]; }
-    uint4* dst = reinterpret_cast<uint4*>(y + i * 16);
-    dst[0] = pack8(lo);
-    dst[1] = pack8(hi);
+    st8(y + i * 16, lo);
+    st8(y + i * 16 + 8, hi);
   }
 }
 
 // dW[co][t] += sum_p dY[p][co] * x[p + tap_t]: every thread walks pixels with an 8x9 register tile (blockIdx.y picks
 // the channel half; 72 FMAs per 10 loads), then warp-shuffle + one atomicAdd per warp and entry.
-__global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+template <typename T>
+__global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                              float* __restrict__ dw /*[16][9]*/, int N, int H, int W) {
   float acc[8][9];
 #pragma unroll
@@ -172,7 +203,7 @@ __global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __rest
       const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
       v[t] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
     }
-    unpack8(reinterpret_cast<const uint4*>(dy + i * 16)[half], g);
+    ld8(dy + i * 16 + half * 8, g);
 #pragma unroll
     for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -195,7 +226,7 @@ __global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __rest
 template <int KS>
 __global__ void __launch_bounds__(256) wgrad_direct_kernel(
     const void* __restrict__ src0, int C0, const void* __restrict__ src1, int C1, int src_f32,
-    const __nv_bfloat16* __restrict__ dy, int CoutP, float* __restrict__ dw, float* __restrict__ dbias,
+    const void* __restrict__ dy, int dy_f32, int CoutP, float* __restrict__ dw, float* __restrict__ dbias,
     int N, int H, int W, int CoutReal, int tiles_x, int tiles_y) {
   constexpr int PAD = KS / 2, TH = 8, TW = 16, HH = TH + 2 * PAD, HWD = TW + 2 * PAD, TAPS = KS * KS;
   __shared__ float s_g[TH * TW][16];
@@ -220,8 +251,7 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      if (gy < H && gx < W)
-        unpack8(*reinterpret_cast<const uint4*>(dy + (((long long)n * H + gy) * W + gx) * CoutP + cob + half * 8), v);
+      if (gy < H && gx < W) ld8_dyn(dy, (((long long)n * H + gy) * W + gx) * CoutP + cob + half * 8, dy_f32, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s_g[p][half * 8 + j] = v[j];
     }
@@ -235,15 +265,15 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(
       if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
         const long long pix = ((long long)n * H + gy) * W + gx;
         const int c = cib + half * 8;
-        if (src_f32) {
+        if (src_f32 && (C0 % 8) != 0) {          // single-channel image
           if (c < Cin) {
             const float* s = reinterpret_cast<const float*>(src0) + pix * C0 + c;
             for (int j = 0; j < 8 && c + j < Cin; ++j) v[j] = s[j];
           }
         } else if (c < C0) {
-          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src0) + pix * C0 + c), v);
+          ld8_dyn(src0, pix * C0 + c, src_f32, v);
         } else if (c < Cin) {
-          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src1) + pix * C1 + (c - C0)), v);
+          ld8_dyn(src1, pix * C1 + (c - C0), src_f32, v);
         }
       }
 #pragma unroll
@@ -315,8 +345,9 @@ __device__ __forceinline__ void bn_finalize_partials(const float* partials, int 
 // Partials [block][2][C]; the last block finalises in fixed order (deterministic):
 //   save[0:C] = mean, save[C:2C] = invstd; ss[0:C] = gamma*invstd, ss[C:2C] = beta - mean*scale;
 //   running_mean/var updated with momentum (unbiased variance), num_batches_tracked += 1.
+template <typename T>
 __global__ void __launch_bounds__(TPB) bn_stats_kernel(
-    const __nv_bfloat16* __restrict__ y, long long P, int C, const float* __restrict__ gamma,
+    const T* __restrict__ y, long long P, int C, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt, float momentum,
     float eps, float* __restrict__ save, float* __restrict__ ss, float* partials, unsigned* ticket) {
   extern __shared__ float s_red[];  // [TPB][16]
@@ -328,7 +359,7 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(
   if (r < rows) {
     for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + p * C + g * 8), v);
+      ld8(y + p * C + g * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
     }
@@ -453,10 +484,11 @@ __device__ __forceinline__ DropCtx make_drop(float p, const uint8_t* mask, unsig
 }
 
 // A = dropout(leaky_relu(y*scale + shift)); optional fused 2x2 max-pool of A (DownBlock, unet.py:38).
+template <typename T>
 __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
-    const __nv_bfloat16* __restrict__ y, const float* __restrict__ ss, int N, int H, int W, int C, float slope,
+    const T* __restrict__ y, const float* __restrict__ ss, int N, int H, int W, int C, float slope,
     float drop_p, const uint8_t* __restrict__ mask, unsigned long long seed, const unsigned long long* seed_ptr,
-    __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ pooled, uint8_t* __restrict__ pool_idx) {
+    T* __restrict__ act, T* __restrict__ pooled, uint8_t* __restrict__ pool_idx) {
   const int cg = C >> 3, rows = TPB / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg, c0 = g * 8;
   const DropCtx dc = make_drop(drop_p, mask, seed, seed_ptr);
@@ -465,7 +497,7 @@ __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
   for (int j = 0; j < 8; ++j) { sc[j] = ss[c0 + j]; sh[j] = ss[C + c0 + j]; }
   auto act8 = [&](int p, float (&o)[8]) {
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + (long long)p * C + c0), v);
+    ld8(y + (long long)p * C + c0, v);
     const uint32_t kb = keep_bits8(dc, (long long)p * C + c0, (uint32_t)p * cg + g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -479,7 +511,7 @@ __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
     for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
       float o[8];
       act8(p, o);
-      *reinterpret_cast<uint4*>(act + (long long)p * C + c0) = pack8(o);
+      st8(act + (long long)p * C + c0, o);
     }
   } else {
     const int Hp = H >> 1, Wp = W >> 1, Q = N * Hp * Wp;
@@ -490,16 +522,15 @@ __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int p = (n * H + yp * 2 + (k >> 1)) * W + xp * 2 + (k & 1);
-        float o[8], ob[8];
+        float o[8];
         act8(p, o);
-        const uint4 pk = pack8(o);
-        *reinterpret_cast<uint4*>(act + (long long)p * C + c0) = pk;
-        unpack8(pk, ob);  // pool over the stored (bf16-rounded) activations
+        st8(act + (long long)p * C + c0, o);
+        round8<T>(o);     // pool over the activations exactly as stored
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (k == 0 || ob[j] > best[j]) { best[j] = ob[j]; arg[j] = k; }  // first maximum wins (torch)
+          if (k == 0 || o[j] > best[j]) { best[j] = o[j]; arg[j] = k; }  // first maximum wins (torch)
       }
-      *reinterpret_cast<uint4*>(pooled + (long long)q * C + c0) = pack8(best);
+      st8(pooled + (long long)q * C + c0, best);
       uint2 ai;
       ai.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
       ai.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
@@ -513,14 +544,15 @@ __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
 // dz      = dA * dropout_factor * leaky'(z),   z = y*scale+shift,  xhat = (y-mean)*invstd
 // reduce : sum dz, sum dz*xhat  -> dbeta, dgamma, c1 = sum dz / P, c2 = sum dz*xhat / P
 // apply  : dY = scale * (dz - c1 - xhat*c2)
+template <typename T>
 struct BnBwdArgs {
-  const __nv_bfloat16* y;
+  const T* y;
   const float* ss;     // scale, shift
   const float* save;   // mean, invstd
-  const __nv_bfloat16* g0;
-  const __nv_bfloat16* g1;
+  const T* g0;
+  const T* g1;
   const float* cs1;    // [N][C] channel scale for g1 (nullable -> 1)
-  const __nv_bfloat16* gp;
+  const T* gp;
   const uint8_t* pool_idx;
   const uint8_t* mask;
   unsigned long long seed;
@@ -535,7 +567,8 @@ struct BnBwdThread {
   DropCtx dc;
 };
 
-__device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs& a) {
+template <typename T>
+__device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs<T>& a) {
   BnBwdThread t;
   t.cg = a.C >> 3;
   t.g = threadIdx.x % t.cg;
@@ -547,15 +580,16 @@ __device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs& a) {
 }
 
 // dz (gradient w.r.t. the BN output z) and the raw conv output y of 8 channels of pixel p
-__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread& t, int p, float (&dz)[8], float (&yv)[8]) {
+template <typename T>
+__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&dz)[8], float (&yv)[8]) {
   float g[8];
   const long long off = (long long)p * a.C + t.c0;
-  unpack8(*reinterpret_cast<const uint4*>(a.y + off), yv);
+  ld8(a.y + off, yv);
 #pragma unroll
   for (int j = 0; j < 8; ++j) g[j] = 0.f;
   if (a.g0) {
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(a.g0 + off), v);
+    ld8(a.g0 + off, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] += v[j];
   }
@@ -563,7 +597,7 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread
     const int x = p % a.W, r = p / a.W, yy = r % a.H, n = r / a.H;
     if (a.g1) {
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(a.g1 + off), v);
+      ld8(a.g1 + off, v);
       if (a.cs1) {
         const float4 s0 = *reinterpret_cast<const float4*>(a.cs1 + (long long)n * a.C + t.c0);
         const float4 s1 = *reinterpret_cast<const float4*>(a.cs1 + (long long)n * a.C + t.c0 + 4);
@@ -579,7 +613,7 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread
       const int k = ((yy & 1) << 1) | (x & 1);
       const uint2 ai = *reinterpret_cast<const uint2*>(a.pool_idx + q);
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(a.gp + q), v);
+      ld8(a.gp + q, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int aj = (j < 4 ? (ai.x >> (8 * j)) : (ai.y >> (8 * (j - 4)))) & 0xff;
@@ -596,7 +630,8 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs& a, const BnBwdThread
   }
 }
 
-__global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ dgamma,
+template <typename T>
+__global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
                                                                float* partials, unsigned* ticket) {
   extern __shared__ float s_red[];
@@ -649,8 +684,9 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs a, floa
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-__global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
-                                                              __nv_bfloat16* __restrict__ dy) {
+template <typename T>
+__global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs<T> a, const float* __restrict__ coef,
+                                                              T* __restrict__ dy) {
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, rows = TPB / t.cg;
   const int P = a.N * a.H * a.W;
@@ -663,7 +699,7 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs a, const
     bn_bwd_dz8(a, t, p, dz, yv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(dz[j], t.sc[j], fmaf(yv[j], kb_[j], kd_[j]));
-    *reinterpret_cast<uint4*>(dy + (long long)p * C + t.c0) = pack8(o);
+    st8(dy + (long long)p * C + t.c0, o);
   }
 }
 
@@ -679,8 +715,9 @@ __device__ __forceinline__ void up_src(int d, int in, int out, int& i0, int& i1,
   lam = s - (float)i0;
 }
 
-__global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ t, int N, int h, int w, int C,
-                                                             __nv_bfloat16* __restrict__ u) {
+template <typename T>
+__global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const T* __restrict__ t, int N, int h, int w, int C,
+                                                             T* __restrict__ u) {
   // thread t owns channel group g = t % (C/8); rows of the block walk output pixels (32-bit indexing)
   const int cg = C >> 3, rows = TPB / cg, H = 2 * h, W = 2 * w;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg, c0 = g * 8;
@@ -693,21 +730,22 @@ __global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const __nv_bfloat16
     const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
     const float ly = sy - (float)y0, lx = sx - (float)x0;
     float a[8], b[8], c[8], d[8], o[8];
-    const __nv_bfloat16* base = t + (long long)n * h * w * C + c0;
-    unpack8(*reinterpret_cast<const uint4*>(base + (y0 * w + x0) * C), a);
-    unpack8(*reinterpret_cast<const uint4*>(base + (y0 * w + x1) * C), b);
-    unpack8(*reinterpret_cast<const uint4*>(base + (y1 * w + x0) * C), c);
-    unpack8(*reinterpret_cast<const uint4*>(base + (y1 * w + x1) * C), d);
+    const T* base = t + (long long)n * h * w * C + c0;
+    ld8(base + (y0 * w + x0) * C, a);
+    ld8(base + (y0 * w + x1) * C, b);
+    ld8(base + (y1 * w + x0) * C, c);
+    ld8(base + (y1 * w + x1) * C, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
-    *reinterpret_cast<uint4*>(u + (long long)p * C + c0) = pack8(o);
+    st8(u + (long long)p * C + c0, o);
   }
 }
 
 // gather form of the transpose: each low-res pixel collects from the <=7x7 high-res pixels that can touch it
-__global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ du, int N, int h, int w, int C,
-                                                             __nv_bfloat16* __restrict__ dt) {
+template <typename T>
+__global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const T* __restrict__ du, int N, int h, int w, int C,
+                                                             T* __restrict__ dt) {
   const int cg = C >> 3, H = 2 * h, W = 2 * w;
   const long long total = (long long)N * h * w * cg;
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
@@ -735,13 +773,13 @@ __global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const __nv_bfloat16
         if (x1 == xi) wx += lx;
         if (wx == 0.f) continue;
         float g[8];
-        unpack8(*reinterpret_cast<const uint4*>(du + ((n * H + Y) * (long long)W + X) * C + c0), g);
+        ld8(du + ((n * H + Y) * (long long)W + X) * C + c0, g);
         const float ww = wy * wx;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, g[j], acc[j]);
       }
     }
-    *reinterpret_cast<uint4*>(dt + p * C + c0) = pack8(acc);
+    st8(dt + p * C + c0, acc);
   }
 }
 
@@ -754,43 +792,46 @@ __global__ void chan_mask_gen_kernel(unsigned long long seed, const unsigned lon
   if (i < n) cs[i] = (wsl_uniform(seed, (unsigned long long)i) >= p) ? 1.f / (1.f - p) : 0.f;
 }
 
-__global__ void __launch_bounds__(TPB) chan_scale_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ cs,
-                                                         long long HW, int C, long long total_vec, __nv_bfloat16* __restrict__ d) {
+template <typename T>
+__global__ void __launch_bounds__(TPB) chan_scale_kernel(const T* __restrict__ a, const float* __restrict__ cs,
+                                                         long long HW, int C, long long total_vec, T* __restrict__ d) {
   const int cg = C >> 3;
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total_vec; i += (long long)gridDim.x * TPB) {
     const long long p = i / cg;
     const int c0 = (int)(i - p * cg) * 8;
     const long long n = p / HW;
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(a + p * C + c0), v);
+    ld8(a + p * C + c0, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= cs[n * C + c0 + j];
-    *reinterpret_cast<uint4*>(d + p * C + c0) = pack8(v);
+    st8(d + p * C + c0, v);
   }
 }
 
 // fp32 NCHW [N,Creal,H,W] -> bf16 NHWC [N,H,W,CP] (zero padded channels); used for dlogits
+template <typename T>
 __global__ void __launch_bounds__(TPB) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int Creal, int CP, long long HW,
-                                                                    long long npix, __nv_bfloat16* __restrict__ dst) {
+                                                                    long long npix, T* __restrict__ dst) {
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
     const long long n = i / HW, o = i - n * HW;
     for (int c0 = 0; c0 < CP; c0 += 8) {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (c0 + j < Creal) ? src[(n * Creal + c0 + j) * HW + o] : 0.f;
-      *reinterpret_cast<uint4*>(dst + i * CP + c0) = pack8(v);
+      st8(dst + i * CP + c0, v);
     }
   }
 }
 
 // bf16 NHWC -> fp32 NCHW (feature export for tests / API)
-__global__ void __launch_bounds__(TPB) nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int C, long long HW,
+template <typename T>
+__global__ void __launch_bounds__(TPB) nhwc_bf16_to_nchw_f32_kernel(const T* __restrict__ src, int C, long long HW,
                                                                     long long total, float* __restrict__ dst) {
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
     const long long p = i / C;
     const int c = (int)(i - p * C);
     const long long n = p / HW, o = p - n * HW;
-    dst[(n * C + c) * HW + o] = __bfloat162float(src[i]);
+    dst[(n * C + c) * HW + o] = (float)src[i];
   }
 }
 
@@ -888,6 +929,13 @@ inline int bn_grid(long long P, int C) {
 
 }  // namespace
 
+// run `expr` with T = bf16 (dtype 0) or float (dtype 1)
+#define WSL_DISPATCH_T(dtype, ...)                      \
+  do {                                                  \
+    if ((dtype) == 1) { using T = float; __VA_ARGS__; } \
+    else { using T = bf16; __VA_ARGS__; }               \
+  } while (0)
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -896,7 +944,7 @@ WSL_API int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, 
                             int CoutStore, int ksize, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_direct: ksize must be 1 or 3");
   WSL_REQUIRE(CinP % 16 == 0 && CoutP % 16 == 0, "wsl_conv_direct: padded channel counts must be multiples of 16");
-  WSL_REQUIRE(src_f32 || (C0 % 8 == 0 && C1 % 8 == 0), "wsl_conv_direct: bf16 sources need C %% 8 == 0");
+  WSL_REQUIRE((src_f32 && C1 == 0) || (C0 % 8 == 0 && C1 % 8 == 0), "wsl_conv_direct: multi-channel sources need C %% 8 == 0");
   const int tx = (W + 15) / 16, ty = (H + 15) / 16;
   dim3 grid(N * tx * ty, CoutP / 16);
   if (ksize == 3)
@@ -906,8 +954,9 @@ WSL_API int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, 
   return wsl_check_launch("conv_direct");
 }
 
-WSL_API int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int CoutP,
-                             float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream) {
+WSL_API int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const void* dy, int dy_f32,
+                             int CoutP, float* dw, float* dbias, int N, int H, int W, int CoutReal, int ksize,
+                             cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_wgrad_direct: ksize must be 1 or 3");
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_wgrad_direct: CoutP must be a multiple of 16");
   const int Cin = C0 + C1;
@@ -919,21 +968,21 @@ WSL_API int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1,
   if (splits < 1) splits = 1;
   dim3 grid(ob, splits);
   if (ksize == 3)
-    wgrad_direct_kernel<3><<<grid, 256, 0, stream>>>(src0, C0, src1, C1, src_f32, (const __nv_bfloat16*)dy, CoutP, dw, dbias, N, H, W, CoutReal, tx, ty);
+    wgrad_direct_kernel<3><<<grid, 256, 0, stream>>>(src0, C0, src1, C1, src_f32, dy, dy_f32, CoutP, dw, dbias, N, H, W, CoutReal, tx, ty);
   else
-    wgrad_direct_kernel<1><<<grid, 256, 0, stream>>>(src0, C0, src1, C1, src_f32, (const __nv_bfloat16*)dy, CoutP, dw, dbias, N, H, W, CoutReal, tx, ty);
+    wgrad_direct_kernel<1><<<grid, 256, 0, stream>>>(src0, C0, src1, C1, src_f32, dy, dy_f32, CoutP, dw, dbias, N, H, W, CoutReal, tx, ty);
   return wsl_check_launch("wgrad_direct");
 }
 
-WSL_API int wsl_bn_stats(const void* y, long long P, int C, const float* gamma, const float* beta, float* running_mean,
+WSL_API int wsl_bn_stats(const void* y, int dtype, long long P, int C, const float* gamma, const float* beta, float* running_mean,
                          float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
                          float* ss, float* ws, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_stats: unsupported channel count %d", C);
   const int grid = bn_grid(P, C);
   WSL_REQUIRE((long long)grid * 2 * C + 64 <= WSL_WS_FLOATS, "wsl_bn_stats: workspace too small");
-  bn_stats_kernel<<<grid, TPB, TPB * 16 * sizeof(float), stream>>>((const __nv_bfloat16*)y, P, C, gamma, beta, running_mean,
-                                                                   running_var, num_batches_tracked, momentum, eps, save, ss,
-                                                                   ws + 64, reinterpret_cast<unsigned*>(ws));
+  WSL_DISPATCH_T(dtype, bn_stats_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(
+                            (const T*)y, P, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, save, ss,
+                            ws + 64, reinterpret_cast<unsigned*>(ws)));
   return wsl_check_launch("bn_stats");
 }
 
@@ -943,47 +992,58 @@ WSL_API int wsl_bn_eval_prepare(const float* gamma, const float* beta, const flo
   return wsl_check_launch("bn_eval_prepare");
 }
 
-WSL_API int wsl_bn_act_fwd(const void* y, const float* ss, int N, int H, int W, int C, float slope, float drop_p,
+WSL_API int wsl_bn_act_fwd(const void* y, int dtype, const float* ss, int N, int H, int W, int C, float slope, float drop_p,
                            const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr, void* act,
                            void* pooled, uint8_t* pool_idx, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_bn_act_fwd: C %% 8 != 0");
   WSL_REQUIRE(pooled == nullptr || (H % 2 == 0 && W % 2 == 0), "wsl_bn_act_fwd: pooling needs even H, W");
   WSL_REQUIRE(TPB % (C / 8) == 0 && (long long)N * H * W < (1LL << 31), "wsl_bn_act_fwd: unsupported C=%d or too many pixels", C);
   const long long items = (long long)N * H * W * (C / 8) / (pooled ? 4 : 1);
-  bn_act_fwd_kernel<<<grid_for((items + 1) / 2), TPB, 0, stream>>>((const __nv_bfloat16*)y, ss, N, H, W, C, slope, drop_p, mask, seed,
-                                                         seed_ptr, (__nv_bfloat16*)act, (__nv_bfloat16*)pooled, pool_idx);
+  WSL_DISPATCH_T(dtype, bn_act_fwd_kernel<T><<<grid_for((items + 1) / 2), TPB, 0, stream>>>(
+                            (const T*)y, ss, N, H, W, C, slope, drop_p, mask, seed, seed_ptr, (T*)act, (T*)pooled, pool_idx));
   return wsl_check_launch("bn_act_fwd");
 }
 
-WSL_API int wsl_bn_bwd(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+template <typename T>
+static int bn_bwd_launch(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+                         const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
+                         const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma,
+                         float* dbeta, float* coef, void* dy, float* ws, cudaStream_t stream) {
+  BnBwdArgs<T> a;
+  a.y = (const T*)y; a.ss = ss; a.save = save; a.g0 = (const T*)g0; a.g1 = (const T*)g1;
+  a.cs1 = cs1; a.gp = (const T*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
+  a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
+  const long long P = (long long)N * H * W;
+  const int grid = bn_grid(P, C);
+  bn_bwd_reduce_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws));
+  int rc = wsl_check_launch("bn_bwd_reduce");
+  if (rc) return rc;
+  bn_bwd_apply_kernel<T><<<grid_for(P * (C / 8) / 2), TPB, 0, stream>>>(a, coef, (T*)dy);
+  return wsl_check_launch("bn_bwd_apply");
+}
+
+WSL_API int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
                        const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                        const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
                        cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_bwd: unsupported channel count %d", C);
-  BnBwdArgs a;
-  a.y = (const __nv_bfloat16*)y; a.ss = ss; a.save = save; a.g0 = (const __nv_bfloat16*)g0; a.g1 = (const __nv_bfloat16*)g1;
-  a.cs1 = cs1; a.gp = (const __nv_bfloat16*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
-  a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
   const long long P = (long long)N * H * W;
-  const int grid = bn_grid(P, C);
-  WSL_REQUIRE((long long)grid * 2 * C + 64 <= WSL_WS_FLOATS, "wsl_bn_bwd: workspace too small");
-  bn_bwd_reduce_kernel<<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws));
-  int rc = wsl_check_launch("bn_bwd_reduce");
-  if (rc) return rc;
-  bn_bwd_apply_kernel<<<grid_for(P * (C / 8) / 2), TPB, 0, stream>>>(a, coef, (__nv_bfloat16*)dy);
-  return wsl_check_launch("bn_bwd_apply");
+  WSL_REQUIRE((long long)bn_grid(P, C) * 2 * C + 64 <= WSL_WS_FLOATS && P < (1LL << 31), "wsl_bn_bwd: workspace too small / too many pixels");
+  if (dtype == 1)
+    return bn_bwd_launch<float>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, stream);
+  return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, stream);
 }
 
-WSL_API int wsl_upsample2x_fwd(const void* t, int N, int h, int w, int C, void* u, cudaStream_t stream) {
+WSL_API int wsl_upsample2x_fwd(const void* t, int dtype, int N, int h, int w, int C, void* u, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_fwd: C %% 8 != 0");
   WSL_REQUIRE(TPB % (C / 8) == 0, "wsl_upsample2x_fwd: unsupported C=%d", C);
-  upsample2x_fwd_kernel<<<grid_for((long long)N * 4 * h * w * (C / 8) / 2), TPB, 0, stream>>>((const __nv_bfloat16*)t, N, h, w, C, (__nv_bfloat16*)u);
+  WSL_DISPATCH_T(dtype, upsample2x_fwd_kernel<T><<<grid_for((long long)N * 4 * h * w * (C / 8) / 2), TPB, 0, stream>>>((const T*)t, N, h, w, C, (T*)u));
   return wsl_check_launch("upsample2x_fwd");
 }
 
-WSL_API int wsl_upsample2x_bwd(const void* du, int N, int h, int w, int C, void* dt, cudaStream_t stream) {
+WSL_API int wsl_upsample2x_bwd(const void* du, int dtype, int N, int h, int w, int C, void* dt, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_bwd: C %% 8 != 0");
-  upsample2x_bwd_kernel<<<grid_for((long long)N * h * w * (C / 8)), TPB, 0, stream>>>((const __nv_bfloat16*)du, N, h, w, C, (__nv_bfloat16*)dt);
+  WSL_DISPATCH_T(dtype, upsample2x_bwd_kernel<T><<<grid_for((long long)N * h * w * (C / 8)), TPB, 0, stream>>>((const T*)du, N, h, w, C, (T*)dt));
   return wsl_check_launch("upsample2x_bwd");
 }
 
@@ -993,24 +1053,24 @@ WSL_API int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long*
   return wsl_check_launch("chan_mask_gen");
 }
 
-WSL_API int wsl_chan_scale(const void* a, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream) {
+WSL_API int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_chan_scale: C %% 8 != 0");
   const long long tv = (long long)N * H * W * (C / 8);
-  chan_scale_kernel<<<grid_for(tv), TPB, 0, stream>>>((const __nv_bfloat16*)a, cs, (long long)H * W, C, tv, (__nv_bfloat16*)d);
+  WSL_DISPATCH_T(dtype, chan_scale_kernel<T><<<grid_for(tv), TPB, 0, stream>>>((const T*)a, cs, (long long)H * W, C, tv, (T*)d));
   return wsl_check_launch("chan_scale");
 }
 
-WSL_API int wsl_nchw_f32_to_nhwc_bf16(const float* src, int N, int Creal, int H, int W, int CP, void* dst, cudaStream_t stream) {
-  WSL_REQUIRE(CP % 8 == 0 && CP >= Creal, "wsl_nchw_f32_to_nhwc_bf16: bad padded channel count");
+WSL_API int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, cudaStream_t stream) {
+  WSL_REQUIRE(CP % 8 == 0 && CP >= Creal, "wsl_nchw_f32_to_nhwc: bad padded channel count");
   const long long npix = (long long)N * H * W;
-  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(npix), TPB, 0, stream>>>(src, Creal, CP, (long long)H * W, npix, (__nv_bfloat16*)dst);
-  return wsl_check_launch("nchw_f32_to_nhwc_bf16");
+  WSL_DISPATCH_T(dtype, nchw_f32_to_nhwc_bf16_kernel<T><<<grid_for(npix), TPB, 0, stream>>>(src, Creal, CP, (long long)H * W, npix, (T*)dst));
+  return wsl_check_launch("nchw_f32_to_nhwc");
 }
 
-WSL_API int wsl_nhwc_bf16_to_nchw_f32(const void* src, int N, int C, int H, int W, float* dst, cudaStream_t stream) {
+WSL_API int wsl_nhwc_to_nchw_f32(const void* src, int dtype, int N, int C, int H, int W, float* dst, cudaStream_t stream) {
   const long long total = (long long)N * H * W * C;
-  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total), TPB, 0, stream>>>((const __nv_bfloat16*)src, C, (long long)H * W, total, dst);
-  return wsl_check_launch("nhwc_bf16_to_nchw_f32");
+  WSL_DISPATCH_T(dtype, nhwc_bf16_to_nchw_f32_kernel<T><<<grid_for(total), TPB, 0, stream>>>((const T*)src, C, (long long)H * W, total, dst));
+  return wsl_check_launch("nhwc_to_nchw_f32");
 }
 
 WSL_API int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,
@@ -1029,19 +1089,19 @@ WSL_API int wsl_sgd_step(float* param, const float* grad, float* mom, long long 
   return wsl_check_launch("sgd_step");
 }
 
-WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout,
                            cudaStream_t stream) {
   WSL_REQUIRE(Cout == 16, "wsl_conv_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
-  conv_first_kernel<<<grid_for((long long)N * H * W), TPB, 0, stream>>>(x, w, bias, (__nv_bfloat16*)y, N, H, W);
+  WSL_DISPATCH_T(dtype, conv_first_kernel<T><<<grid_for((long long)N * H * W), TPB, 0, stream>>>(x, w, bias, (T*)y, N, H, W));
   return wsl_check_launch("conv_first");
 }
 
-WSL_API int wsl_wgrad_first(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, cudaStream_t stream) {
+WSL_API int wsl_wgrad_first(const float* x, const void* dy, int dtype, float* dw, int N, int H, int W, int Cout, cudaStream_t stream) {
   WSL_REQUIRE(Cout == 16, "wsl_wgrad_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
   long long b = ((long long)N * H * W + 128 * 16 - 1) / (128 * 16);
   if (b > 148 * 4) b = 148 * 4;
   if (b < 1) b = 1;
-  wgrad_first_kernel<<<dim3((int)b, 2), 128, 0, stream>>>(x, (const __nv_bfloat16*)dy, dw, N, H, W);
+  WSL_DISPATCH_T(dtype, wgrad_first_kernel<T><<<dim3((int)b, 2), 128, 0, stream>>>(x, (const T*)dy, dw, N, H, W));
   return wsl_check_launch("wgrad_first");
 }
 

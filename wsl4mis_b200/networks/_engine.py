@@ -86,8 +86,15 @@ class UNetExecutor:
 
     MAX_SLOTS = 4
 
-    def __init__(self, model: nn.Module, encoder: nn.Module, decoders: List[nn.Module], aux_dropout: Sequence[bool]):
+    def __init__(self, model: nn.Module, encoder: nn.Module, decoders: List[nn.Module], aux_dropout: Sequence[bool],
+                 precision: str = "bf16"):
+        assert precision in ("bf16", "fp32")
         self.model = model
+        # storage precision of activations / activation gradients: "bf16" = tensor-core fast path; "fp32" = parity mode
+        # (CUDA-core direct convolutions, everything in fp32: matches the fp32 reference to ~1e-5)
+        self.precision = precision
+        self.act_dtype = BF16 if precision == "bf16" else torch.float32
+        self.dt = 0 if precision == "bf16" else 1
         self.aux = list(aux_dropout)
         self.layers: List[ConvLayer] = []
         ft = encoder.ft_chns
@@ -137,7 +144,8 @@ class UNetExecutor:
         self.stats = {"launches": 0}
 
     # ---------------------------------------------------------------- buffers
-    def buf(self, slot, name, shape, dtype=BF16):
+    def buf(self, slot, name, shape, dtype=None):
+        dtype = self.act_dtype if dtype is None else dtype
         key = (slot, name, tuple(shape), dtype)
         t = self._bufs.get(key)
         if t is None:
@@ -220,10 +228,10 @@ class UNetExecutor:
 
     def _tc2_ok(self, layer_cin_list, H, W):
         """persistent / resident-weight / halo-view kernels: 8 x 16 pixel tiles"""
-        return (self.use_tc and self.use_tc2 and all(c % 16 == 0 for c in layer_cin_list) and W % 8 == 0 and H % 16 == 0)
+        return (self.dt == 0 and self.use_tc and self.use_tc2 and all(c % 16 == 0 for c in layer_cin_list) and W % 8 == 0 and H % 16 == 0)
 
     def _tc_ok(self, layer_cin_list, H, W):
-        return (self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
+        return (self.dt == 0 and self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
 
     def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, want_stats=False):
         """Returns the number of BatchNorm partial-statistics rows the conv epilogue produced (0 = none)."""
@@ -234,8 +242,11 @@ class UNetExecutor:
         c0 = L.srcC[0]
         c1 = L.srcC[1] if len(L.srcC) > 1 else 0
         self._tag("fwd", L, N, H, W, L.Cin, L.Cout)
-        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode == 0:
-            call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, N, H, W, L.Cout)
+        f32 = 1 if (src_f32 or self.dt == 1) else 0
+        if out_mode == 0 and self.dt == 1:
+            out_mode = 2                                   # fp32 NHWC activations
+        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2):
+            call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout)
         elif not src_f32 and self._tc2_ok(L.srcC, H, W):
             if want_stats and self.fuse_bn_stats:
                 sb = self._stat_scratch()
@@ -247,7 +258,7 @@ class UNetExecutor:
         elif not src_f32 and self._tc_ok(L.srcC, H, W):
             call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         else:
-            call("wsl_conv_direct", s0, c0, s1, c1, 1 if src_f32 else 0, pk["wf"], pk["bias"], out, out_mode, N, H, W,
+            call("wsl_conv_direct", s0, c0, s1, c1, f32, pk["wf"], pk["bias"], out, out_mode, N, H, W,
                  L.CinP, L.CoutP, cout_store, L.ks)
         self._untag()
         return rows
@@ -262,7 +273,7 @@ class UNetExecutor:
         elif self._tc_ok([L.CoutP], H, W):
             call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
         else:
-            call("wsl_conv_direct", dy, L.CoutP, None, 0, 0, pk["wd"][i], None, out, 0, N, H, W, L.CoutP, sp, ci, L.ks)
+            call("wsl_conv_direct", dy, L.CoutP, None, 0, self.dt, pk["wd"][i], None, out, 2 if self.dt else 0, N, H, W, L.CoutP, sp, ci, L.ks)
         self._untag()
 
     def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False):
@@ -274,7 +285,7 @@ class UNetExecutor:
         tc = (not src_f32 and self.use_tc_wgrad and self._tc_ok(L.srcC, H, W)
               and (L.CoutP < 128 or L.CoutP % 128 == 0))
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and L.bn is not None:
-            call("wsl_wgrad_first", s0, dy, self.gview(L.conv.weight), N, H, W, L.Cout)
+            call("wsl_wgrad_first", s0, dy, self.dt, self.gview(L.conv.weight), N, H, W, L.Cout)
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W) and self.wgrad_version == 3 and (L.CoutP <= 64 or L.CoutP % 128 == 0):
             call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W):
@@ -282,13 +293,13 @@ class UNetExecutor:
         elif tc:
             call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
         else:
-            call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if src_f32 else 0, dy, L.CoutP, self.gview(L.conv.weight),
-                 self.gview(L.conv.bias) if L.bn is None else None, N, H, W, L.Cout, L.ks)
+            call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if (src_f32 or self.dt) else 0, dy, self.dt, L.CoutP,
+                 self.gview(L.conv.weight), self.gview(L.conv.bias) if L.bn is None else None, N, H, W, L.Cout, L.ks)
         self._untag()
         # Bias gradient.  A conv bias that feeds training-mode BatchNorm has an exactly-zero gradient (BN removes the
         # per-channel mean); the reference holds ~1e-8 rounding noise there.  We leave the zero-filled bucket as is.
         if tc and L.bn is None:
-            call("wsl_channel_sum", dy, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias))
+            call("wsl_channel_sum", dy, self.dt, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias))
 
     def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None, stat_rows=0):
         bn = L.bn
@@ -300,13 +311,13 @@ class UNetExecutor:
             call("wsl_bn_finalize", self._stat_scratch(), stat_rows, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                  bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss)
         elif training:
-            call("wsl_bn_stats", y, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+            call("wsl_bn_stats", y, self.dt, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                  bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"))
         else:
             call("wsl_bn_eval_prepare", bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), C, ss)
         p = L.drop_p if training else 0.0
         seed = self._layer_seed(L)
-        call("wsl_bn_act_fwd", y, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
+        call("wsl_bn_act_fwd", y, self.dt, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
              act, pooled, pool_idx)
         return save, ss
 
@@ -315,7 +326,7 @@ class UNetExecutor:
         C = L.Cout
         coef = self.buf(slot, tag + ".coef", (2 * C,), torch.float32)
         p = L.drop_p
-        call("wsl_bn_bwd", y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
+        call("wsl_bn_bwd", y, self.dt, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
              self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
              self.gview(bn.bias), coef, dy, self._ws("bn"))
 
@@ -414,7 +425,7 @@ class UNetExecutor:
                     else:
                         call("wsl_chan_mask_gen", (di + 1) * 7919 + i, self.seed_dev, N * ft[i], 0.5, c)
                     d = self.buf(slot, f"dec{di}.drop{i}", tuple(f.shape))
-                    call("wsl_chan_scale", f, c, N, f.shape[1], f.shape[2], ft[i], d)
+                    call("wsl_chan_scale", f, self.dt, c, N, f.shape[1], f.shape[2], ft[i], d)
                     cs.append(c)
                     fe.append(d)
                 drec["cs"] = cs
@@ -426,7 +437,7 @@ class UNetExecutor:
                 t = self.buf(slot, f"dec{di}.up{j}.t", (N, hh, ww, C2))
                 self.conv_fwd(c1, [xlow], t, 0, N, hh, ww, C2)
                 u = self.buf(slot, f"dec{di}.up{j}.u", (N, 2 * hh, 2 * ww, C2))
-                call("wsl_upsample2x_fwd", t, N, hh, ww, C2, u)
+                call("wsl_upsample2x_fwd", t, self.dt, N, hh, ww, C2, u)
                 hh, ww = 2 * hh, 2 * ww
                 r = run_block(f"dec{di}.up{j}", blk, [skip, u], hh, ww, None, pool=False)
                 r["xlow"] = xlow
@@ -469,7 +480,7 @@ class UNetExecutor:
         gflat, _ = self.grads()
         if zero_grads:
             gflat.zero_()
-        B = lambda name, shape, dt=BF16: self.buf(slot, "g." + name, shape, dt)
+        B = lambda name, shape, dt=None: self.buf(slot, "g." + name, shape, dt)
 
         def block_bwd(tag, blk, r, g0, g1=None, cs1=None, gpool=None, need_dsrc=True):
             """returns list of gradients w.r.t. the block's sources (None for the image)."""
@@ -504,7 +515,7 @@ class UNetExecutor:
                 continue
             g = g.contiguous()
             dl = B(f"dec{di}.dl", (N, H, W, 16))
-            call("wsl_nchw_f32_to_nhwc_bf16", g, N, self.n_class, H, W, 16, dl)
+            call("wsl_nchw_f32_to_nhwc", g, N, self.n_class, H, W, 16, dl, self.dt)
             with self.on_side():
                 self.conv_wgrad(oc, [drec["xlast"]], dl, N, H, W)
             da = B(f"dec{di}.dlast", (N, H, W, ft[0]))
@@ -517,7 +528,7 @@ class UNetExecutor:
                 skip_grads[lvl].append((dskip, drec["cs"][lvl] if drec["cs"] else None))
                 hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
                 dt = B(f"dec{di}.up{j}.dt", (N, hh, ww, C2))
-                call("wsl_upsample2x_bwd", du, N, hh, ww, C2, dt)
+                call("wsl_upsample2x_bwd", du, self.dt, N, hh, ww, C2, dt)
                 with self.on_side():
                     self.conv_wgrad(c1, [r["xlow"]], dt, N, hh, ww)
                 da = B(f"dec{di}.up{j}.dxlow", (N, hh, ww, c1.Cin))

@@ -140,10 +140,20 @@ class _PlannedNet(nn.Module):
         self.dropout_masks = None      # {encoder level: uint8 NHWC keep-mask}  (tests / parity runs)
         self.channel_keep = None       # [five [N,C] keep masks]               (tests / parity runs)
 
+    precision = "bf16"     # "bf16": tensor-core fast path; "fp32": reference-accurate parity mode (set_precision)
+
+    def set_precision(self, precision):
+        """'bf16' (default; activations stored in bf16, tcgen05 convolutions) or 'fp32' (every activation and
+        gradient in fp32, CUDA-core convolutions: numerically equivalent to the fp32 reference, ~100x slower)."""
+        assert precision in ("bf16", "fp32")
+        object.__setattr__(self, "precision", precision)
+        object.__setattr__(self, "_holder", None)
+        return self
+
     @property
     def executor(self):
         if self._holder is None:
-            ex = UNetExecutor(self, self.encoder, [getattr(self, n) for n in self._decoders], list(self._aux))
+            ex = UNetExecutor(self, self.encoder, [getattr(self, n) for n in self._decoders], list(self._aux), self.precision)
             object.__setattr__(self, "_holder", _Holder(ex))
         return self._holder.executor
 
