@@ -448,8 +448,12 @@ struct ConvV2Cfg {
                                         : (2 * MT * NT <= 256) ? 256 : 512;
 };
 
+// conv_tc2 runs EIGHT epilogue warps (two per TMEM lane quarter, each taking half of the accumulator columns): the
+// epilogue (tcgen05.ld, bias, bf16 pack, stores, BatchNorm partial sums) was the pacing stage with four.
+constexpr int CONV2_THREADS = 64 + 256;
+
 template <int KS, int KBLK, int NT, int MT, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0,
+__global__ void __launch_bounds__(CONV2_THREADS) conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0,
                                                                const __grid_constant__ CUtensorMap map_a1,
                                                                const __grid_constant__ CUtensorMap map_b, const ConvV2Params p,
                                                                const int w_bytes) {
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
     prefetch_tmap(&map_a0);
@@ -545,6 +549,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    constexpr int NCH = NT / 16;                           // 16-column chunks of the accumulator
+    const int half = (warp - 2) >> 2;                      // which half of the chunks this warp owns
+    const int ch_lo = (NCH >= 2) ? half * (NCH / 2) : 0;
+    const int ch_hi = (NCH >= 2) ? (half + 1) * (NCH / 2) : (half == 0 ? 1 : 0);
     float rs[NT / 16], rq[NT / 16];       // running per-channel sum / sum of squares (channel = chunk*16 + ((lane>>1)&15))
 #pragma unroll
     for (int c = 0; c < NT / 16; ++c) rs[c] = rq[c] = 0.f;
@@ -561,6 +569,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
         const int gy = y0 + 16 * j + m / 8, gx = x0 + (m & 7);
 #pragma unroll
         for (int c = 0; c < NT; c += 16) {
+          if (c / 16 < ch_lo || c / 16 >= ch_hi) continue;   // warp-uniform: the other epilogue warp of this quarter owns it
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + j) * NT + c), v);
           if (p.bias) {
@@ -606,13 +615,14 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc2_kernel(const __grid_cons
       if ((lane & 1) == 0) {
 #pragma unroll
         for (int c = 0; c < NT / 16; ++c) {
+          if (c < ch_lo || c >= ch_hi) continue;
           s_stat[q][0][c * 16 + ((lane >> 1) & 15)] = rs[c];
           s_stat[q][1][c * 16 + ((lane >> 1) & 15)] = rq[c];
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;      // 0..127 over the epilogue warps
-      for (int c = t; c < 2 * NT; c += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - 64;      // 0..255 over the epilogue warps
+      for (int c = t; c < 2 * NT; c += 256) {
         const int which = c / NT, ch = c % NT;
         const float a = ((s_stat[0][which][ch] + s_stat[1][which][ch]) + s_stat[2][which][ch]) + s_stat[3][which][ch];
         p.stat_partials[((size_t)blockIdx.x * 2 + which) * p.CoutP + n0 + ch] = a;
@@ -1196,7 +1206,7 @@ int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid(gx, n_tiles);
   g_conv2_last_rows = gx;
-  conv_tc2_kernel<KS, KBLK, NT, MT, STAGES><<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p, w_bytes);
+  conv_tc2_kernel<KS, KBLK, NT, MT, STAGES><<<grid, CONV2_THREADS, smem, stream>>>(a0, a1, b, p, w_bytes);
   return wsl_check_launch("conv_tc2");
 }
 

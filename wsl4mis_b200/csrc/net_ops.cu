@@ -923,7 +923,7 @@ inline int bn_grid(long long P, int C) {
   // every block should stream >= ~96 KB so that the fixed-order finalize (one pass over all partials) stays negligible
   long long b = (P * C * 2 + 96 * 1024 - 1) / (96 * 1024);
   if (b < 1) b = 1;
-  if (b > 148 * 4) b = 148 * 4;
+  if (b > 148 * 3) b = 148 * 3;      // one full wave at 3 resident blocks / SM (80 registers, 256 threads)
   return (int)b;
 }
 
@@ -1018,7 +1018,7 @@ static int bn_bwd_launch(const void* y, const float* ss, const float* save, cons
   bn_bwd_reduce_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws));
   int rc = wsl_check_launch("bn_bwd_reduce");
   if (rc) return rc;
-  bn_bwd_apply_kernel<T><<<grid_for(P * (C / 8) / 2), TPB, 0, stream>>>(a, coef, (T*)dy);
+  bn_bwd_apply_kernel<T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
   return wsl_check_launch("bn_bwd_apply");
 }
 
