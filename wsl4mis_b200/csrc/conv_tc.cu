@@ -450,10 +450,11 @@ struct ConvV2Cfg {
 
 // conv_tc2 runs EIGHT epilogue warps (two per TMEM lane quarter, each taking half of the accumulator columns): the
 // epilogue (tcgen05.ld, bias, bf16 pack, stores, BatchNorm partial sums) was the pacing stage with four.
-constexpr int CONV2_THREADS = 64 + 256;
+template <int NT, int MT>
+struct Conv2Epi { static constexpr int WARPS = (NT >= 64 && MT == 1) ? 8 : 4; static constexpr int THREADS = 64 + 32 * WARPS; };
 
 template <int KS, int KBLK, int NT, int MT, int STAGES>
-__global__ void __launch_bounds__(CONV2_THREADS) conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0,
+__global__ void __launch_bounds__(Conv2Epi<NT, MT>::THREADS) conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0,
                                                                const __grid_constant__ CUtensorMap map_a1,
                                                                const __grid_constant__ CUtensorMap map_b, const ConvV2Params p,
                                                                const int w_bytes) {
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(CONV2_THREADS) conv_tc2_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Conv2Epi<NT, MT>::WARPS); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
     prefetch_tmap(&map_a0);
@@ -550,9 +551,10 @@ __global__ void __launch_bounds__(CONV2_THREADS) conv_tc2_kernel(const __grid_co
     const int q = warp & 3;
     const int m = q * 32 + lane;
     constexpr int NCH = NT / 16;                           // 16-column chunks of the accumulator
-    const int half = (warp - 2) >> 2;                      // which half of the chunks this warp owns
-    const int ch_lo = (NCH >= 2) ? half * (NCH / 2) : 0;
-    const int ch_hi = (NCH >= 2) ? (half + 1) * (NCH / 2) : (half == 0 ? 1 : 0);
+    constexpr int EW = Conv2Epi<NT, MT>::WARPS;
+    const int half = (warp - 2) >> 2;                      // which half of the chunks this warp owns (EW == 8)
+    const int ch_lo = (EW == 8) ? half * (NCH / 2) : 0;
+    const int ch_hi = (EW == 8) ? (half + 1) * (NCH / 2) : NCH;
     float rs[NT / 16], rq[NT / 16];       // running per-channel sum / sum of squares (channel = chunk*16 + ((lane>>1)&15))
 #pragma unroll
     for (int c = 0; c < NT / 16; ++c) rs[c] = rq[c] = 0.f;
@@ -620,9 +622,9 @@ __global__ void __launch_bounds__(CONV2_THREADS) conv_tc2_kernel(const __grid_co
           s_stat[q][1][c * 16 + ((lane >> 1) & 15)] = rq[c];
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int t = threadIdx.x - 64;      // 0..255 over the epilogue warps
-      for (int c = t; c < 2 * NT; c += 256) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+      const int t = threadIdx.x - 64;      // index over the epilogue warps
+      for (int c = t; c < 2 * NT; c += 32 * EW) {
         const int which = c / NT, ch = c % NT;
         const float a = ((s_stat[0][which][ch] + s_stat[1][which][ch]) + s_stat[2][which][ch]) + s_stat[3][which][ch];
         p.stat_partials[((size_t)blockIdx.x * 2 + which) * p.CoutP + n0 + ch] = a;
@@ -1206,7 +1208,7 @@ int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid(gx, n_tiles);
   g_conv2_last_rows = gx;
-  conv_tc2_kernel<KS, KBLK, NT, MT, STAGES><<<grid, CONV2_THREADS, smem, stream>>>(a0, a1, b, p, w_bytes);
+  conv_tc2_kernel<KS, KBLK, NT, MT, STAGES><<<grid, Conv2Epi<NT, MT>::THREADS, smem, stream>>>(a0, a1, b, p, w_bytes);
   return wsl_check_launch("conv_tc2");
 }
 
