@@ -238,6 +238,7 @@ def main():
         peaks = load_peaks()
         prof = _lib.Profiler()
         eager = TrainStep(model, args.variant, graph=False, world_size=1)
+        eager.ex.multi_stream = False        # serialise: per-kernel event times are only meaningful without overlap
         eager(img_d, lab_d)
         torch.cuda.synchronize()
         _lib.PROFILE = prof
@@ -269,10 +270,17 @@ def main():
                  for k, v in sorted(byname.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(byname.items(), key=lambda kv: kv[1]["ms"])
         name, v = top
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("kernel") == name:
+                traffic = {"dram_MB_per_launch": round(tj["dram_bytes_per_launch_MB"], 1), "source": tj["source"]}
         if v["flops"] > 0:
             ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
             roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None,
+                    "frac": round(ach / peaks["tf_sustained"], 4), "traffic": traffic,
+                    "algorithmic_MB_per_launch": round(v["bytes"] / v["launches"] / 1e6, 1),
                     "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
                     "avg_launch_ms": round(v["ms"] / v["launches"], 4), "algorithmic_flops_per_launch": v["flops"] / v["launches"]}
         else:
@@ -294,8 +302,8 @@ def main():
                        "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush needed"},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel()), "d2h_bytes_per_step": 4},
-            "gpu_launches": (launches_per_step or 0) * K if step.graph_enabled else launches_eager,
-            "gpu_launches_per_step": launches_per_step,
+            "gpu_launches": (step.launches_per_step * K) if step.graph_enabled else launches_eager,
+            "gpu_launches_per_step": step.launches_per_step,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": table,
             "loss_first": first_loss, "loss_last": float(lv),
         }

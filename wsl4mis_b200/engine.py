@@ -22,6 +22,7 @@ import random
 import torch
 
 from . import ddp
+from . import _lib
 from ._lib import call, workspace
 
 VARIANTS = ("pce", "pce_gatedcrf", "pce_ms", "pce_tv", "dmpls")
@@ -71,6 +72,7 @@ class TrainStep:
         else:
             self.n_trained = n
         self.loss_parts = {}
+        self.launches_per_step = 0
 
     # ------------------------------------------------------------------
     def _head(self, logits_list, image, label, slot):
@@ -146,11 +148,13 @@ class TrainStep:
 
     def _fwd_bwd(self, image, label):
         ex = self.ex
+        c0 = _lib.COUNTERS["launch_calls"]
         outs, slot = ex.forward(image, True, True, getattr(self.model, "dropout_masks", None),
                                 getattr(self.model, "channel_keep", None))
         loss, dl = self._head(outs, image, label, slot)
         gflat = ex.backward(slot, dl)
         self._outs = outs
+        self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0 + 1     # + the SGD kernel (also inside the graph)
         return loss, gflat
 
     def _opt(self, gflat):
