@@ -19,6 +19,7 @@ _SCALARS = {
     "float": ctypes.c_float,
     "long long": ctypes.c_longlong,
     "unsigned long long": ctypes.c_ulonglong,
+    "unsigned int": ctypes.c_uint,
     "cudaStream_t": ctypes.c_void_p,
 }
 

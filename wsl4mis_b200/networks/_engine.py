@@ -174,7 +174,7 @@ class UNetExecutor:
         """per-stream scratch for the conv-epilogue BatchNorm partial rows"""
         key = "side" if self._on_side else "main"
         if key not in self._stat_bufs or self._stat_bufs[key].device != self.dev:
-            self._stat_bufs[key] = torch.zeros(592 * 2 * 256, dtype=torch.float32, device=self.dev)
+            self._stat_bufs[key] = torch.zeros(592 * 2 * 256 + 64, dtype=torch.float32, device=self.dev)   # + ticket word
         return self._stat_bufs[key]
 
     # ---------------------------------------------------------------- two-stream scheduling
@@ -233,10 +233,12 @@ class UNetExecutor:
     def _tc_ok(self, layer_cin_list, H, W):
         return (self.dt == 0 and self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
 
-    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, want_stats=False):
-        """Returns the number of BatchNorm partial-statistics rows the conv epilogue produced (0 = none)."""
+    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, bn_out=None):
+        """bn_out = (save, ss) buffers: when the convolution runs on the persistent tcgen05 kernel the complete
+        training-mode BatchNorm statistics of its output are produced by the kernel itself (partial rows in the epilogue,
+        finalised by the last CTA).  Returns True when that happened."""
         pk = L.packs(self.dev)
-        rows = 0
+        rows = False
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
         c0 = L.srcC[0]
@@ -248,11 +250,13 @@ class UNetExecutor:
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2):
             call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout)
         elif not src_f32 and self._tc2_ok(L.srcC, H, W):
-            if want_stats and self.fuse_bn_stats:
+            if bn_out is not None and self.fuse_bn_stats and out_mode == 0:
                 sb = self._stat_scratch()
-                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks,
-                     sb, ctypes.addressof(self._stat_rows))
-                rows = self._stat_rows.value
+                bn = L.bn
+                call("wsl_conv_tc2_bn", s0, c0, s1, c1, pk["bf"], pk["bias"], out, N, H, W, L.CoutP, L.Cout, L.ks, sb,
+                     bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(bn.momentum),
+                     float(bn.eps), bn_out[0], bn_out[1], sb[592 * 2 * 256:])
+                rows = True
             else:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks, None, None)
         elif not src_f32 and self._tc_ok(L.srcC, H, W):
@@ -301,15 +305,18 @@ class UNetExecutor:
         if tc and L.bn is None:
             call("wsl_channel_sum", dy, self.dt, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias))
 
-    def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None, stat_rows=0):
+    def bn_bufs(self, L, slot, tag):
+        C = L.Cout
+        return (self.buf(slot, tag + ".save", (2 * C,), torch.float32), self.buf(slot, tag + ".ss", (2 * C,), torch.float32))
+
+    def bn_fwd(self, L: ConvLayer, y, act, N, H, W, training, slot, tag, mask=None, pooled=None, pool_idx=None, stats_done=False):
         bn = L.bn
         C = L.Cout
         pk = L.packs(self.dev)
         save = self.buf(slot, tag + ".save", (2 * C,), torch.float32)
         ss = self.buf(slot, tag + ".ss", (2 * C,), torch.float32)
-        if training and stat_rows > 0:
-            call("wsl_bn_finalize", self._stat_scratch(), stat_rows, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss)
+        if training and stats_done:
+            pass                       # save / ss were written by the convolution kernel
         elif training:
             call("wsl_bn_stats", y, self.dt, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                  bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"))
@@ -361,7 +368,7 @@ class UNetExecutor:
                 pk["bias"][: L.Cout].copy_(L.conv.bias.detach())
 
     def forward(self, x: torch.Tensor, training: bool, need_grad: bool, masks: Optional[dict] = None,
-                chan_keep: Optional[list] = None):
+                chan_keep: Optional[list] = None, defer_join: bool = False):
         """x: fp32 [N, in_chns, H, W] CUDA.  Returns (list of fp32 NCHW logits, slot)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4, "input must be a CUDA fp32 NCHW tensor"
         assert x.shape[1] == self.in_chns == 1, "executor is specialised to single-channel inputs (ACDC slices)"
@@ -385,14 +392,14 @@ class UNetExecutor:
             a1 = self.buf(slot, tag + ".a1", (N, h, w, C))
             y2 = self.buf(slot, tag + ".y2", (N, h, w, C))
             a2 = self.buf(slot, tag + ".a2", (N, h, w, C))
-            r1 = self.conv_fwd(l1, srcs, y1, 0, N, h, w, C, src_f32, want_stats=training)
-            sv1, ss1 = self.bn_fwd(l1, y1, a1, N, h, w, training, slot, tag + ".bn1", mask, stat_rows=r1)
-            r2 = self.conv_fwd(l2, [a1], y2, 0, N, h, w, C, want_stats=training)
+            r1 = self.conv_fwd(l1, srcs, y1, 0, N, h, w, C, src_f32, bn_out=self.bn_bufs(l1, slot, tag + ".bn1") if training else None)
+            sv1, ss1 = self.bn_fwd(l1, y1, a1, N, h, w, training, slot, tag + ".bn1", mask, stats_done=r1)
+            r2 = self.conv_fwd(l2, [a1], y2, 0, N, h, w, C, bn_out=self.bn_bufs(l2, slot, tag + ".bn2") if training else None)
             pooled = idx = None
             if pool:
                 pooled = self.buf(slot, tag + ".pool", (N, h // 2, w // 2, C))
                 idx = self.buf(slot, tag + ".pidx", (N, h // 2, w // 2, C), torch.uint8)
-            sv2, ss2 = self.bn_fwd(l2, y2, a2, N, h, w, training, slot, tag + ".bn2", None, pooled, idx, stat_rows=r2)
+            sv2, ss2 = self.bn_fwd(l2, y2, a2, N, h, w, training, slot, tag + ".bn2", None, pooled, idx, stats_done=r2)
             return {"srcs": srcs, "y1": y1, "a1": a1, "y2": y2, "a2": a2, "sv1": sv1, "ss1": ss1, "sv2": sv2, "ss2": ss2,
                     "pool": pooled, "pidx": idx, "mask": mask, "h": h, "w": w, "src_f32": src_f32}
 
@@ -452,7 +459,8 @@ class UNetExecutor:
             with self.on_side():
                 drecs[di] = run_decoder(di, *self.dec[di])
         drecs[0] = run_decoder(0, *self.dec[0])
-        self.join_side()
+        if not (defer_join and need_grad):
+            self.join_side()           # otherwise backward() joins: the aux outputs must not be read before that
         rec["dec"] = drecs
         if need_grad:
             self._recs[slot] = rec
