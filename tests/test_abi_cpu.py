@@ -76,3 +76,32 @@ def test_ramps():
     assert ramps.sigmoid_rampup(0, 10) == pytest.approx(0.006737947, rel=1e-6)
     assert ramps.sigmoid_rampup(10, 10) == 1.0 and ramps.sigmoid_rampup(5, 0) == 1.0
     assert ramps.linear_rampup(5, 10) == 0.5 and ramps.cosine_rampdown(0, 10) == 1.0
+
+
+def test_dropin_shim_exposes_the_reference_module_names():
+    """`dropin/` ahead of the reference's code/ on PYTHONPATH gives the scripts' own import lines the B200 modules
+    (train_weakly_supervised_pCE_GatedCRFLoss_2D.py:23-28)."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.") or k == "networks" or k.startswith("networks.")}
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        nf = importlib.import_module("networks.net_factory")
+        un = importlib.import_module("networks.unet")
+        lo = importlib.import_module("utils.losses")
+        cr = importlib.import_module("utils.gate_crf_loss")
+        ra = importlib.import_module("utils.ramps")
+        assert callable(nf.net_factory)
+        for name in ("ConvBlock", "DownBlock", "UpBlock", "Encoder", "Decoder", "UNet", "UNet_CCT", "UNet_DS", "UNet_CCT_3H",
+                     "Decoder_DS", "Decoder_URDS", "Dropout", "FeatureDropout", "FeatureNoise"):
+            assert hasattr(un, name), name
+        for name in ("pDLoss", "DiceLoss", "MumfordShah_Loss", "entropy_loss", "softmax_mse_loss", "entropy_minmization",
+                     "symmetric_mse_loss", "dice_loss"):
+            assert hasattr(lo, name), name
+        assert hasattr(cr, "ModelLossSemsegGatedCRF") and hasattr(ra, "sigmoid_rampup")
+    finally:
+        sys.path.remove(os.path.join(root, "dropin"))
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "networks" or k.startswith("networks.")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
