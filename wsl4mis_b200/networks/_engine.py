@@ -135,7 +135,7 @@ class UNetExecutor:
         self.use_tc2 = os.environ.get("WSL4MIS_NO_TC2", "0") != "1"
         self.wgrad_version = int(os.environ.get("WSL4MIS_WGRAD", "3"))
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
-        self.fuse_bn_finalize = os.environ.get("WSL4MIS_FUSE_FINALIZE", "1") == "1"
+        self.fuse_bn_finalize = os.environ.get("WSL4MIS_FUSE_FINALIZE", "0") == "1"   # measured: no gain over the separate 1-block finalize kernel inside a graph
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._side = None
