@@ -115,13 +115,6 @@ int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void*
 /* stat_partials (optional, device, >= 592*2*CoutP floats): per-CTA sum / sum-of-squares rows of the stored outputs for the
  * following BatchNorm; *stat_rows_host (optional, HOST int) receives the number of rows written.  wsl_bn_finalize turns
  * the rows into {mean, invstd, scale, shift} and updates the running statistics exactly like wsl_bn_stats. */
-/* conv_tc2 (bf16 NHWC output) + the complete training-mode BatchNorm statistics of its output: the last CTA to finish
- * (ticket = one zero-initialised device word) turns the partial rows into save/ss and updates the running statistics,
- * so no separate statistics or finalize launch sits on the critical path. */
-int wsl_conv_tc2_bn(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                    int N, int H, int W, int CoutP, int Cout, int ksize, float* stat_partials, const float* gamma,
-                    const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
-                    float momentum, float eps, float* save, float* ss, unsigned int* ticket, cudaStream_t stream);
 int wsl_bn_finalize(const float* partials, int nrows, long long P, int C, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                     float* save, float* ss, cudaStream_t stream);

@@ -208,43 +208,6 @@ def test_wgrad_tc(case, ver):
     assert rel_l2(dw.cpu(), 2 * gw.float()) < 1e-4
 
 
-@pytest.mark.parametrize("case", [(2, 32, 32, 16, 0, 16, 3), (1, 32, 32, 64, 64, 64, 3), (2, 16, 16, 128, 0, 256, 3), (2, 64, 32, 32, 0, 32, 3)])
-def test_conv_with_fused_batchnorm_statistics(case):
-    """wsl_conv_tc2_bn: conv output + complete training-mode BatchNorm statistics (last-CTA finalisation)."""
-    N, H, W, C0, C1, Cout, ks = case
-    g = torch.Generator().manual_seed(31)
-    x = bf16_round(torch.randn(N, C0 + C1, H, W, generator=g))
-    w = torch.randn(Cout, C0 + C1, ks, ks, generator=g) / np.sqrt((C0 + C1) * ks * ks)
-    b = torch.randn(Cout, generator=g) * 0.1
-    gamma, beta = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.2
-    rm, rv = torch.randn(Cout, generator=g) * 0.1, torch.rand(Cout, generator=g) + 0.5
-    pk = _pack(w.to(DEV), [C0, C1] if C1 else [C0])
-    out = torch.zeros((N, H, W, Cout), device=DEV, dtype=BF)
-    parts = torch.zeros(592 * 2 * 256 + 64, device=DEV)
-    save, ss = torch.zeros(2 * Cout, device=DEV), torch.zeros(2 * Cout, device=DEV)
-    rmd, rvd, nbt = rm.to(DEV), rv.to(DEV), torch.zeros((), dtype=torch.int64, device=DEV)
-    s0 = nhwc(x[:, :C0]).to(DEV)
-    s1 = nhwc(x[:, C0:]).to(DEV) if C1 else None
-    for rep in range(2):   # twice: the ticket must be left at zero
-        call("wsl_conv_tc2_bn", s0, C0, s1, C1, pk["bf"], b.to(DEV), out, N, H, W, pk["CoutP"], Cout, ks, parts, gamma.to(DEV),
-             beta.to(DEV), rmd, rvd, nbt, 0.1, 1e-5, save, ss, parts[592 * 2 * 256:])
-    torch.cuda.synchronize()
-    y = nchw(out.cpu())
-    ref = F.conv2d(x.double(), bf16_round(w).double(), b.double(), padding=ks // 2).float()
-    assert (y - ref).abs().max().item() / ref.abs().max().item() < 2 ** -7
-    mean, var = y.double().mean((0, 2, 3)), y.double().var((0, 2, 3), unbiased=False)
-    assert torch.allclose(save[:Cout].cpu().double(), mean, atol=1e-5)
-    assert torch.allclose(save[Cout:].cpu().double(), 1 / torch.sqrt(var + 1e-5), rtol=1e-4)
-    sc = gamma.double() / torch.sqrt(var + 1e-5)
-    assert torch.allclose(ss[:Cout].cpu().double(), sc, rtol=1e-4)
-    assert torch.allclose(ss[Cout:].cpu().double(), beta.double() - mean * sc, atol=1e-4)
-    assert nbt.item() == 2
-    n = N * H * W
-    rm2 = 0.9 * (0.9 * rm.double() + 0.1 * mean) + 0.1 * mean
-    rv2 = 0.9 * (0.9 * rv.double() + 0.1 * var * n / (n - 1)) + 0.1 * var * n / (n - 1)
-    assert torch.allclose(rmd.cpu().double(), rm2, atol=1e-5) and torch.allclose(rvd.cpu().double(), rv2, rtol=1e-4)
-
-
 @pytest.mark.parametrize("shape", [(2, 32, 32), (3, 24, 40), (1, 7, 9)])
 def test_first_layer_kernels(shape):
     N, H, W = shape

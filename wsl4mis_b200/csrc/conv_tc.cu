@@ -407,18 +407,6 @@ struct ConvV2Params {
   const float* bias;
   void* out;
   float* stat_partials;   // optional [gridDim.x][2][CoutP]: per-CTA sum / sum of squares of the stored (bf16-rounded) outputs
-  // optional fused BatchNorm finalisation by the last CTA to finish (ticket): statistics -> {mean, invstd, scale, shift},
-  // running-stat update (nn.BatchNorm2d training semantics, unet.py:20,24)
-  const float* bn_gamma;
-  const float* bn_beta;
-  float* bn_running_mean;
-  float* bn_running_var;
-  long long* bn_nbt;
-  float* bn_save;
-  float* bn_ss;
-  unsigned* bn_ticket;
-  float bn_momentum, bn_eps;
-  int bn_C;
 };
 
 // Sum over the 32 lanes of a warp for 16 per-lane values with a transpose-reduction (16 shuffles instead of 80):
@@ -640,58 +628,6 @@ __global__ void __launch_bounds__(Conv2Epi<NT, MT>::THREADS) conv_tc2_kernel(con
         const int which = c / NT, ch = c % NT;
         const float a = ((s_stat[0][which][ch] + s_stat[1][which][ch]) + s_stat[2][which][ch]) + s_stat[3][which][ch];
         p.stat_partials[((size_t)blockIdx.x * 2 + which) * p.CoutP + n0 + ch] = a;
-      }
-      if (p.bn_ticket != nullptr) {
-        // ---- last CTA (over the whole grid) finalises the statistics: no extra launch on the critical path ----
-        constexpr int ET = 32 * EW;
-        __shared__ double s_part[ET * 2];
-        __shared__ int s_last;
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-        if (t == 0) s_last = (atomicAdd(p.bn_ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
-        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-        if (s_last) {
-          __threadfence();
-          const int C = p.bn_C, rows = gridDim.x;
-          const double P = (double)p.N * p.H * p.W;
-          for (int cbase = 0; cbase < C; cbase += ET) {
-            const int cw = min(C - cbase, ET), parts = ET / cw;
-            const int c = cbase + t % cw, part = t / cw;
-            double a = 0.0, b = 0.0;
-            if (part < parts) {
-              for (int r = part; r < rows; r += parts) {       // fixed order -> deterministic
-                a += (double)__ldcg(&p.stat_partials[((size_t)r * 2 + 0) * p.CoutP + c]);
-                b += (double)__ldcg(&p.stat_partials[((size_t)r * 2 + 1) * p.CoutP + c]);
-              }
-            }
-            s_part[t * 2] = a;
-            s_part[t * 2 + 1] = b;
-            asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-            if (t < cw) {
-              double x = 0.0, y = 0.0;
-              for (int qq = 0; qq < parts; ++qq) { x += s_part[(qq * cw + t) * 2]; y += s_part[(qq * cw + t) * 2 + 1]; }
-              const double mean = x / P;
-              double var = y / P - mean * mean;
-              if (var < 0.0) var = 0.0;
-              const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-              p.bn_save[c] = (float)mean;
-              p.bn_save[C + c] = invstd;
-              const float sc = p.bn_gamma[c] * invstd;
-              p.bn_ss[c] = sc;
-              p.bn_ss[C + c] = p.bn_beta[c] - (float)mean * sc;
-              if (p.bn_running_mean) {
-                p.bn_running_mean[c] = (1.f - p.bn_momentum) * p.bn_running_mean[c] + p.bn_momentum * (float)mean;
-                const double unb = (P > 1.0) ? var * P / (P - 1.0) : var;
-                p.bn_running_var[c] = (1.f - p.bn_momentum) * p.bn_running_var[c] + p.bn_momentum * (float)unb;
-              }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-          }
-          if (t == 0) {
-            if (p.bn_nbt) *p.bn_nbt += 1;
-            *p.bn_ticket = 0u;
-          }
-        }
       }
     }
   }
@@ -1391,14 +1327,9 @@ WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Cr
 }
 
 // conv_tc v2 entry point (same contract as wsl_conv_tc; needs W % 8 == 0 and H % (16*MT) == 0)
-struct Conv2BnHost {
-  const float* gamma; const float* beta; float* rm; float* rv; long long* nbt; float* save; float* ss; unsigned* ticket;
-  float momentum, eps; int C;
-};
-
-static int conv_tc2_impl(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
                          int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, float* stat_partials,
-                         int* stat_rows_host, const Conv2BnHost* bn, cudaStream_t stream) {
+                         int* stat_rows_host, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc2: ksize must be 1 or 3");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc2: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc2: CoutP must be a multiple of 16");
@@ -1442,12 +1373,6 @@ static int conv_tc2_impl(const void* src0, int C0, const void* src1, int C1, con
   p.tiles_x = W / 8; p.tiles_y = H / (16 * mt); p.ntiles = N * p.tiles_x * p.tiles_y;
   p.out_mode = out_mode; p.desc_mode = desc_mode; p.bias = bias; p.out = out;
   p.stat_partials = (out_mode == 0) ? stat_partials : nullptr;
-  p.bn_ticket = nullptr; p.bn_gamma = p.bn_beta = nullptr; p.bn_running_mean = p.bn_running_var = nullptr; p.bn_nbt = nullptr;
-  p.bn_save = p.bn_ss = nullptr; p.bn_momentum = p.bn_eps = 0.f; p.bn_C = 0;
-  if (bn != nullptr && p.stat_partials != nullptr) {
-    p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_running_mean = bn->rm; p.bn_running_var = bn->rv; p.bn_nbt = bn->nbt;
-    p.bn_save = bn->save; p.bn_ss = bn->ss; p.bn_ticket = bn->ticket; p.bn_momentum = bn->momentum; p.bn_eps = bn->eps; p.bn_C = bn->C;
-  }
 #define WSL_C2(KS_, KB_, MT_)                                                   \
   do {                                                                         \
     int rc_ = conv2_dispatch_nt<KS_, KB_, MT_>(nt, a0, a1, b, p, stream);      \
@@ -1565,20 +1490,3 @@ WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, co
 #undef WSL_W3
 }
 
-WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                         int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, float* stat_partials,
-                         int* stat_rows_host, cudaStream_t stream) {
-  return conv_tc2_impl(src0, C0, src1, C1, wpk_bf16, bias, out, out_mode, N, H, W, CoutP, CoutStore, ksize, stat_partials,
-                       stat_rows_host, nullptr, stream);
-}
-
-// conv_tc2 + complete training-mode BatchNorm statistics: the last CTA to finish finalises {mean, invstd} (save),
-// {scale, shift} (ss) and the running statistics; `ticket` is one zero-initialised device word (left zero again).
-WSL_API int wsl_conv_tc2_bn(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                            int N, int H, int W, int CoutP, int Cout, int ksize, float* stat_partials, const float* gamma,
-                            const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
-                            float momentum, float eps, float* save, float* ss, unsigned int* ticket, cudaStream_t stream) {
-  WSL_REQUIRE(stat_partials != nullptr && ticket != nullptr && Cout <= 256, "wsl_conv_tc2_bn: partial buffer / ticket required, C <= 256");
-  Conv2BnHost bn{gamma, beta, running_mean, running_var, num_batches_tracked, save, ss, ticket, momentum, eps, Cout};
-  return conv_tc2_impl(src0, C0, src1, C1, wpk_bf16, bias, out, 0, N, H, W, CoutP, Cout, ksize, stat_partials, nullptr, &bn, stream);
-}

@@ -135,7 +135,6 @@ class UNetExecutor:
         self.use_tc2 = os.environ.get("WSL4MIS_NO_TC2", "0") != "1"
         self.wgrad_version = int(os.environ.get("WSL4MIS_WGRAD", "3"))
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
-        self.fuse_bn_finalize = os.environ.get("WSL4MIS_FUSE_FINALIZE", "0") == "1"   # measured: no gain over the separate 1-block finalize kernel inside a graph
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._side = None
@@ -252,20 +251,13 @@ class UNetExecutor:
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2):
             call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout)
         elif not src_f32 and self._tc2_ok(L.srcC, H, W):
-            if bn_out is not None and self.fuse_bn_stats and out_mode == 0 and not self.fuse_bn_finalize:
+            if bn_out is not None and self.fuse_bn_stats and out_mode == 0:
                 sb = self._stat_scratch()
                 bn = L.bn
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks,
                      sb, ctypes.addressof(self._stat_rows))
                 call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
                      bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
-                rows = True
-            elif bn_out is not None and self.fuse_bn_stats and out_mode == 0:
-                sb = self._stat_scratch()
-                bn = L.bn
-                call("wsl_conv_tc2_bn", s0, c0, s1, c1, pk["bf"], pk["bias"], out, N, H, W, L.CoutP, L.Cout, L.ks, sb,
-                     bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(bn.momentum),
-                     float(bn.eps), bn_out[0], bn_out[1], sb[592 * 2 * 256:])
                 rows = True
             else:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks, None, None)
