@@ -228,18 +228,30 @@ def main():
             bufs[i][1].copy_(lab_h, non_blocking=True)
             copied[i].record(copy_stream)
 
+    loss_h = torch.zeros(2, dtype=torch.float32).pin_memory()
+    read_ev = [torch.cuda.Event(), torch.cuda.Event()]
     barrier()
     e0.record()
     n_e2e = 0 if args.skip_e2e else K
     if n_e2e:
         prefetch(0)
+    lv = float("nan")
     for k in range(n_e2e):
         cur = k % 2
         main_stream.wait_event(copied[cur])          # this step's inputs have landed
         loss = step(*bufs[cur])
+        loss_h[cur:cur + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H of this step's result ...
+        read_ev[cur].record()
         if k + 1 < n_e2e:
+            if k >= 1:
+                copy_stream.wait_event(read_ev[1 - cur])   # step k-1, the last reader of that buffer pair, has finished
             prefetch((k + 1) % 2)                    # next step's H2D runs under this step's graph
-        lv = loss.item()                             # D2H of the step's result (also orders buffer reuse)
+        if k >= 1:                                   # ... consumed on the host one step later (software pipelining:
+            read_ev[1 - cur].synchronize()           # the launch of step k is never stalled by reading step k-1)
+            lv = float(loss_h[1 - cur])
+    if n_e2e:
+        read_ev[(n_e2e - 1) % 2].synchronize()
+        lv = float(loss_h[(n_e2e - 1) % 2])
     e1.record()
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), 1e-6)
