@@ -80,6 +80,20 @@ int wsl_pdice_bwd(const float* probs, const uint8_t* target, const float* msum, 
 int wsl_tv_loss(const float* probs, int planes, int H, int W, float grad_scale, float* gprobs_zeroed, float* out1,
                 float* ws, cudaStream_t stream);
 
+/* Uncertainty-aware mean-teacher consistency (train_uncertainty_aware_mean_teacher_2D.py:164-188): mean softmax of the T
+ * stochastic teacher passes (mc_logits [T*B,4,H,W], script layout) -> entropy -> mask (u8 [B,H,W]) -> masked
+ * softmax_mse_loss(student, teacher) (utils/losses.py:65-82) / (2*sum(mask)+1e-16).  out3 = {sum, count, loss}.
+ * threshold / weight are read from device memory when the *_ptr is non-NULL (graph-capture friendly ramps). */
+int wsl_uamt_consistency_fwd(const float* student, const float* teacher, const float* mc_logits, int T, int B, int C, int H,
+                             int W, const float* threshold_ptr, float threshold, uint8_t* mask, float* out3, float* ws,
+                             cudaStream_t stream);
+int wsl_uamt_consistency_bwd(const float* student, const float* teacher, const uint8_t* mask, const float* stats3,
+                             const float* weight_ptr, float weight, int B, int C, int H, int W, float* dlogits,
+                             cudaStream_t stream);
+/* out[r*n + i] = x[i] + clamp(sigma*N(0,1), -clamp, clamp)  (:147-149,167-169), counter RNG, r < reps */
+int wsl_add_clamped_noise(const float* x, long long n, int reps, float sigma, float clamp, unsigned long long seed,
+                          const unsigned long long* seed_ptr, float* out, cudaStream_t stream);
+
 /* ---- network operators (networks/unet.py) ---------------------------------------------------------------- */
 
 /* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the
@@ -146,10 +160,11 @@ int wsl_bn_act_fwd(const void* y, int dtype, const float* ss, int N, int H, int 
                    const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr, void* act,
                    void* pooled, uint8_t* pool_idx, cudaStream_t stream);
 
-/* backward of the same chain: dA = g0 + cs1*g1 + maxpool-routed gpool (each optional) -> dY (bf16), dgamma, dbeta. */
+/* backward of the same chain: dA = g0 + cs1*g1 + maxpool-routed gpool (each optional) -> dY, dgamma, dbeta (added to the
+ * existing values when accumulate != 0: a second backward through shared weights, e.g. the mean-teacher student). */
 int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
                const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
-               const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
+               const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws, int accumulate,
                cudaStream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:56-57) and its transpose. */

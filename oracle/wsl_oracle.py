@@ -373,6 +373,36 @@ def step_loss_pce_tv(logits, label):
     return ce + 1e-2 * tv, ce, tv
 
 
+def sigmoid_rampup(current, rampup_length):
+    """utils/ramps.py:19-26."""
+    if rampup_length == 0:
+        return 1.0
+    cur = min(max(float(current), 0.0), float(rampup_length))
+    ph = 1.0 - cur / rampup_length
+    return float(math.exp(-5.0 * ph * ph))
+
+
+def uamt_losses(out_l, out_u, ema_out, mc_logits, label_l, iter_num, max_iterations, consistency=0.1,
+                consistency_rampup=200.0, T=8):
+    """Loss composition of train_uncertainty_aware_mean_teacher_2D.py:151-190.
+    out_l / out_u: student logits on the labelled / unlabelled half; ema_out: teacher logits on the noisy unlabelled
+    inputs (:157-158); mc_logits: the [T*B,4,H,W] buffer of the T/2 teacher calls on the twice-repeated batch (:164-170).
+    label_l is dense (uint8/int64, no ignore_index: ce_loss = CrossEntropyLoss() at :127)."""
+    B = out_u.shape[0]
+    preds = F.softmax(mc_logits, dim=1).reshape(T, B, *mc_logits.shape[1:]).mean(0)            # :171-173
+    uncertainty = -(preds * torch.log(preds + 1e-6)).sum(1, keepdim=True)                     # :175-176
+    soft_l = torch.softmax(out_l, 1)
+    loss_ce = F.cross_entropy(out_l, label_l.long())                                          # :178
+    loss_dice = dice_loss(soft_l, label_l.long().unsqueeze(1))                                # :179
+    supervised = 0.5 * (loss_dice + loss_ce)                                                  # :180
+    cw = consistency * sigmoid_rampup(iter_num // 300, consistency_rampup)                    # :73-75, :181-182
+    dist = softmax_mse(out_u, ema_out)                                                        # :183-184
+    threshold = (0.75 + 0.25 * sigmoid_rampup(iter_num, max_iterations)) * math.log(2)        # :185-186
+    mask = (uncertainty < threshold).float()                                                  # :187
+    cons = (mask * dist).sum() / (2 * mask.sum() + 1e-16)                                     # :188-189
+    return supervised + cw * cons, supervised, cons, mask, cw, threshold                      # :191
+
+
 def sgd_step(params, grads, moms, lr, momentum=0.9, weight_decay=1e-4):
     """optim.SGD(lr, momentum=0.9, weight_decay=1e-4).step(), train_weakly_supervised_pCE_2D.py:79-80,104.
     torch semantics: g += wd*w; first step buf = g, afterwards buf = mu*buf + g; w -= lr*buf.

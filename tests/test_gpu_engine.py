@@ -76,6 +76,76 @@ def test_step_matches_oracle(variant, cct):
     print(f"[{variant} cct={cct}] loss {loss.item():.5f} (oracle {ref_loss.item():.5f}), worst update cosine {worst:.4f}")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_uamt_step_matches_oracle(precision):
+    """BASELINE config 5 (train_uncertainty_aware_mean_teacher_2D.py:138-197): student on labelled + unlabelled halves,
+    never-updated teacher with T = 8 noisy passes, uncertainty-masked consistency.  Noise and dropout masks injected."""
+    from wsl4mis_b200.engine import UAMTStep
+    B, hw = 2, 32
+    torch.manual_seed(21)
+    student, teacher = UNet(1, 4), UNet(1, 4)
+    ps = {k: v.clone() for k, v in student.state_dict().items()}
+    pt = {k: v.clone() for k, v in teacher.state_dict().items()}
+    student, teacher = student.to(DEV).set_precision(precision), teacher.to(DEV).set_precision(precision)
+    ones = [torch.ones(B, O.FT[i], hw >> i, hw >> i, dtype=torch.uint8) for i in range(5)]
+    for m in (student, teacher):
+        m.dropout_masks = {i: e.permute(0, 2, 3, 1).contiguous().to(DEV) for i, e in enumerate(ones)}
+    om = {k: e for k, e in zip(ENC_MASK_KEYS, ones)}
+    om2 = {k: e.repeat(2, 1, 1, 1) for k, e in om.items()}
+    g = torch.Generator().manual_seed(5)
+    img_l, img_u = torch.rand(B, 1, hw, hw, generator=g), torch.rand(B, 1, hw, hw, generator=g)
+    lab_l = torch.randint(0, 4, (B, hw, hw), generator=g, dtype=torch.uint8)
+    noises = [torch.clamp(torch.randn(B, 1, hw, hw, generator=g) * 0.1, -0.2, 0.2)] + \
+             [torch.clamp(torch.randn(2 * B, 1, hw, hw, generator=g) * 0.1, -0.2, 0.2) for _ in range(4)]
+    step = UAMTStep(student, teacher, base_lr=0.01, max_iterations=30000)
+    step.iter_num = 900                       # non-trivial consistency weight / threshold
+    loss = step(img_l.to(DEV), lab_l.to(DEV), img_u.to(DEV), [n.to(DEV) for n in noises])
+    torch.cuda.synchronize()
+    # ---- oracle ----
+    if precision == "bf16":
+        O.QUANT = True
+    try:
+        leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in ps.items()}
+        out_l = O.unet_forward(leaves, img_l, True, om)
+        out_u = O.unet_forward(leaves, img_u, True, om)
+        with torch.no_grad():
+            ema_out = O.unet_forward(pt, img_u + noises[0], True, om)
+            mc = torch.cat([O.unet_forward(pt, img_u.repeat(2, 1, 1, 1) + noises[1 + i], True, om2) for i in range(4)], 0)
+        ref_loss, sup, cons, mask, cw, thr = O.uamt_losses(out_l, out_u, ema_out, mc, lab_l, 900, 30000)
+        names = [k for k, v in leaves.items() if v.requires_grad]
+        grads = dict(zip(names, torch.autograd.grad(ref_loss, [leaves[k] for k in names], allow_unused=True)))
+    finally:
+        O.QUANT = None
+    tol = 1e-4 if precision == "fp32" else 0.03
+    assert abs(step.parts["weight"] - cw) < 1e-9 and abs(step.parts["threshold"] - thr) < 1e-9
+    assert abs(loss.item() - ref_loss.item()) < tol * abs(ref_loss.item()) + 1e-5, (loss.item(), ref_loss.item())
+    agree = (step.parts["mask"].cpu().float() == mask[:, 0]).float().mean().item()
+    assert agree > (0.9999 if precision == "fp32" else 0.97), agree
+    named = dict(student.named_parameters())
+    worst = 1.0
+    for k, gr in grads.items():
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue
+        delta = named[k].detach().cpu() - ps[k]
+        ref_delta = -0.01 * (gr + 1e-4 * ps[k])
+        c = cosine(delta, ref_delta)
+        worst = min(worst, c)
+        assert c > (0.9999 if precision == "fp32" else 0.85), (k, c)
+    print(f"[uamt {precision}] loss {loss.item():.6f} (oracle {ref_loss.item():.6f}), mask agreement {agree:.4f}, worst update cosine {worst:.5f}")
+
+
+def test_clamped_noise_kernel_statistics():
+    from wsl4mis_b200._lib import call
+    x = torch.zeros(1 << 20, device=DEV)
+    out = torch.empty(2 << 20, device=DEV)
+    call("wsl_add_clamped_noise", x, x.numel(), 2, 0.1, 0.2, 7, None, out)
+    torch.cuda.synchronize()
+    o = out.cpu()
+    assert o.abs().max().item() <= 0.2 + 1e-6 and abs(o.mean().item()) < 1e-3
+    assert abs(o.std().item() - 0.0954) < 3e-3          # std of N(0, 0.1) clamped at 2 sigma
+    assert not torch.equal(o[: 1 << 20], o[1 << 20:])   # the repeated copies draw different noise
+
+
 def test_graph_replay_equals_eager():
     n, hw = 4, 64
     img, lab = O.synth_batch(n, hw, hw, seed=5, frac=0.05)

@@ -314,7 +314,7 @@ def test_bn_backward_chain(shape):
     dgam, dbet, coef = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2 * C, device=DEV)
     dy = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
     call("wsl_bn_bwd", yd, 0, ss, save, nhwc(g0).to(DEV), nhwc(g1).to(DEV), cs.to(DEV), nhwc(gp).to(DEV), pidx, mk, 0, None, p,
-         0.01, N, H, W, C, dgam, dbet, coef, dy, workspace("bn"))
+         0.01, N, H, W, C, dgam, dbet, coef, dy, workspace("bn"), 0)
     torch.cuda.synchronize()
     assert rel_l2(dgam.cpu(), dgr.float()) < 1e-4
     assert rel_l2(dbet.cpu(), dbr.float()) < 1e-4

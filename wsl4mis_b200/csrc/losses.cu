@@ -503,6 +503,119 @@ __global__ void __launch_bounds__(TPB) tv_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K13: uncertainty-aware mean-teacher consistency (train_uncertainty_aware_mean_teacher_2D.py:164-188):
+//   p_bar  = mean_t softmax(mc_logits[t])                         (T stochastic teacher passes, :164-174)
+//   unc    = -sum_c p_bar log(p_bar + 1e-6)                       (:175-176)
+//   mask   = unc < threshold                                      (:184-186)
+//   dist_c = (softmax(student)_c - softmax(teacher)_c)^2          (utils/losses.py:65-82, softmax_mse_loss)
+//   loss   = sum(mask * dist) / (2 * sum(mask) + 1e-16)           (:187-188)
+// mc_logits is the [T*B,4,H,W] buffer the script fills with T/2 teacher calls on the twice-repeated batch:
+// row (2*B*i + r) holds pass t = 2i + r/B of sample r % B.
+// fwd: one pass, emits the mask (u8) and {sum masked dist, mask count, loss}; bwd: d loss/d student logits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax4(const float (&x)[C4], float (&p)[C4]) {
+  const float m = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C4; ++c) { p[c] = expf(x[c] - m); s += p[c]; }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int c = 0; c < C4; ++c) p[c] *= inv;
+}
+
+__global__ void __launch_bounds__(TPB) uamt_consistency_fwd_kernel(
+    const float* __restrict__ student, const float* __restrict__ teacher, const float* __restrict__ mc, int T, int B, int HW,
+    const float* __restrict__ threshold_ptr, float threshold, uint8_t* __restrict__ mask, float* partials, unsigned* ticket,
+    float* out /*[3]: sum, count, loss*/) {
+  const float thr = threshold_ptr ? *threshold_ptr : threshold;
+  float acc[2] = {0.f, 0.f};
+  const long long npix = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
+    const long long b = i / HW, o = i - b * HW;
+    float pbar[C4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < T; ++t) {
+      const long long row = (long long)(t >> 1) * 2 * B + (long long)(t & 1) * B + b;
+      float x[C4], p[C4];
+#pragma unroll
+      for (int c = 0; c < C4; ++c) x[c] = mc[(row * C4 + c) * HW + o];
+      softmax4(x, p);
+#pragma unroll
+      for (int c = 0; c < C4; ++c) pbar[c] += p[c];
+    }
+    float unc = 0.f;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      const float q = pbar[c] / (float)T;
+      unc -= q * logf(q + 1e-6f);
+    }
+    const bool on = unc < thr;
+    mask[i] = on ? 1 : 0;
+    if (on) {
+      float xs[C4], xt[C4], ps[C4], pt[C4];
+#pragma unroll
+      for (int c = 0; c < C4; ++c) { xs[c] = student[(b * C4 + c) * HW + o]; xt[c] = teacher[(b * C4 + c) * HW + o]; }
+      softmax4(xs, ps);
+      softmax4(xt, pt);
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < C4; ++c) d += (ps[c] - pt[c]) * (ps[c] - pt[c]);
+      acc[0] += d;
+      acc[1] += 1.f;
+    }
+  }
+  __shared__ double res[2];
+  if (block_reduce_final<2, TPB>(acc, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      out[0] = (float)res[0];
+      out[1] = (float)res[1];
+      out[2] = (float)(res[0] / (2.0 * res[1] + 1e-16));
+    }
+  }
+}
+
+// d (w * loss) / d student logits = softmax-Jacobian applied to g_c = w * 2 * mask * (ps_c - pt_c) / (2*count + 1e-16)
+__global__ void __launch_bounds__(TPB) uamt_consistency_bwd_kernel(
+    const float* __restrict__ student, const float* __restrict__ teacher, const uint8_t* __restrict__ mask,
+    const float* __restrict__ stats, const float* __restrict__ weight_ptr, float weight, int B, int HW,
+    float* __restrict__ dlogits) {
+  const float w = (weight_ptr ? *weight_ptr : weight) * 2.f / (2.f * stats[1] + 1e-16f);
+  const long long npix = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
+    const long long b = i / HW, o = i - b * HW;
+    float d[C4] = {0.f, 0.f, 0.f, 0.f};
+    if (mask[i]) {
+      float xs[C4], xt[C4], ps[C4], pt[C4], g[C4];
+#pragma unroll
+      for (int c = 0; c < C4; ++c) { xs[c] = student[(b * C4 + c) * HW + o]; xt[c] = teacher[(b * C4 + c) * HW + o]; }
+      softmax4(xs, ps);
+      softmax4(xt, pt);
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C4; ++c) { g[c] = w * (ps[c] - pt[c]); dot += g[c] * ps[c]; }
+#pragma unroll
+      for (int c = 0; c < C4; ++c) d[c] = ps[c] * (g[c] - dot);
+    }
+#pragma unroll
+    for (int c = 0; c < C4; ++c) dlogits[(b * C4 + c) * HW + o] = d[c];
+  }
+}
+
+// x + clamp(sigma * N(0,1), -c, c): torch.clamp(torch.randn_like(x) * 0.1, -0.2, 0.2) + x (:147-149,167-169) with the
+// counter RNG (Box-Muller); `reps` stacks the batch (x.repeat(reps,1,1,1)).
+__global__ void __launch_bounds__(TPB) add_clamped_noise_kernel(const float* __restrict__ x, long long n, int reps, float sigma,
+                                                                float clampv, unsigned long long seed,
+                                                                const unsigned long long* seed_ptr, float* __restrict__ out) {
+  if (seed_ptr) seed += *seed_ptr;
+  const long long total = n * reps;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const float u1 = fmaxf(wsl_uniform(seed, (unsigned long long)(2 * i)), 1e-7f);
+    const float u2 = wsl_uniform(seed, (unsigned long long)(2 * i + 1));
+    const float z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    out[i] = x[i % n] + fminf(fmaxf(z * sigma, -clampv), clampv);
+  }
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -616,4 +729,30 @@ WSL_API int wsl_tv_loss(const float* probs, int planes, int H, int W, float grad
   tv_kernel<<<grid_for(total, TPB), TPB, 0, stream>>>(probs, planes, H, W, grad_scale / (float)total, gprobs_zeroed,
                                                       ws + 64, reinterpret_cast<unsigned*>(ws), out1);
   return wsl_check_launch("tv_loss");
+}
+
+WSL_API int wsl_uamt_consistency_fwd(const float* student, const float* teacher, const float* mc_logits, int T, int B, int C,
+                                     int H, int W, const float* threshold_ptr, float threshold, uint8_t* mask, float* out3,
+                                     float* ws, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4 && T >= 2 && T % 2 == 0, "wsl_uamt_consistency_fwd: C must be 4 and T even (got C=%d, T=%d)", C, T);
+  const long long npix = (long long)B * H * W;
+  uamt_consistency_fwd_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(student, teacher, mc_logits, T, B, H * W, threshold_ptr,
+                                                                       threshold, mask, ws + 64, reinterpret_cast<unsigned*>(ws), out3);
+  return wsl_check_launch("uamt_consistency_fwd");
+}
+
+WSL_API int wsl_uamt_consistency_bwd(const float* student, const float* teacher, const uint8_t* mask, const float* stats3,
+                                     const float* weight_ptr, float weight, int B, int C, int H, int W, float* dlogits,
+                                     cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_uamt_consistency_bwd: C must be 4 (got %d)", C);
+  const long long npix = (long long)B * H * W;
+  uamt_consistency_bwd_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(student, teacher, mask, stats3, weight_ptr, weight, B,
+                                                                       H * W, dlogits);
+  return wsl_check_launch("uamt_consistency_bwd");
+}
+
+WSL_API int wsl_add_clamped_noise(const float* x, long long n, int reps, float sigma, float clamp, unsigned long long seed,
+                                  const unsigned long long* seed_ptr, float* out, cudaStream_t stream) {
+  add_clamped_noise_kernel<<<grid_for(n * reps, TPB), TPB, 0, stream>>>(x, n, reps, sigma, clamp, seed, seed_ptr, out);
+  return wsl_check_launch("add_clamped_noise");
 }

@@ -633,7 +633,7 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs<T>& a, const BnBwdThr
 template <typename T>
 __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
-                                                               float* partials, unsigned* ticket) {
+                                                               float* partials, unsigned* ticket, int accumulate) {
   extern __shared__ float s_red[];
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, cg = t.cg, rows = TPB / cg;
@@ -673,8 +673,8 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, f
   bn_finalize_partials(partials, gridDim.x, C, s_fin, s_part);
   for (int c = threadIdx.x; c < C; c += TPB) {
     const double x = s_fin[c], y = s_fin[C + c];
-    dbeta[c] = (float)x;
-    dgamma[c] = (float)y;
+    dbeta[c] = accumulate ? dbeta[c] + (float)x : (float)x;      // accumulate: second backward through shared weights
+    dgamma[c] = accumulate ? dgamma[c] + (float)y : (float)y;
     // apply-pass constants: dY = dz*A + y*B + D with A = scale, B = -scale*c2*invstd, D = -scale*c1 + scale*c2*mean*invstd
     const double c1 = x / (double)P, c2 = y / (double)P;
     const double sc = (double)a.ss[c], istd = (double)a.save[C + c], mean = (double)a.save[c];
@@ -1008,14 +1008,14 @@ template <typename T>
 static int bn_bwd_launch(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
                          const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                          const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma,
-                         float* dbeta, float* coef, void* dy, float* ws, cudaStream_t stream) {
+                         float* dbeta, float* coef, void* dy, float* ws, int accumulate, cudaStream_t stream) {
   BnBwdArgs<T> a;
   a.y = (const T*)y; a.ss = ss; a.save = save; a.g0 = (const T*)g0; a.g1 = (const T*)g1;
   a.cs1 = cs1; a.gp = (const T*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
   a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
   const long long P = (long long)N * H * W;
   const int grid = bn_grid(P, C);
-  bn_bwd_reduce_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws));
+  bn_bwd_reduce_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws), accumulate);
   int rc = wsl_check_launch("bn_bwd_reduce");
   if (rc) return rc;
   bn_bwd_apply_kernel<T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
@@ -1024,14 +1024,14 @@ static int bn_bwd_launch(const void* y, const float* ss, const float* save, cons
 
 WSL_API int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
                        const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
-                       const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws,
+                       const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws, int accumulate,
                        cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_bwd: unsupported channel count %d", C);
   const long long P = (long long)N * H * W;
   WSL_REQUIRE((long long)bn_grid(P, C) * 2 * C + 64 <= WSL_WS_FLOATS && P < (1LL << 31), "wsl_bn_bwd: workspace too small / too many pixels");
   if (dtype == 1)
-    return bn_bwd_launch<float>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, stream);
-  return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, stream);
+    return bn_bwd_launch<float>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
+  return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
 }
 
 WSL_API int wsl_upsample2x_fwd(const void* t, int dtype, int N, int h, int w, int C, void* u, cudaStream_t stream) {

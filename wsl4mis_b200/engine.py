@@ -238,3 +238,97 @@ class TrainStep:
     @property
     def outputs(self):
         return self._outs
+
+
+class UAMTStep:
+    """Per-step body of train_uncertainty_aware_mean_teacher_2D.py:138-197 (BASELINE config 5) on the fused kernels.
+
+    Batch = labelled half + unlabelled half.  Student: two training forwards with gradient (labelled, unlabelled);
+    teacher (`ema_model`, never updated and never put in eval mode by the reference): one no-grad forward on the
+    noisy unlabelled inputs and T/2 = 4 no-grad forwards on the twice-repeated noisy batch (T = 8 stochastic passes).
+    Loss = 0.5*(Dice + CE) on the labelled half + w(t) * uncertainty-masked softmax-MSE consistency (K13 kernels).
+    Two-head models (unet_cct) use main_seg on both sides."""
+
+    def __init__(self, model, ema_model, base_lr=0.01, max_iterations=30000, consistency=0.1, consistency_rampup=200.0,
+                 momentum=0.9, weight_decay=1e-4, T=8):
+        from .utils import ramps
+        self.ramps = ramps
+        self.model, self.ema_model = model, ema_model
+        self.ex, self.ex_t = model.executor, ema_model.executor
+        self.base_lr, self.max_iterations = float(base_lr), int(max_iterations)
+        self.consistency, self.consistency_rampup = float(consistency), float(consistency_rampup)
+        self.momentum, self.weight_decay, self.T = float(momentum), float(weight_decay), int(T)
+        self.iter_num = 0
+        dev = next(model.parameters()).device
+        self.dev = dev
+        params = self.ex.params
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        first_aux = next(model.aux_decoder1.parameters()) if len(self.ex.dec) == 2 else None
+        self.n_trained = n if first_aux is None else sum(p.numel() for p in params[: [id(q) for q in params].index(id(first_aux))])
+        self.mom = torch.zeros_like(self.flat)
+        self.lr_dev = torch.full((1,), self.base_lr, dtype=torch.float32, device=dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def _noisy(self, x, reps, salt, given):
+        if given is not None:
+            return (x.repeat(reps, 1, 1, 1) + given).contiguous()
+        out = torch.empty((x.shape[0] * reps,) + tuple(x.shape[1:]), dtype=torch.float32, device=self.dev)
+        call("wsl_add_clamped_noise", x, x.numel(), reps, 0.1, 0.2, 0xA5A5 + salt, self.seed_dev, out)
+        return out
+
+    def __call__(self, image_l, label_l, image_u, noises=None):
+        """image_l/image_u: fp32 [B,1,H,W]; label_l: uint8 [B,H,W] dense.  noises (tests): list of 1 + T/2 tensors holding
+        the already-clamped noise of :147-149 and :167-169.  Returns the loss (0-dim device tensor)."""
+        ex, ex_t, dev = self.ex, self.ex_t, self.dev
+        self.model.train()
+        self.ema_model.train()
+        B, _, H, W = image_u.shape
+        C, T = 4, self.T
+        self.seed_dev.add_(1)
+        masks, ck = getattr(self.model, "dropout_masks", None), getattr(self.model, "channel_keep", None)
+        tmasks, tck = getattr(self.ema_model, "dropout_masks", None), getattr(self.ema_model, "channel_keep", None)
+        outs_l, slot_l = ex.forward(image_l.contiguous(), True, True, masks, ck)
+        outs_u, slot_u = ex.forward(image_u.contiguous(), True, True, masks, ck)
+        out_l, out_u = outs_l[0], outs_u[0]
+        ema_out = ex_t.forward(self._noisy(image_u, 1, 0, None if noises is None else noises[0]), True, False, tmasks, tck)[0][0]
+        mc = ex.buf("uamt", "mc", (T * B, C, H, W), torch.float32)
+        for i in range(T // 2):
+            tm2 = None if tmasks is None else {k: v.repeat(2, 1, 1, 1) for k, v in tmasks.items()}
+            tck2 = None if tck is None else [c.repeat(2, 1) for c in tck]
+            lg = ex_t.forward(self._noisy(image_u, 2, 1 + i, None if noises is None else noises[1 + i]), True, False, tm2, tck2)[0][0]
+            mc[2 * B * i: 2 * B * (i + 1)].copy_(lg)
+        Bf = lambda name, shape, dt=torch.float32: ex.buf("uamt", name, shape, dt)
+        # ---- supervised half: 0.5 * (Dice + CE), CE without ignore_index (:127,:178-180) ----
+        probs, st = Bf("probs_l", (B, C, H, W)), Bf("stats_l", (2,))
+        call("wsl_softmax_pce_fwd", out_l, label_l, probs, B, C, H, W, 255, st, workspace("pce", dev))
+        sums = Bf("dice", (13,))
+        call("wsl_pdice_fwd", probs, label_l, None, 1.0, B, C, H, W, sums, workspace("pdice", dev))
+        gp = Bf("gprobs_l", (B, C, H, W))
+        call("wsl_pdice_bwd", probs, label_l, None, 1.0, sums, B, C, H, W, 0.5, 0, gp)
+        dl_l = Bf("dl_l", (B, C, H, W))
+        call("wsl_head_bwd", probs, label_l, st, None, 0.5, gp, 1.0, B, C, H, W, 255, dl_l)
+        # ---- consistency half (:181-189) ----
+        cw = self.consistency * self.ramps.sigmoid_rampup(self.iter_num // 300, self.consistency_rampup)
+        import math
+        thr = (0.75 + 0.25 * self.ramps.sigmoid_rampup(self.iter_num, self.max_iterations)) * math.log(2)
+        mask, cst = Bf("mask", (B, H, W), torch.uint8), Bf("cons", (3,))
+        call("wsl_uamt_consistency_fwd", out_u, ema_out, mc, T, B, C, H, W, None, float(thr), mask, cst, workspace("uamt", dev))
+        dl_u = Bf("dl_u", (B, C, H, W))
+        call("wsl_uamt_consistency_bwd", out_u, ema_out, mask, cst, None, float(cw), B, C, H, W, dl_u)
+        loss = 0.5 * (sums[0] + st[0]) + cw * cst[2]
+        self.parts = {"supervised": 0.5 * (sums[0] + st[0]), "consistency": cst[2], "weight": cw, "threshold": thr, "mask": mask}
+        # ---- two backward passes through the shared student weights, gradients accumulated in the flat bucket ----
+        nd = len(ex.dec)
+        ex.backward(slot_u, [dl_u] + [None] * (nd - 1), zero_grads=True)
+        g = ex.backward(slot_l, [dl_l] + [None] * (nd - 1), zero_grads=False)
+        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay, 1.0)
+        lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
+        self.lr_dev.fill_(lr_)
+        self.iter_num += 1
+        return loss

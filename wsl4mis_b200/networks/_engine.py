@@ -142,6 +142,7 @@ class UNetExecutor:
         self._side_dirty = False
         self._stat_bufs = {}
         self._stat_rows = ctypes.c_int(0)
+        self._accumulate = False
         self.stats = {"launches": 0}
 
     # ---------------------------------------------------------------- buffers
@@ -337,7 +338,7 @@ class UNetExecutor:
         p = L.drop_p
         call("wsl_bn_bwd", y, self.dt, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
              self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
-             self.gview(bn.bias), coef, dy, self._ws("bn"))
+             self.gview(bn.bias), coef, dy, self._ws("bn"), 1 if self._accumulate else 0)
 
     def _layer_seed(self, L):
         return (self.layers.index(L) + 1) * 0x9E3779B1
@@ -490,6 +491,7 @@ class UNetExecutor:
         gflat, _ = self.grads()
         if zero_grads:
             gflat.zero_()
+        self._accumulate = not zero_grads      # BN affine gradients are written (not added) unless accumulating
         B = lambda name, shape, dt=None: self.buf(slot, "g." + name, shape, dt)
 
         def block_bwd(tag, blk, r, g0, g1=None, cs1=None, gpool=None, need_dsrc=True):
