@@ -42,10 +42,12 @@ int wsl_softmax_pce_fwd(const float* logits, const uint8_t* label, float* probs,
                         int ignore_index, float* out2, float* ws, cudaStream_t stream);
 
 /* d(w_ce*pCE + <gprobs*gprobs_scale, softmax(logits)>)/dlogits, times *grad_out (NULL -> 1).
- * Replaces autograd through softmax / log_softmax+nll_loss.  label/gprobs may be NULL. */
+ * Replaces autograd through softmax / log_softmax+nll_loss.  label/gprobs may be NULL.  Either output may be NULL:
+ * dlogits = fp32 NCHW (API layout), dlogits_nhwc16_bf16 = channels-last bf16 padded to 16 channels (the layout the
+ * out_conv gradient kernels consume; saves a conversion pass in the fused step). */
 int wsl_head_bwd(const float* probs, const uint8_t* label, const float* ce_stats, const float* grad_out,
                  float w_ce, const float* gprobs, float gprobs_scale, int N, int C, int H, int W,
-                 int ignore_index, float* dlogits, cudaStream_t stream);
+                 int ignore_index, float* dlogits, void* dlogits_nhwc16_bf16, cudaStream_t stream);
 
 /* ModelLossSemsegGatedCRF.forward(y, [{'weight':w,'xy':sxy,'rgb':srgb}], radius, image, H, W)['loss']:
  * utils/gate_crf_loss.py:20-117 (fast path: no masks, Potts).  Also emits d loss / d y into gprobs (may be
@@ -61,9 +63,10 @@ int wsl_mumford_shah_bwd(const float* image, const float* probs, const float* ce
                          int W, float scale, int accumulate, float* gprobs, cudaStream_t stream);
 
 /* argmax(beta*p1 + (1-beta)*p2, dim=1): train_weakly_supervised_segmentation_pCE_ours_proposed.py:117-120.
- * p2 may be NULL (plain argmax). */
-int wsl_mix_argmax(const float* p1, const float* p2, float beta, float one_minus_beta, int N, int C, int H, int W,
-                   uint8_t* out, cudaStream_t stream);
+ * p2 may be NULL (plain argmax).  beta_ptr (optional, device {beta, 1-beta}) overrides the scalars so that a captured
+ * CUDA graph follows the script's per-step `random.random()` (:117). */
+int wsl_mix_argmax(const float* p1, const float* p2, float beta, float one_minus_beta, const float* beta_ptr, int N, int C,
+                   int H, int W, uint8_t* out, cudaStream_t stream);
 
 /* batch-summed ignore mask of pDLoss (utils/losses.py:219-220 + the [N,1,H,W] broadcast at :209-211). */
 int wsl_mask_count(const uint8_t* target, int N, int H, int W, int ignore_index, float* msum, cudaStream_t stream);

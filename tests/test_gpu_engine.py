@@ -166,6 +166,27 @@ def test_graph_replay_equals_eager():
     assert losses[True][-1] < losses[True][0]
 
 
+def test_dmpls_graph_follows_host_beta():
+    """DMPLS inside a captured graph: the per-step beta of Python's `random` reaches the kernels through device memory."""
+    import random
+    n, hw = 4, 64
+    img, lab = O.synth_batch(n, hw, hw, seed=5, frac=0.05)
+    img, lab = img.to(DEV), lab.to(DEV)
+    res = {}
+    for graph in (False, True):
+        torch.manual_seed(7)
+        random.seed(99)
+        m = UNet_CCT(1, 4).to(DEV)
+        step = TrainStep(m, "dmpls", graph=graph)
+        ls, betas = [], []
+        for _ in range(6):
+            ls.append(step(img, lab).item())
+            betas.append(step.beta)
+        res[graph] = (ls, betas)
+    assert res[False][1] == res[True][1] and len(set(res[True][1])) == 6
+    assert np.allclose(res[False][0], res[True][0], rtol=5e-3), res
+
+
 def test_lr_schedule_follows_the_script():
     torch.manual_seed(0)
     m = UNet(1, 4).to(DEV)

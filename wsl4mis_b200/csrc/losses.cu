@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TPB) softmax_pce_fwd_kernel(
 __global__ void __launch_bounds__(TPB) head_bwd_kernel(
     const float* __restrict__ probs, const uint8_t* __restrict__ label, const float* __restrict__ ce_stats,
     const float* __restrict__ go_ptr, float w_ce, const float* __restrict__ gprobs, float gs,
-    int HW, long long nquads, int ignore_index, float* __restrict__ dlogits) {
+    int HW, long long nquads, int ignore_index, float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_nhwc16) {
   const int qpi = HW >> 2;
   const float go = go_ptr ? *go_ptr : 1.0f;
   const float cew = (label != nullptr && w_ce != 0.f) ? w_ce * go / ce_stats[1] : 0.f;
@@ -120,8 +120,23 @@ __global__ void __launch_bounds__(TPB) head_bwd_kernel(
         d[c][j] = v;
       }
     }
+    if (dlogits != nullptr) {
 #pragma unroll
-    for (int c = 0; c < C4; ++c) st4(dlogits + off + (long long)c * HW, make_float4(d[c][0], d[c][1], d[c][2], d[c][3]));
+      for (int c = 0; c < C4; ++c) st4(dlogits + off + (long long)c * HW, make_float4(d[c][0], d[c][1], d[c][2], d[c][3]));
+    }
+    if (dl_nhwc16 != nullptr) {
+      // the executor's layout for the out_conv gradient: channels-last bf16, 4 real + 12 zero channels per pixel
+      uint4* o = reinterpret_cast<uint4*>(dl_nhwc16 + (n * (long long)HW + r * 4) * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack_bf16(d[0][j], d[1][j]);
+        v.y = pack_bf16(d[2][j], d[3][j]);
+        v.z = 0u; v.w = 0u;
+        o[2 * j] = v;
+        o[2 * j + 1] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
   }
 }
 
@@ -359,8 +374,9 @@ __global__ void __launch_bounds__(TPB) ms_bwd_kernel(
 // The rounding of the mix follows torch: two fp32 multiplies and one fp32 add, no FMA contraction.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) mix_argmax_kernel(
-    const float* __restrict__ p1, const float* __restrict__ p2, float beta, float omb, int HW, long long npix,
-    uint8_t* __restrict__ out) {
+    const float* __restrict__ p1, const float* __restrict__ p2, float beta, float omb, const float* __restrict__ beta_ptr,
+    int HW, long long npix, uint8_t* __restrict__ out) {
+  if (beta_ptr) { beta = beta_ptr[0]; omb = beta_ptr[1]; }     // device-side {beta, 1-beta}: graph replays follow the host RNG
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
     const long long n = i / HW, o = i - n * HW;
     const float* a = p1 + n * C4 * (long long)HW + o;
@@ -641,12 +657,12 @@ WSL_API int wsl_softmax_pce_fwd(const float* logits, const uint8_t* label, float
 
 WSL_API int wsl_head_bwd(const float* probs, const uint8_t* label, const float* ce_stats, const float* grad_out,
                          float w_ce, const float* gprobs, float gprobs_scale, int N, int C, int H, int W,
-                         int ignore_index, float* dlogits, cudaStream_t stream) {
+                         int ignore_index, float* dlogits, void* dlogits_nhwc16_bf16, cudaStream_t stream) {
   WSL_REQUIRE(C == C4, "wsl_head_bwd: C must be 4 (got %d)", C);
   WSL_REQUIRE(((long long)H * W) % 4 == 0, "wsl_head_bwd: H*W must be a multiple of 4");
   const long long nq = (long long)N * H * W / 4;
   head_bwd_kernel<<<grid_for(nq, TPB), TPB, 0, stream>>>(probs, label, ce_stats, grad_out, w_ce, gprobs, gprobs_scale,
-                                                         H * W, nq, ignore_index, dlogits);
+                                                         H * W, nq, ignore_index, dlogits, (__nv_bfloat16*)dlogits_nhwc16_bf16);
   return wsl_check_launch("head_bwd");
 }
 
@@ -692,11 +708,11 @@ WSL_API int wsl_mumford_shah_bwd(const float* image, const float* probs, const f
   return wsl_check_launch("mumford_shah_bwd");
 }
 
-WSL_API int wsl_mix_argmax(const float* p1, const float* p2, float beta, float one_minus_beta, int N, int C, int H, int W,
-                           uint8_t* out, cudaStream_t stream) {
+WSL_API int wsl_mix_argmax(const float* p1, const float* p2, float beta, float one_minus_beta, const float* beta_ptr, int N, int C,
+                           int H, int W, uint8_t* out, cudaStream_t stream) {
   WSL_REQUIRE(C == C4, "wsl_mix_argmax: C must be 4 (got %d)", C);
   const long long npix = (long long)N * H * W;
-  mix_argmax_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(p1, p2, beta, one_minus_beta, H * W, npix, out);
+  mix_argmax_kernel<<<grid_for(npix, TPB), TPB, 0, stream>>>(p1, p2, beta, one_minus_beta, beta_ptr, H * W, npix, out);
   return wsl_check_launch("mix_argmax");
 }
 

@@ -36,7 +36,7 @@ class TrainStep:
         self.ex = model.executor
         self.base_lr, self.max_iterations = float(base_lr), int(max_iterations)
         self.momentum, self.weight_decay = float(momentum), float(weight_decay)
-        self.graph_enabled = bool(graph) and variant != "dmpls"   # dmpls draws a host-side beta every step
+        self.graph_enabled = bool(graph)
         self.world_size = int(world_size)
         self.pg = process_group
         self.iter_num = 0
@@ -60,6 +60,8 @@ class TrainStep:
             ddp.broadcast_flat(self.flat, 0, self.pg)     # identical replicas (DDP does the same at construction)
         self.mom = torch.zeros_like(self.flat)
         self.lr_dev = torch.full((1,), self.base_lr, dtype=torch.float32, device=dev)
+        self.beta_dev = torch.tensor([0.5, 0.5], dtype=torch.float32, device=dev)
+        self.beta = 0.5
         self.two_heads = len(self.ex.dec) == 2
         self.n_heads_trained = 2 if (variant == "dmpls") else 1
         if variant == "dmpls":
@@ -75,6 +77,16 @@ class TrainStep:
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------
+    @staticmethod
+    def _dlogits(ex, slot, name, N, C, H, W):
+        """(fp32 NCHW buffer or None, bf16 NHWC-16 buffer or None, what backward() receives): in bf16 mode the head
+        writes the out_conv gradient directly in the executor's layout (no conversion pass)."""
+        if ex.dt == 0:
+            d16 = ex.buf(slot, "head." + name + ".nhwc16", (N, H, W, 16), torch.bfloat16)
+            return None, d16, ("nhwc16", d16)
+        d = ex.buf(slot, "head." + name, (N, C, H, W), torch.float32)
+        return d, None, d
+
     def _head(self, logits_list, image, label, slot):
         """loss head: returns (loss tensor, [dlogits per decoder or None])."""
         ex = self.ex
@@ -94,17 +106,15 @@ class TrainStep:
         ce = stats[0][0]
         if v == "pce":
             loss = ce
-            d = B("dl0", (N, C, H, W))
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, None, 0.0, N, C, H, W, 4, d)
-            dl[0] = d
+            d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, None, 0.0, N, C, H, W, 4, d, d16)
         elif v == "pce_gatedcrf":
             gp = B("gprobs0", (N, C, H, W))
             out = B("crf", (2,))
             call("wsl_gatedcrf_fwd", probs[0], image, gp, N, C, H, W, 5, 6.0, 0.1, 1.0, out, workspace("crf", dev))
             loss = ce + 0.1 * out[0]
-            d = B("dl0", (N, C, H, W))
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 0.1, N, C, H, W, 4, d)
-            dl[0] = d
+            d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 0.1, N, C, H, W, 4, d, d16)
             self.loss_parts = {"ce": ce, "crf": out[0]}
         elif v == "pce_ms":
             gp = B("gprobs0", (N, C, H, W))
@@ -113,9 +123,8 @@ class TrainStep:
             call("wsl_mumford_shah_fwd", image, probs[0], N, C, H, W, out, cent, workspace("ms", dev))
             call("wsl_mumford_shah_bwd", image, probs[0], cent, N, C, H, W, 1e-6, 0, gp)
             loss = ce + 1e-6 * out[0]
-            d = B("dl0", (N, C, H, W))
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d)
-            dl[0] = d
+            d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
         elif v == "pce_tv":
             # tv_loss(outputs_soft[1:]) -- batch slice, sample 0 gets no TV term
             gp = B("gprobs0", (N, C, H, W))
@@ -126,13 +135,11 @@ class TrainStep:
                 loss = ce + 1e-2 * out[0]
             else:
                 loss = ce   # mean over an empty tensor is NaN in the reference; N=1 is never used with this script
-            d = B("dl0", (N, C, H, W))
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d)
-            dl[0] = d
+            d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
         else:  # dmpls
-            beta = random.random() + 1e-10            # host RNG, as the script (:117)
             pseudo = B("pseudo", (N, H, W), torch.uint8)
-            call("wsl_mix_argmax", probs[0], probs[1], beta, 1.0 - beta, N, C, H, W, pseudo)
+            call("wsl_mix_argmax", probs[0], probs[1], 0.0, 0.0, self.beta_dev, N, C, H, W, pseudo)   # beta from device memory
             loss = 0.5 * (stats[0][0] + stats[1][0])
             for h in heads:
                 sums = B(f"pd{h}", (13,))
@@ -140,10 +147,8 @@ class TrainStep:
                 gp = B(f"gprobs{h}", (N, C, H, W))
                 call("wsl_pdice_bwd", probs[h], pseudo, None, float(N), sums, N, C, H, W, 0.25, 0, gp)
                 loss = loss + 0.25 * sums[0]
-                d = B(f"dl{h}", (N, C, H, W))
-                call("wsl_head_bwd", probs[h], label, stats[h], None, 0.5, gp, 1.0, N, C, H, W, 4, d)
-                dl[h] = d
-            self.beta = beta
+                d, d16, dl[h] = self._dlogits(ex, slot, f"dl{h}", N, C, H, W)
+                call("wsl_head_bwd", probs[h], label, stats[h], None, 0.5, gp, 1.0, N, C, H, W, 4, d, d16)
         return loss, dl
 
     def _fwd_bwd(self, image, label):
@@ -178,6 +183,11 @@ class TrainStep:
         (bench.py's end-to-end leg does).  Tensors that are not one of those buffers are copied into set 0."""
         assert image.is_cuda and label.is_cuda and label.dtype == torch.uint8
         self.model.train()
+        if self.variant == "dmpls":
+            # beta = random.random() + 1e-10 from Python's host RNG, as the script (:117); handed to the kernels through
+            # device memory so the captured graph sees a fresh value every replay
+            self.beta = random.random() + 1e-10
+            self.beta_dev.copy_(torch.tensor([self.beta, 1.0 - self.beta], dtype=torch.float32), non_blocking=False)
         if not self.graph_enabled:
             loss, g = self._fwd_bwd(image, label)
             self._allreduce(g)
@@ -312,7 +322,7 @@ class UAMTStep:
         gp = Bf("gprobs_l", (B, C, H, W))
         call("wsl_pdice_bwd", probs, label_l, None, 1.0, sums, B, C, H, W, 0.5, 0, gp)
         dl_l = Bf("dl_l", (B, C, H, W))
-        call("wsl_head_bwd", probs, label_l, st, None, 0.5, gp, 1.0, B, C, H, W, 255, dl_l)
+        call("wsl_head_bwd", probs, label_l, st, None, 0.5, gp, 1.0, B, C, H, W, 255, dl_l, None)
         # ---- consistency half (:181-189) ----
         cw = self.consistency * self.ramps.sigmoid_rampup(self.iter_num // 300, self.consistency_rampup)
         import math

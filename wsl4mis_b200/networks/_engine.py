@@ -525,9 +525,12 @@ class UNetExecutor:
             drec = rec["dec"][di]
             if g is None:
                 continue
-            g = g.contiguous()
-            dl = B(f"dec{di}.dl", (N, H, W, 16))
-            call("wsl_nchw_f32_to_nhwc", g, N, self.n_class, H, W, 16, dl, self.dt)
+            if isinstance(g, tuple):                      # ("nhwc16", tensor): already in the executor's layout
+                dl = g[1]
+            else:
+                g = g.contiguous()
+                dl = B(f"dec{di}.dl", (N, H, W, 16))
+                call("wsl_nchw_f32_to_nhwc", g, N, self.n_class, H, W, 16, dl, self.dt)
             with self.on_side():
                 self.conv_wgrad(oc, [drec["xlast"]], dl, N, H, W)
             da = B(f"dec{di}.dlast", (N, H, W, ft[0]))
