@@ -1,13 +1,16 @@
-"""net_factory with the reference's signature and behaviour (networks/net_factory.py:6-22): returns a CUDA
-module for the accelerated model names, ``None`` for unknown names."""
+"""Model factory with the reference's call signature ``net_factory(net_type, in_chns, class_num)`` and its
+behaviour at the edges (networks/net_factory.py:6-22): the model is returned already on the GPU, an unknown name yields
+``None``.  Only the two architectures of the accelerated hot path are constructible here."""
 from .unet import UNet, UNet_CCT
+
+_ACCELERATED = {"unet": UNet, "unet_cct": UNet_CCT}
+_KNOWN_BUT_OFF_PATH = ("unet_cct_3h", "unet_ds", "efficient_unet", "pnet")
 
 
 def net_factory(net_type="unet", in_chns=1, class_num=3):
-    if net_type == "unet":
-        return UNet(in_chns=in_chns, class_num=class_num).cuda()
-    if net_type == "unet_cct":
-        return UNet_CCT(in_chns=in_chns, class_num=class_num).cuda()
-    if net_type in ("unet_cct_3h", "unet_ds", "efficient_unet", "pnet"):
-        raise NotImplementedError(f"net_type '{net_type}' is outside the accelerated hot path (unet, unet_cct)")
+    ctor = _ACCELERATED.get(net_type)
+    if ctor is not None:
+        return ctor(in_chns=in_chns, class_num=class_num).cuda()
+    if net_type in _KNOWN_BUT_OFF_PATH:
+        raise NotImplementedError(f"net_type '{net_type}' is outside the accelerated hot path ({', '.join(_ACCELERATED)})")
     return None
