@@ -97,6 +97,13 @@ int wsl_uamt_consistency_bwd(const float* student, const float* teacher, const u
 int wsl_add_clamped_noise(const float* x, long long n, int reps, float sigma, float clamp, unsigned long long seed,
                           const unsigned long long* seed_ptr, float* out, cudaStream_t stream);
 
+/* Validation path (val_2D.py:18-50): scipy.ndimage.zoom(order=0) semantics on S slices ([S,h,w] -> [S,H,W], fp32 images
+ * or uint8 label maps, including SciPy's cval=0 read when rounding pushes the last coordinate past in-1) and per-class
+ * overlap counts {|P&G|, |P|, |G|} (index c*3+k, classes 1..classes-1) for medpy-style Dice. */
+int wsl_zoom_nearest(const void* src, int is_u8, int S, int h, int w, int H, int W, void* dst, cudaStream_t stream);
+int wsl_overlap_counts(const uint8_t* pred, const uint8_t* gt, long long n, int classes, unsigned long long* counts_zeroed,
+                       cudaStream_t stream);
+
 /* ---- network operators (networks/unet.py) ---------------------------------------------------------------- */
 
 /* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the

@@ -632,6 +632,51 @@ __global__ void __launch_bounds__(TPB) add_clamped_noise_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Validation path (val_2D.py:18-50): scipy.ndimage.zoom(order=0) of every slice to the
+// network size and of the label map back, and per-class overlap counts for Dice, on the GPU for a whole volume.
+// zoom(order=0) as SciPy computes it: coordinate cc = o * (in-1)/(out-1) in double, index floor(cc + 0.5),
+// and -- mode='constant' -- a coordinate that rounding pushes past in-1 reads cval = 0 (this does happen for the
+// last row/column of some sizes; reproduced because the reference's predictions contain it).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int zoom0_index(int o, int n_in, int n_out, bool& oob) {
+  const double scale = (n_out > 1) ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
+  const double cc = (double)o * scale;
+  oob = (cc < 0.0) || (cc > (double)(n_in - 1));
+  int i = (int)floor(cc + 0.5);
+  return i < 0 ? 0 : (i > n_in - 1 ? n_in - 1 : i);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) zoom_nearest_kernel(const T* __restrict__ src, int S, int h, int w, int H, int W,
+                                                           T* __restrict__ dst) {
+  const long long total = (long long)S * H * W;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long long s = i / ((long long)W * H);
+    bool oy, ox;
+    const int iy = zoom0_index(y, h, H, oy), ix = zoom0_index(x, w, W, ox);
+    dst[i] = (oy || ox) ? (T)0 : src[(s * h + iy) * w + ix];
+  }
+}
+
+// counts[c] = {|pred==c & gt==c|, |pred==c|, |gt==c|} for c = 1..classes-1 (medpy.metric.binary.dc inputs)
+__global__ void __launch_bounds__(TPB) overlap_counts_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
+                                                             long long n, int classes, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int s_c[16 * 3];
+  for (int i = threadIdx.x; i < 48; i += TPB) s_c[i] = 0;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    const int p = pred[i], g = gt[i];
+    if (p > 0 && p < classes) atomicAdd(&s_c[p * 3 + 1], 1u);
+    if (g > 0 && g < classes) atomicAdd(&s_c[g * 3 + 2], 1u);
+    if (p == g && p > 0 && p < classes) atomicAdd(&s_c[p * 3 + 0], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < classes * 3; i += TPB)
+    if (s_c[i]) atomicAdd(&counts[i], (unsigned long long)s_c[i]);
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -771,4 +816,18 @@ WSL_API int wsl_add_clamped_noise(const float* x, long long n, int reps, float s
                                   const unsigned long long* seed_ptr, float* out, cudaStream_t stream) {
   add_clamped_noise_kernel<<<grid_for(n * reps, TPB), TPB, 0, stream>>>(x, n, reps, sigma, clamp, seed, seed_ptr, out);
   return wsl_check_launch("add_clamped_noise");
+}
+
+WSL_API int wsl_zoom_nearest(const void* src, int is_u8, int S, int h, int w, int H, int W, void* dst, cudaStream_t stream) {
+  const long long total = (long long)S * H * W;
+  if (is_u8) zoom_nearest_kernel<uint8_t><<<grid_for(total, TPB), TPB, 0, stream>>>((const uint8_t*)src, S, h, w, H, W, (uint8_t*)dst);
+  else zoom_nearest_kernel<float><<<grid_for(total, TPB), TPB, 0, stream>>>((const float*)src, S, h, w, H, W, (float*)dst);
+  return wsl_check_launch("zoom_nearest");
+}
+
+WSL_API int wsl_overlap_counts(const uint8_t* pred, const uint8_t* gt, long long n, int classes, unsigned long long* counts_zeroed,
+                               cudaStream_t stream) {
+  WSL_REQUIRE(classes >= 2 && classes <= 16, "wsl_overlap_counts: 2..16 classes (got %d)", classes);
+  overlap_counts_kernel<<<grid_for(n, TPB * 4), TPB, 0, stream>>>(pred, gt, n, classes, counts_zeroed);
+  return wsl_check_launch("overlap_counts");
 }
