@@ -83,6 +83,18 @@ int wsl_pdice_bwd(const float* probs, const uint8_t* target, const float* msum, 
 int wsl_tv_loss(const float* probs, int planes, int H, int W, float grad_scale, float* gprobs_zeroed, float* out1,
                 float* ws, cudaStream_t stream);
 
+/* losses.entropy_loss(p, C) (utils/losses.py:30-36; train_weakly_supervised_pCE_Entropy_Mini_2D.py:99-102) and its gradient
+ * (gprobs (+)= scale * d/dp). */
+int wsl_entropy_fwd(const float* probs, int N, int C, int H, int W, float* out1, float* ws, cudaStream_t stream);
+int wsl_entropy_bwd(const float* probs, int N, int C, int H, int W, float scale, int accumulate, float* gprobs,
+                    cudaStream_t stream);
+/* inter_class_variance - intra_class_variance (train_weakly_supervised_pCE_Inter&Intra_Class_2D.py:30-36,114).
+ * out3 = {inter - intra, inter, intra}; stats = [N*4*2 + N*2] scratch kept for the backward. */
+int wsl_class_variance_fwd(const float* image, const float* probs, int N, int C, int H, int W, float* out3, float* stats,
+                           float* ws, cudaStream_t stream);
+int wsl_class_variance_bwd(const float* image, const float* probs, const float* stats, int N, int C, int H, int W,
+                           float scale, int accumulate, float* gprobs, cudaStream_t stream);
+
 /* Uncertainty-aware mean-teacher consistency (train_uncertainty_aware_mean_teacher_2D.py:164-188): mean softmax of the T
  * stochastic teacher passes (mc_logits [T*B,4,H,W], script layout) -> entropy -> mask (u8 [B,H,W]) -> masked
  * softmax_mse_loss(student, teacher) (utils/losses.py:65-82) / (2*sum(mask)+1e-16).  out3 = {sum, count, loss}.

@@ -329,6 +329,20 @@ def entropy_minimization(prob):
     return (-(prob * torch.log(prob + 1e-6)).sum(1)).mean()
 
 
+def entropy_loss(prob, C=4):
+    """losses.entropy_loss, utils/losses.py:30-36 (as called at train_weakly_supervised_pCE_Entropy_Mini_2D.py:99)."""
+    return (-(prob * torch.log(prob + 1e-6)).sum(1) / math.log(C)).mean()
+
+
+def class_variance_loss(prob, img):
+    """inter_class_variance(prob, img) - intra_class_variance(prob, img),
+    train_weakly_supervised_pCE_Inter&Intra_Class_2D.py:30-36,114."""
+    v = img * prob
+    intra = torch.std(v, dim=[2, 3]).mean()
+    inter = torch.std(torch.mean(v, dim=[2, 3]), dim=1).mean()
+    return inter - intra
+
+
 def softmax_mse(a_logits, b_logits):
     """softmax_mse_loss (sigmoid=False), utils/losses.py:65-82."""
     return (F.softmax(a_logits, 1) - F.softmax(b_logits, 1)) ** 2
@@ -452,6 +466,11 @@ def full_step(p, image, label, variant="pce_gatedcrf", cct=False, masks=None, ch
         loss = step_loss_pce_tv(main, label)[0]
     elif variant == "dmpls":
         loss = step_loss_dmpls(main, aux, label, beta)[0]
+    elif variant == "pce_entropy":       # train_weakly_supervised_pCE_Entropy_Mini_2D.py:97-102
+        loss = pce_loss(main, label) + 0.1 * entropy_loss(torch.softmax(main, 1), 4)
+    elif variant.startswith("pce_variance"):   # ...Inter&Intra_Class_2D.py:112-118, weight passed as "pce_variance:<w>"
+        w = float(variant.split(":")[1]) if ":" in variant else 0.1
+        loss = pce_loss(main, label) + w * class_variance_loss(torch.softmax(main, 1), image)
     else:
         raise ValueError(variant)
     names = [k for k, v in leaves.items() if v.requires_grad]

@@ -33,13 +33,18 @@ def _setup(cct, n, hw, seed=3):
 
 
 @pytest.mark.parametrize("variant,cct", [("pce", False), ("pce_gatedcrf", False), ("pce_gatedcrf", True), ("pce_ms", False),
-                                         ("pce_tv", False), ("dmpls", True)])
+                                         ("pce_tv", False), ("dmpls", True), ("pce_entropy", False), ("pce_variance", False)])
 def test_step_matches_oracle(variant, cct):
     n, hw = 4, 64
     m, p, om, ock, image, label = _setup(cct, n, hw)
     step = TrainStep(m, variant, base_lr=0.01, graph=False)
     import random
     random.seed(123)
+    ovariant = variant
+    if variant == "pce_variance":
+        from wsl4mis_b200.utils import ramps
+        step.iter_num = 4500                   # a non-trivial ramp weight
+        ovariant = f"pce_variance:{0.1 * ramps.sigmoid_rampup(4500 // 150, 200.0)}"
     loss = step(image.to(DEV), label.to(DEV))
     torch.cuda.synchronize()
     beta = getattr(step, "beta", 0.5)
@@ -54,7 +59,7 @@ def test_step_matches_oracle(variant, cct):
             gs = torch.autograd.grad(ref_loss, [leaves[k] for k in names], allow_unused=True)
             grads = {k: g for k, g in zip(names, gs)}
         else:
-            ref_loss, grads, _ = O.full_step(p, image, label, variant, cct, om, ock, beta)
+            ref_loss, grads, _ = O.full_step(p, image, label, ovariant, cct, om, ock, beta)
     finally:
         O.QUANT = None
     assert abs(loss.item() - ref_loss.item()) < 0.02 * abs(ref_loss.item()) + 1e-4, (loss.item(), ref_loss.item())

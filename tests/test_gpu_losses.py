@@ -171,3 +171,30 @@ def test_full_size_properties():
     lg.requires_grad_(True)
     (gr,) = torch.autograd.grad(Fn.gated_crf(Fn.softmax4(lg), img), lg)
     assert gr.sum(1).abs().max().item() < 1e-7
+
+
+def test_entropy_and_class_variance_kernels(kat):
+    """K-level parity of the two remaining script-local regularisers against the oracle (fp32, 1e-5 / 1e-4)."""
+    from wsl4mis_b200._lib import call, workspace
+    lg = torch.from_numpy(kat["logits"])
+    img = torch.from_numpy(kat["image"])
+    p = torch.softmax(lg, 1).requires_grad_(True)
+    ent, var = O.entropy_loss(p, 4), O.class_variance_loss(p, img)
+    (ge,) = torch.autograd.grad(ent, p)
+    (gv,) = torch.autograd.grad(var, p)
+    pd, imd = p.detach().to(DEV).contiguous(), img.to(DEV)
+    N, C, H, W = pd.shape
+    out = torch.zeros(1, device=DEV)
+    g = torch.zeros_like(pd)
+    call("wsl_entropy_fwd", pd, N, C, H, W, out, workspace("ent"))
+    call("wsl_entropy_bwd", pd, N, C, H, W, 1.0, 0, g)
+    torch.cuda.synchronize()
+    assert abs(out.item() - ent.item()) < 1e-5 * abs(ent.item())
+    assert (g.cpu() - ge).abs().max().item() < 1e-4 * ge.abs().max().item()
+    out3 = torch.zeros(3, device=DEV)
+    st = torch.zeros(N * C * 2 + N * 2, device=DEV)
+    call("wsl_class_variance_fwd", imd, pd, N, C, H, W, out3, st, workspace("var"))
+    call("wsl_class_variance_bwd", imd, pd, st, N, C, H, W, 1.0, 0, g)
+    torch.cuda.synchronize()
+    assert abs(out3[0].item() - var.item()) < 1e-5 * abs(var.item()) + 1e-7
+    assert (g.cpu() - gv).abs().max().item() < 2e-4 * gv.abs().max().item()

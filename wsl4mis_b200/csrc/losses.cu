@@ -677,6 +677,144 @@ __global__ void __launch_bounds__(TPB) overlap_counts_kernel(const uint8_t* __re
     if (s_c[i]) atomicAdd(&counts[i], (unsigned long long)s_c[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Entropy minimisation: losses.entropy_loss(p, C) = mean_px(-sum_c p log(p + 1e-6)) / log(C)  (utils/losses.py:30-36,
+// train_weakly_supervised_pCE_Entropy_Mini_2D.py:99-102).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) entropy_fwd_kernel(const float* __restrict__ probs, long long total, float inv_norm,
+                                                          float* partials, unsigned* ticket, float* out) {
+  float acc[1] = {0.f};
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const float p = probs[i];
+    acc[0] -= p * logf(p + 1e-6f);
+  }
+  __shared__ double res[1];
+  if (block_reduce_final<1, TPB>(acc, partials, ticket, res)) {
+    if (threadIdx.x == 0) out[0] = (float)(res[0] * (double)inv_norm);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) entropy_bwd_kernel(const float* __restrict__ probs, long long total, float scale,
+                                                          int accumulate, float* __restrict__ gprobs) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const float p = probs[i];
+    const float g = -scale * (logf(p + 1e-6f) + p / (p + 1e-6f));
+    gprobs[i] = accumulate ? gprobs[i] + g : g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inter / intra class variance (train_weakly_supervised_pCE_Inter&Intra_Class_2D.py:30-36,114):
+//   v = img * p_c;  intra = mean_{n,c} std_{hw}(v)  (unbiased);  inter = mean_n std_c(mean_{hw}(v))  (unbiased over C)
+//   loss = inter - intra.   fwd: per-(n,c) sums S1 = sum v, S2 = sum v^2 (grid = (chunks, N)), finalised by the last
+//   block into stats[n][c] = {mean, std} + stats_n[n] = {mean over classes, std over classes}; bwd is elementwise.
+// A zero standard deviation yields a zero gradient here (the reference's autograd would produce inf/NaN).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) variance_fwd_kernel(const float* __restrict__ image, const float* __restrict__ probs, int N,
+                                                           long long HW, float* partials, unsigned* ticket, float* out /*[3]*/,
+                                                           float* stats /*[N*4*2 + N*2]*/) {
+  const int n = blockIdx.y;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < HW; i += (long long)gridDim.x * TPB) {
+    const float iv = image[n * HW + i];
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      const float v = iv * probs[(n * C4 + c) * HW + i];
+      acc[c] += v;
+      acc[4 + c] = fmaf(v, v, acc[4 + c]);
+    }
+  }
+  __shared__ float s_w[TPB / 32][8];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float r = warp_sum(acc[k]);
+    if (lane == 0) s_w[warp][k] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float r = 0.f;
+    for (int w = 0; w < TPB / 32; ++w) r += s_w[w][threadIdx.x];
+    partials[((size_t)n * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = r;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_intra[TPB / 32], s_inter[TPB / 32];
+  double w_intra = 0.0, w_inter = 0.0;
+  const double M = (double)HW;
+  for (int nn = warp; nn < N; nn += TPB / 32) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += (double)__ldcg(&partials[((size_t)nn * gridDim.x + b) * 8 + k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if (lane == 0) {
+      double mean[C4], mbar = 0.0;
+      for (int c = 0; c < C4; ++c) {
+        mean[c] = a[c] / M;
+        double var = (a[4 + c] - a[c] * a[c] / M) / (M - 1.0);
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var);
+        stats[(nn * C4 + c) * 2 + 0] = (float)mean[c];
+        stats[(nn * C4 + c) * 2 + 1] = (float)sd;
+        w_intra += sd;
+        mbar += mean[c];
+      }
+      mbar /= C4;
+      double vv = 0.0;
+      for (int c = 0; c < C4; ++c) vv += (mean[c] - mbar) * (mean[c] - mbar);
+      const double sdn = sqrt(vv / (C4 - 1.0));
+      stats[N * C4 * 2 + nn * 2 + 0] = (float)mbar;
+      stats[N * C4 * 2 + nn * 2 + 1] = (float)sdn;
+      w_inter += sdn;
+    }
+  }
+  if (lane == 0) { s_intra[warp] = w_intra; s_inter[warp] = w_inter; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ia = 0.0, ie = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) { ia += s_intra[w]; ie += s_inter[w]; }
+    ia /= (double)(N * C4);
+    ie /= (double)N;
+    out[0] = (float)(ie - ia);
+    out[1] = (float)ie;
+    out[2] = (float)ia;
+    *ticket = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) variance_bwd_kernel(const float* __restrict__ image, const float* __restrict__ probs,
+                                                           const float* __restrict__ stats, int N, long long HW, float scale,
+                                                           int accumulate, float* __restrict__ gprobs) {
+  const long long total = (long long)N * C4 * HW;
+  const float M = (float)HW;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long nc = i / HW, o = i - nc * HW;
+    const int n = (int)(nc / C4);
+    const float iv = image[n * HW + o];
+    const float v = iv * probs[i];
+    const float mean = stats[nc * 2], sd = stats[nc * 2 + 1];
+    const float mbar = stats[N * C4 * 2 + n * 2], sdn = stats[N * C4 * 2 + n * 2 + 1];
+    float g = 0.f;
+    if (sdn > 0.f) g += (mean - mbar) / ((C4 - 1.f) * sdn * M * (float)N);                 // + d inter / d v
+    if (sd > 0.f) g -= (v - mean) / ((M - 1.f) * sd * (float)(N * C4));                    // - d intra / d v
+    g *= scale * iv;
+    gprobs[i] = accumulate ? gprobs[i] + g : g;
+  }
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -830,4 +968,38 @@ WSL_API int wsl_overlap_counts(const uint8_t* pred, const uint8_t* gt, long long
   WSL_REQUIRE(classes >= 2 && classes <= 16, "wsl_overlap_counts: 2..16 classes (got %d)", classes);
   overlap_counts_kernel<<<grid_for(n, TPB * 4), TPB, 0, stream>>>(pred, gt, n, classes, counts_zeroed);
   return wsl_check_launch("overlap_counts");
+}
+
+WSL_API int wsl_entropy_fwd(const float* probs, int N, int C, int H, int W, float* out1, float* ws, cudaStream_t stream) {
+  const long long total = (long long)N * C * H * W;
+  const float inv_norm = (float)(1.0 / ((double)N * H * W * log((double)C)));
+  entropy_fwd_kernel<<<grid_for(total, TPB * 4), TPB, 0, stream>>>(probs, total, inv_norm, ws + 64, reinterpret_cast<unsigned*>(ws), out1);
+  return wsl_check_launch("entropy_fwd");
+}
+
+WSL_API int wsl_entropy_bwd(const float* probs, int N, int C, int H, int W, float scale, int accumulate, float* gprobs,
+                            cudaStream_t stream) {
+  const long long total = (long long)N * C * H * W;
+  const float sc = (float)((double)scale / ((double)N * H * W * log((double)C)));
+  entropy_bwd_kernel<<<grid_for(total, TPB * 4), TPB, 0, stream>>>(probs, total, sc, accumulate, gprobs);
+  return wsl_check_launch("entropy_bwd");
+}
+
+WSL_API int wsl_class_variance_fwd(const float* image, const float* probs, int N, int C, int H, int W, float* out3, float* stats,
+                                   float* ws, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_class_variance_fwd: C must be 4 (got %d)", C);
+  int chunks = (int)(((long long)H * W + TPB * 4 - 1) / (TPB * 4));
+  if (chunks > 64) chunks = 64;
+  WSL_REQUIRE((long long)chunks * N * 8 + 64 <= WSL_WS_FLOATS, "wsl_class_variance_fwd: batch too large for the workspace");
+  variance_fwd_kernel<<<dim3(chunks, N), TPB, 0, stream>>>(image, probs, N, (long long)H * W, ws + 64, reinterpret_cast<unsigned*>(ws),
+                                                           out3, stats);
+  return wsl_check_launch("class_variance_fwd");
+}
+
+WSL_API int wsl_class_variance_bwd(const float* image, const float* probs, const float* stats, int N, int C, int H, int W,
+                                   float scale, int accumulate, float* gprobs, cudaStream_t stream) {
+  WSL_REQUIRE(C == C4, "wsl_class_variance_bwd: C must be 4 (got %d)", C);
+  variance_bwd_kernel<<<grid_for((long long)N * C * H * W, TPB * 2), TPB, 0, stream>>>(image, probs, stats, N, (long long)H * W, scale,
+                                                                                      accumulate, gprobs);
+  return wsl_check_launch("class_variance_bwd");
 }

@@ -6,6 +6,8 @@
   pce_ms         train_weakly_supervised_pCE_MumfordShah_Loss_2D.py:98-110
   pce_tv         train_weakly_supervised_pCE_TV_2D.py:109-121
   dmpls          train_weakly_supervised_segmentation_pCE_ours_proposed.py:108-132
+  pce_entropy    train_weakly_supervised_pCE_Entropy_Mini_2D.py:97-109
+  pce_variance   train_weakly_supervised_pCE_Inter&Intra_Class_2D.py:112-125 (weight = consistency * sigmoid_rampup(it//150, 200))
 as ONE launch sequence: executor forward -> fused loss head (softmax+pCE, regulariser, combined backward into
 dlogits) -> executor backward into a flat fp32 gradient bucket -> (NCCL all-reduce of that bucket when
 world_size > 1) -> fused SGD(momentum 0.9, wd 1e-4) over the flat parameter buffer with the poly LR read from
@@ -25,7 +27,7 @@ from . import ddp
 from . import _lib
 from ._lib import call, workspace
 
-VARIANTS = ("pce", "pce_gatedcrf", "pce_ms", "pce_tv", "dmpls")
+VARIANTS = ("pce", "pce_gatedcrf", "pce_ms", "pce_tv", "dmpls", "pce_entropy", "pce_variance")
 
 
 class TrainStep:
@@ -61,6 +63,10 @@ class TrainStep:
         self.mom = torch.zeros_like(self.flat)
         self.lr_dev = torch.full((1,), self.base_lr, dtype=torch.float32, device=dev)
         self.beta_dev = torch.tensor([0.5, 0.5], dtype=torch.float32, device=dev)
+        self.cw_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.consistency, self.consistency_rampup = 0.1, 200.0
+        if variant == "pce_variance":
+            self.graph_enabled = False      # the ramp weight is a launch argument of the backward kernel
         self.beta = 0.5
         self.two_heads = len(self.ex.dec) == 2
         self.n_heads_trained = 2 if (variant == "dmpls") else 1
@@ -137,6 +143,27 @@ class TrainStep:
                 loss = ce   # mean over an empty tensor is NaN in the reference; N=1 is never used with this script
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
             call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
+        elif v == "pce_entropy":
+            gp = B("gprobs0", (N, C, H, W))
+            out = B("ent", (1,))
+            call("wsl_entropy_fwd", probs[0], N, C, H, W, out, workspace("ent", dev))
+            call("wsl_entropy_bwd", probs[0], N, C, H, W, 0.1, 0, gp)
+            loss = ce + 0.1 * out[0]
+            d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
+        elif v == "pce_variance":
+            from .utils import ramps
+            w = self.consistency * ramps.sigmoid_rampup(self.iter_num // 150, self.consistency_rampup)
+            gp = B("gprobs0", (N, C, H, W))
+            out = B("var", (3,))
+            st = B("varstats", (N * C * 2 + N * 2,))
+            call("wsl_class_variance_fwd", image, probs[0], N, C, H, W, out, st, workspace("var", dev))
+            call("wsl_class_variance_bwd", image, probs[0], st, N, C, H, W, 1.0, 0, gp)
+            # the ramp weight changes every 150 iterations: it multiplies on the device side so graphs stay valid
+            self.cw_dev.fill_(w)
+            loss = ce + self.cw_dev[0] * out[0]
+            d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, float(w), N, C, H, W, 4, d, d16)
         else:  # dmpls
             pseudo = B("pseudo", (N, H, W), torch.uint8)
             call("wsl_mix_argmax", probs[0], probs[1], 0.0, 0.0, self.beta_dev, N, C, H, W, pseudo)   # beta from device memory
