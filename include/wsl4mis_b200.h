@@ -116,6 +116,11 @@ int wsl_zoom_nearest(const void* src, int is_u8, int S, int h, int w, int H, int
 int wsl_overlap_counts(const uint8_t* pred, const uint8_t* gt, long long n, int classes, unsigned long long* counts_zeroed,
                        cudaStream_t stream);
 
+/* torch.rot90(x, k, [2,3]) of square fp32 maps ([planes,S,S]; dst (+)= rot(src)) and the mean-teacher EMA update
+ * ema = alpha*ema + (1-alpha)*param (train_weakly_supervised_ustm_2D.py:61-65,124-125,150,163). */
+int wsl_rot90(const float* src, long long planes, int S, int k, int accumulate, float* dst, cudaStream_t stream);
+int wsl_ema_update(float* ema, const float* param, long long n, float alpha, cudaStream_t stream);
+
 /* ---- network operators (networks/unet.py) ---------------------------------------------------------------- */
 
 /* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the

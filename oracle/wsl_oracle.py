@@ -417,6 +417,30 @@ def uamt_losses(out_l, out_u, ema_out, mc_logits, label_l, iter_num, max_iterati
     return supervised + cw * cons, supervised, cons, mask, cw, threshold                      # :191
 
 
+def ustm_losses(out, ema_out, mc_logits, label, rot_times, iter_num, max_iterations, T=8):
+    """Loss composition of train_weakly_supervised_ustm_2D.py:119-157: pCE on the scribbles + uncertainty-masked consistency
+    between rot90(student logits) and the teacher's logits on the rotated noisy input."""
+    B = out.shape[0]
+    preds = F.softmax(mc_logits, dim=1).reshape(T, B, *mc_logits.shape[1:]).mean(0)
+    uncertainty = -(preds * torch.log(preds + 1e-6)).sum(1, keepdim=True)
+    ce = pce_loss(out, label)                                                                  # :120-121
+    cw = 1.0 * sigmoid_rampup(iter_num // 1000, 60)                                            # :55-57,147-148
+    dist = softmax_mse(torch.rot90(out, rot_times, [2, 3]), ema_out)                           # :150-152
+    threshold = (0.75 + 0.25 * sigmoid_rampup(iter_num, max_iterations)) * math.log(2)         # :153-154
+    mask = (uncertainty < threshold).float()
+    cons = (mask * dist).sum() / (2 * mask.sum() + 1e-16)                                      # :155-157
+    return ce + cw * cons, ce, cons, mask, cw, threshold
+
+
+def ema_update(ema_params, params, alpha, global_step):
+    """update_ema_variables, train_weakly_supervised_ustm_2D.py:61-65 (parameters only, buffers untouched)."""
+    a = min(1 - 1 / (global_step + 1), alpha)
+    for k in ema_params:
+        if ema_params[k].is_floating_point() and "running" not in k:
+            ema_params[k] = ema_params[k] * a + (1 - a) * params[k]
+    return a
+
+
 def sgd_step(params, grads, moms, lr, momentum=0.9, weight_decay=1e-4):
     """optim.SGD(lr, momentum=0.9, weight_decay=1e-4).step(), train_weakly_supervised_pCE_2D.py:79-80,104.
     torch semantics: g += wd*w; first step buf = g, afterwards buf = mu*buf + g; w -= lr*buf.

@@ -200,3 +200,63 @@ def test_lr_schedule_follows_the_script():
     for it in range(3):
         step(img.to(DEV), lab.to(DEV))
         assert abs(step.lr_dev.item() - O.poly_lr(0.03, it, 100)) < 1e-8
+
+
+def test_rot90_and_ema_kernels():
+    from wsl4mis_b200._lib import call
+    x = torch.randn(3, 4, 16, 16, device=DEV)
+    for k in range(4):
+        out = torch.empty_like(x)
+        call("wsl_rot90", x, 12, 16, k, 0, out)
+        assert torch.equal(out, torch.rot90(x, k, [2, 3]).contiguous())
+    acc = torch.ones_like(x)
+    call("wsl_rot90", x, 12, 16, 3, 1, acc)
+    assert torch.allclose(acc, 1 + torch.rot90(x, 3, [2, 3]))
+    e, p = torch.randn(1000, device=DEV), torch.randn(1000, device=DEV)
+    ref = e * 0.75 + 0.25 * p
+    call("wsl_ema_update", e, p, 1000, 0.75)
+    assert torch.allclose(e, ref, atol=1e-7)
+
+
+@pytest.mark.parametrize("rot", [0, 1, 3])
+def test_ustm_step_matches_oracle(rot):
+    """train_weakly_supervised_ustm_2D.py:113-170 in fp32 parity mode: loss, SGD update and the EMA teacher update."""
+    from wsl4mis_b200.engine import USTMStep
+    B, hw = 2, 32
+    torch.manual_seed(33)
+    student, teacher = UNet(1, 4), UNet(1, 4)
+    ps = {k: v.clone() for k, v in student.state_dict().items()}
+    pt = {k: v.clone() for k, v in teacher.state_dict().items()}
+    student, teacher = student.to(DEV).set_precision("fp32"), teacher.to(DEV).set_precision("fp32")
+    ones = [torch.ones(B, O.FT[i], hw >> i, hw >> i, dtype=torch.uint8) for i in range(5)]
+    for m in (student, teacher):
+        m.dropout_masks = {i: e.permute(0, 2, 3, 1).contiguous().to(DEV) for i, e in enumerate(ones)}
+    om = {k: e for k, e in zip(ENC_MASK_KEYS, ones)}
+    om2 = {k: e.repeat(2, 1, 1, 1) for k, e in om.items()}
+    img, lab = O.synth_batch(B, hw, hw, seed=8, frac=0.1)
+    g = torch.Generator().manual_seed(6)
+    noises = [torch.clamp(torch.randn(B, 1, hw, hw, generator=g) * 0.1, -0.2, 0.2)] + \
+             [torch.clamp(torch.randn(2 * B, 1, hw, hw, generator=g) * 0.1, -0.2, 0.2) for _ in range(4)]
+    step = USTMStep(student, teacher, base_lr=0.03, max_iterations=60000)
+    step.iter_num = 5000
+    loss = step(img.to(DEV), lab.to(DEV), [n.to(DEV) for n in noises], rot_times=rot)
+    torch.cuda.synchronize()
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in ps.items()}
+    out = O.unet_forward(leaves, img, True, om)
+    rimg = torch.rot90(img, rot, [2, 3])
+    with torch.no_grad():
+        ema_out = O.unet_forward(pt, rimg + noises[0], True, om)
+        mc = torch.cat([O.unet_forward(pt, rimg.repeat(2, 1, 1, 1) + noises[1 + i], True, om2) for i in range(4)], 0)
+    ref_loss, ce, cons, mask, cw, thr = O.ustm_losses(out, ema_out, mc, lab, rot, 5000, 60000)
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    names = [k for k, v in leaves.items() if v.requires_grad]
+    grads = dict(zip(names, torch.autograd.grad(ref_loss, [leaves[k] for k in names])))
+    new_s = {k: ps[k] - 0.03 * (grads[k] + 1e-4 * ps[k]) for k in names}
+    named, tnamed = dict(student.named_parameters()), dict(teacher.named_parameters())
+    alpha = min(1 - 1 / (5000 + 1), 0.99)
+    for k in names:
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue
+        assert cosine(named[k].detach().cpu() - ps[k], new_s[k] - ps[k]) > 0.999, k
+        ref_t = pt[k] * alpha + (1 - alpha) * named[k].detach().cpu()
+        assert torch.allclose(tnamed[k].detach().cpu(), ref_t, atol=1e-6), k

@@ -815,6 +815,32 @@ __global__ void __launch_bounds__(TPB) variance_bwd_kernel(const float* __restri
   }
 }
 
+// torch.rot90(x, k, [2, 3]) for square maps (train_weakly_supervised_ustm_2D.py:124-125,150): k=1: out[i][j] = in[j][S-1-i];
+// k=2: out[i][j] = in[S-1-i][S-1-j]; k=3: out[i][j] = in[S-1-j][i].  accumulate: dst += rot(src).
+__global__ void __launch_bounds__(TPB) rot90_kernel(const float* __restrict__ src, long long planes, int S, int k, int accumulate,
+                                                    float* __restrict__ dst) {
+  const long long total = planes * S * S;
+  for (long long t = blockIdx.x * (long long)TPB + threadIdx.x; t < total; t += (long long)gridDim.x * TPB) {
+    const int j = (int)(t % S), i = (int)((t / S) % S);
+    const long long pl = t / ((long long)S * S);
+    int si, sj;
+    switch (k & 3) {
+      case 1: si = j; sj = S - 1 - i; break;
+      case 2: si = S - 1 - i; sj = S - 1 - j; break;
+      case 3: si = S - 1 - j; sj = i; break;
+      default: si = i; sj = j; break;
+    }
+    const float v = src[(pl * S + si) * S + sj];
+    dst[t] = accumulate ? dst[t] + v : v;
+  }
+}
+
+// update_ema_variables (train_weakly_supervised_ustm_2D.py:61-65): ema = alpha*ema + (1-alpha)*param over a flat buffer
+__global__ void __launch_bounds__(TPB) ema_update_kernel(float* __restrict__ ema, const float* __restrict__ param, long long n, float alpha) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB)
+    ema[i] = ema[i] * alpha + (1.f - alpha) * param[i];
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -1002,4 +1028,15 @@ WSL_API int wsl_class_variance_bwd(const float* image, const float* probs, const
   variance_bwd_kernel<<<grid_for((long long)N * C * H * W, TPB * 2), TPB, 0, stream>>>(image, probs, stats, N, (long long)H * W, scale,
                                                                                       accumulate, gprobs);
   return wsl_check_launch("class_variance_bwd");
+}
+
+WSL_API int wsl_rot90(const float* src, long long planes, int S, int k, int accumulate, float* dst, cudaStream_t stream) {
+  WSL_REQUIRE(src != dst, "wsl_rot90: in-place rotation is not supported");
+  rot90_kernel<<<grid_for(planes * S * S, TPB * 2), TPB, 0, stream>>>(src, planes, S, k, accumulate, dst);
+  return wsl_check_launch("rot90");
+}
+
+WSL_API int wsl_ema_update(float* ema, const float* param, long long n, float alpha, cudaStream_t stream) {
+  ema_update_kernel<<<grid_for(n, TPB * 2), TPB, 0, stream>>>(ema, param, n, alpha);
+  return wsl_check_launch("ema_update");
 }

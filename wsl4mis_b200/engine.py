@@ -369,3 +369,71 @@ class UAMTStep:
         self.lr_dev.fill_(lr_)
         self.iter_num += 1
         return loss
+
+
+class USTMStep(UAMTStep):
+    """Per-step body of train_weakly_supervised_ustm_2D.py:113-170: pCE on scribbles + uncertainty-aware self-ensembling with a
+    random rot90 transform (Python host RNG, :123) and the EMA teacher update the script really performs (:163)."""
+
+    def __init__(self, model, ema_model, base_lr=0.01, max_iterations=60000, ema_decay=0.99, **kw):
+        super().__init__(model, ema_model, base_lr=base_lr, max_iterations=max_iterations, **kw)
+        self.ema_decay = float(ema_decay)
+        tparams = self.ex_t.params
+        n = sum(p.numel() for p in tparams)
+        self.tflat = torch.empty(n, dtype=torch.float32, device=self.dev)
+        off = 0
+        for p in tparams:
+            self.tflat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.tflat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def __call__(self, image, label, noises=None, rot_times=None):
+        import math
+        ex, ex_t, dev = self.ex, self.ex_t, self.dev
+        self.model.train()
+        self.ema_model.train()
+        B, _, H, W = image.shape
+        assert H == W, "rot90 consistency needs square inputs"
+        C, T = 4, self.T
+        self.seed_dev.add_(1)
+        k = random.randrange(0, 4) if rot_times is None else int(rot_times)
+        self.rot_times = k
+        masks, ck = getattr(self.model, "dropout_masks", None), getattr(self.model, "channel_keep", None)
+        tmasks, tck = getattr(self.ema_model, "dropout_masks", None), getattr(self.ema_model, "channel_keep", None)
+        outs, slot = ex.forward(image.contiguous(), True, True, masks, ck)
+        out = outs[0]
+        Bf = lambda name, shape, dt=torch.float32: ex.buf("ustm", name, shape, dt)
+        rimg = Bf("rimg", (B, 1, H, W))
+        call("wsl_rot90", image.contiguous(), B, H, k, 0, rimg)
+        ema_out = ex_t.forward(self._noisy(rimg, 1, 0, None if noises is None else noises[0]), True, False, tmasks, tck)[0][0]
+        mc = Bf("mc", (T * B, C, H, W))
+        for i in range(T // 2):
+            tm2 = None if tmasks is None else {kk: v.repeat(2, 1, 1, 1) for kk, v in tmasks.items()}
+            tck2 = None if tck is None else [c.repeat(2, 1) for c in tck]
+            lg = ex_t.forward(self._noisy(rimg, 2, 1 + i, None if noises is None else noises[1 + i]), True, False, tm2, tck2)[0][0]
+            mc[2 * B * i: 2 * B * (i + 1)].copy_(lg)
+        # pCE (ignore_index 4)
+        probs, st = Bf("probs", (B, C, H, W)), Bf("stats", (2,))
+        call("wsl_softmax_pce_fwd", out, label, probs, B, C, H, W, 4, st, workspace("pce", dev))
+        d = Bf("dl", (B, C, H, W))
+        call("wsl_head_bwd", probs, label, st, None, 1.0, None, 0.0, B, C, H, W, 4, d, None)
+        # consistency on the rotated student logits
+        rout = Bf("rout", (B, C, H, W))
+        call("wsl_rot90", out, B * C, H, k, 0, rout)
+        cw = 1.0 * self.ramps.sigmoid_rampup(self.iter_num // 1000, 60)
+        thr = (0.75 + 0.25 * self.ramps.sigmoid_rampup(self.iter_num, self.max_iterations)) * math.log(2)
+        mask, cst = Bf("mask", (B, H, W), torch.uint8), Bf("cons", (3,))
+        call("wsl_uamt_consistency_fwd", rout, ema_out, mc, T, B, C, H, W, None, float(thr), mask, cst, workspace("uamt", dev))
+        dr = Bf("dr", (B, C, H, W))
+        call("wsl_uamt_consistency_bwd", rout, ema_out, mask, cst, None, float(cw), B, C, H, W, dr)
+        call("wsl_rot90", dr, B * C, H, (4 - k) % 4, 1, d)              # rotate the gradient back and add it to the pCE part
+        loss = st[0] + cw * cst[2]
+        self.parts = {"ce": st[0], "consistency": cst[2], "weight": cw, "threshold": thr, "mask": mask}
+        g = ex.backward(slot, [d] + [None] * (len(ex.dec) - 1))
+        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay, 1.0)
+        alpha = min(1 - 1 / (self.iter_num + 1), self.ema_decay)         # :63, global_step = iter_num before the increment
+        call("wsl_ema_update", self.tflat, self.flat, min(self.tflat.numel(), self.flat.numel()), float(alpha))
+        lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
+        self.lr_dev.fill_(lr_)
+        self.iter_num += 1
+        return loss
