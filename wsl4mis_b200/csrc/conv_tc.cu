@@ -93,6 +93,33 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Issue-path helpers.  The MMA warp stays converged; ONE elected lane issues, and every operand of the issue loop is a
+// warp-uniform value (read through lane 0), so the compiler keeps descriptors in uniform registers and emits back-to-back
+// UTCHMMA instead of a per-instruction ELECT / R2UR / branch sequence (measured on the B200: ~80 -> ~50 cycles per
+// M=128,N=16 MMA; profiles/micro/mma_rate.cu).  A descriptor is {lo = addr>>4 | LBO<<16, hi = constant}.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+  return e;
+}
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// high word of a shared-memory descriptor: SBO | version 1 | swizzle layout
+template <int SW>
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (((SW == 128) ? 2u : (SW == 64) ? 4u : 6u) << 29);
+}
+
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -514,6 +541,12 @@ __global__ void __launch_bounds__(Conv2Epi<NT, MT>::THREADS) conv_tc2_kernel(con
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(NT);
+    constexpr uint32_t a_hi = desc_hi<SW>(Cfg::HW_ * Cfg::ROWB), b_hi = desc_hi<SW>(8 * SW);
+    const uint32_t elected = elect_one();
+    const uint32_t tmem_u = uniform(tmem_base);
+    const uint32_t a_lo0 = (uniform(smem_u32(a_smem)) >> 4) | 0x10000u;      // LBO field = 1 (ignored for swizzled K-major)
+    const uint32_t w_lo0 = (uniform(smem_u32(w_smem)) >> 4) | 0x10000u;
+    const uint32_t w_tap = (uint32_t)(nkb * Cfg::W_SUB) >> 4;               // descriptor units between two taps of the weights
     mbar_wait(w_bar, 0);
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
@@ -524,21 +557,19 @@ __global__ void __launch_bounds__(Conv2Epi<NT, MT>::THREADS) conv_tc2_kernel(con
         const int s = it % STAGES;
         mbar_wait(&a_full[s], (it / STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = smem_u32(a_smem + s * Cfg::A_STAGE);
-          const uint32_t w_base = smem_u32(w_smem);
+        if (elected) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)(s * (Cfg::A_STAGE >> 4));
+          const uint32_t w_lo = w_lo0 + (uint32_t)(kb * (Cfg::W_SUB >> 4));
+          const uint32_t d0 = tmem_u + (uint32_t)(acc * MT * NT);
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
 #pragma unroll
             for (int t = 0; t < T; ++t) {
               const int dy = t / KS, dx = t % KS;
-              const uint32_t a_addr = a_base + (uint32_t)(((16 * j + dy) * Cfg::HW_ + dx) * Cfg::ROWB);
-              const uint64_t adesc = make_kmajor_desc_sbo<SW>(a_addr, Cfg::HW_ * Cfg::ROWB, p.desc_mode);
-              const uint64_t bdesc = make_kmajor_desc_sbo<SW>(w_base + (uint32_t)((t * nkb + kb) * Cfg::W_SUB), 8 * SW, 0);
 #pragma unroll
               for (int k = 0; k < KBLK / 16; ++k)
-                umma_f16(tmem_base + (uint32_t)((acc * MT + j) * NT), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                         (kb > 0 || t > 0 || k > 0) ? 1u : 0u);
+                umma_f16_w(d0 + (uint32_t)(j * NT), a_lo + (uint32_t)(((((16 * j + dy) * Cfg::HW_ + dx) * Cfg::ROWB) >> 4) + 2 * k), a_hi,
+                           w_lo + (uint32_t)t * w_tap + (uint32_t)(2 * k), b_hi, idesc, (kb > 0 || t > 0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(&a_empty[s]);
@@ -965,12 +996,20 @@ int launch_wgrad2(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensor
 //   D_dy[(dx, ci)][co], dy = 0..2: three accumulators of N columns in TMEM.
 // MMAs per 128-pixel chunk and 32-channel Cin block: 3 dy x 8 k-steps = 24 (v2 issued 72 narrow ones).
 // ================================================================================================
-template <int CWB, int CWN, int NBOX, int STAGES>
+// DYN (NBOX == 1 only): the filter ROWS go into the MMA's N dimension as well.  dY is loaded with one halo row above and below
+// (18 x 8 pixels); N-group g of the B operand is the dY tile viewed g - 1 rows further down (LBO = one tile row), while A is
+// the un-shifted X row block (16 x 10 pixels, LBO = one pixel -> filter column in M).  X[p + (1 - g) rows + dx] * dY[p] lands
+// in column group g, i.e. dy = 2 - g; the products that fall outside the chunk's rows are exactly those against the zero
+// padding (TMA zero fill).  One N = 3*NTILE MMA replaces three N = NTILE ones: 8 instead of 24 per chunk; with the measured
+// issue cost 10 + 32 (A read) + N/2 cycles that is 528 instead of 1224 cycles per chunk for the 16-channel layers.
+template <int CWB, int CWN, int NBOX, int STAGES, bool DYN>
 struct Wgrad3Smem {
   static constexpr int ROWB = CWB * 2;
-  static constexpr int N_BOX = TILE_M * CWN * 2;
-  static constexpr int A_HALO = ((10 * 18 * ROWB + 1023) / 1024) * 1024;
-  static constexpr int STAGE_BYTES = ((NBOX * N_BOX + A_HALO + 1023) / 1024) * 1024;
+  static constexpr int N_ROWS = DYN ? 18 : 16, X_ROWS = DYN ? 16 : 18;
+  static constexpr int N_BOX = N_ROWS * 8 * CWN * 2;
+  static constexpr int A_OFF = ((NBOX * N_BOX + 1023) / 1024) * 1024;
+  static constexpr int A_BYTES = 10 * X_ROWS * ROWB;
+  static constexpr int STAGE_BYTES = ((A_OFF + A_BYTES + 1023) / 1024) * 1024;
   static constexpr int SLACK = 2048;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + SLACK + 1024 + 256;
 };
@@ -984,11 +1023,12 @@ struct Wgrad3Params {
   float* dw;
 };
 
-template <int CWB, int CWN, int NBOX, int STAGES>
+template <int CWB, int CWN, int NBOX, int STAGES, bool DYN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_dy,
                                                                    const __grid_constant__ CUtensorMap map_x0,
                                                                    const __grid_constant__ CUtensorMap map_x1, const Wgrad3Params p) {
-  using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES>;
+  using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES, DYN>;
+  static_assert(!DYN || NBOX == 1, "row merging needs a single dY box");
   constexpr int NTILE = CWN * NBOX;
   constexpr int SWX = CWB * 2, SWN = CWN * 2;
   constexpr uint32_t TMEM_COLS = (3 * NTILE <= 64) ? 64 : (3 * NTILE <= 128) ? 128 : (3 * NTILE <= 256) ? 256 : 512;
@@ -1033,31 +1073,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc3_kernel(const __grid_
         const int s = it % STAGES;
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
         uint8_t* b_dst = smem + s * S::STAGE_BYTES;          // dY boxes
-        uint8_t* a_dst = b_dst + NBOX * S::N_BOX;            // X halo
-        mbar_expect_tx(&full_bar[s], NBOX * S::N_BOX + 10 * 18 * S::ROWB);
+        uint8_t* a_dst = b_dst + S::A_OFF;                   // X block
+        mbar_expect_tx(&full_bar[s], NBOX * S::N_BOX + S::A_BYTES);
 #pragma unroll
-        for (int i = 0; i < NBOX; ++i) tma_load_4d(&map_dy, &full_bar[s], b_dst + i * S::N_BOX, n0 + i * CWN, x0, y0, n);
-        tma_load_4d(mx, &full_bar[s], a_dst, cb0, x0 - 1, y0 - 1, n);
+        for (int i = 0; i < NBOX; ++i)
+          tma_load_4d(&map_dy, &full_bar[s], b_dst + i * S::N_BOX, n0 + i * CWN, x0, DYN ? y0 - 1 : y0, n);
+        tma_load_4d(mx, &full_bar[s], a_dst, cb0, x0 - 1, DYN ? y0 : y0 - 1, n);
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(NTILE, 1, 1, 128);
+    constexpr uint32_t idesc = make_idesc_bf16(DYN ? 3 * NTILE : NTILE, 1, 1, 128);
+    // A: channel-group stride (LBO) = one pixel, so group g == filter column dx = g; 8-pixel-row groups 10 halo pixels apart
+    constexpr uint32_t a_hi = desc_hi<SWX>(10 * S::ROWB), b_hi = desc_hi<SWN>(8 * SWN);
+    constexpr uint32_t a_lbo = ((uint32_t)(S::ROWB >> 4) & 0x3fffu) << 16;
+    constexpr uint32_t b_lbo = ((uint32_t)((DYN ? 8 * SWN : S::N_BOX) >> 4) & 0x3fffu) << 16;
+    const uint32_t elected = elect_one();
+    const uint32_t tmem_u = uniform(tmem_base);
+    const uint32_t s_lo0 = uniform(smem_u32(smem)) >> 4;
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it % STAGES;
       mbar_wait(&full_bar[s], (it / STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t b_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t a_addr = b_addr + NBOX * S::N_BOX;
-        const uint64_t bdesc = make_mnmajor_desc_sbo<SWN>(b_addr, S::N_BOX, 8 * SWN);
+      if (elected) {
+        const uint32_t b_lo = (s_lo0 + (uint32_t)(s * (S::STAGE_BYTES >> 4))) | b_lbo;
+        const uint32_t a_lo = (s_lo0 + (uint32_t)(s * (S::STAGE_BYTES >> 4) + (S::A_OFF >> 4))) | a_lbo;
+        if constexpr (DYN) {
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          // channel-group stride (LBO) = one pixel: group g == filter column dx = g
-          const uint64_t adesc = make_mnmajor_desc_sbo<SWX>(a_addr + (uint32_t)(dy * 10 * S::ROWB), S::ROWB, 10 * S::ROWB);
+          for (int k = 0; k < 8; ++k)      // k-step = 16 pixels = chunk rows 2k, 2k+1
+            umma_f16_w(tmem_u, a_lo + (uint32_t)((k * 2 * 10 * S::ROWB) >> 4), a_hi, b_lo + (uint32_t)((k * 16 * SWN) >> 4), b_hi, idesc,
+                       (it > 0 || k > 0) ? 1u : 0u);
+        } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_f16(tmem_base + dy * NTILE, adesc + (uint64_t)((k * 2 * 10 * S::ROWB) >> 4), bdesc + (uint64_t)((k * 16 * SWN) >> 4), idesc,
-                     (it > 0 || k > 0) ? 1u : 0u);
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_f16_w(tmem_u + (uint32_t)(dy * NTILE), a_lo + (uint32_t)(((dy * 10 * S::ROWB) >> 4) + ((k * 2 * 10 * S::ROWB) >> 4)), a_hi,
+                         b_lo + (uint32_t)((k * 16 * SWN) >> 4), b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);
         if (it == my_chunks - 1) umma_commit(accum_bar);
@@ -1072,11 +1124,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc3_kernel(const __grid_
     tc_fence_after();
     const int CinTot = p.C0 + p.C1;
 #pragma unroll 1
-    for (int dy = 0; dy < 3; ++dy) {
+    for (int grp = 0; grp < 3; ++grp) {
+      const int dy = DYN ? 2 - grp : grp;       // column group -> filter row
 #pragma unroll 1
       for (int c = 0; c < NTILE; c += 16) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dy * NTILE + c), v);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * NTILE + c), v);
         if (g < 3) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -1095,12 +1148,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc3_kernel(const __grid_
 template <int CWB, int CWN, int NBOX>
 int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const Wgrad3Params& p, int n_tiles,
                   cudaStream_t stream) {
+  constexpr bool DYN = (NBOX == 1);
   constexpr int per_stage = NBOX * TILE_M * CWN * 2 + 12 * 1024;
   constexpr int STAGES = per_stage >= 40 * 1024 ? 3 : 4;
-  using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES>;
+  using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES, DYN>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) { wsl_set_error("wgrad_tc3: cudaFuncSetAttribute(%d bytes): %s", S::TOTAL, cudaGetErrorString(e)); return -5; }
     attr = true;
   }
@@ -1109,7 +1163,7 @@ int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensor
   if (splits > p.nchunks) splits = p.nchunks;
   if (splits < 1) splits = 1;
   dim3 grid(splits, gy);
-  wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
+  wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES, DYN><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
   return wsl_check_launch("wgrad_tc3");
 }
 
@@ -1455,22 +1509,23 @@ WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, co
   const int cwn = CoutP >= 64 ? 64 : CoutP;
   const int ntile = CoutP >= 128 ? 128 : CoutP;
   const int n_tiles = CoutP / ntile;
+  const bool dyn = ntile < 128;          // single dY box: filter rows merged into the MMA's N dimension (18-row dY box, 16-row X box)
   CUtensorMap mdy, mx0, mx1;
   {
     long long d[4] = {CoutP, W, H, N};
-    int bx[4] = {cwn, 8, 16, 1};
+    int bx[4] = {cwn, 8, dyn ? 18 : 16, 1};
     int rc = get_map(dy, 4, d, bx, cwn, &mdy);
     if (rc) return rc;
   }
   {
     long long d[4] = {C0, W, H, N};
-    int bx[4] = {cwb, 10, 18, 1};
+    int bx[4] = {cwb, 10, dyn ? 16 : 18, 1};
     int rc = get_map(src0, 4, d, bx, cwb, &mx0);
     if (rc) return rc;
   }
   if (C1 > 0) {
     long long d[4] = {C1, W, H, N};
-    int bx[4] = {cwb, 10, 18, 1};
+    int bx[4] = {cwb, 10, dyn ? 16 : 18, 1};
     int rc = get_map(src1, 4, d, bx, cwb, &mx1);
     if (rc) return rc;
   } else {

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TPB, 4) conv_first_kernel(const float* __restr
 // dW[co][t] += sum_p dY[p][co] * x[p + tap_t]: every thread walks pixels with an 8x9 register tile (blockIdx.y picks
 // the channel half; 72 FMAs per 10 loads), then warp-shuffle + one atomicAdd per warp and entry.
 template <typename T>
-__global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 2) wgrad_first_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                              float* __restrict__ dw /*[16][9]*/, int N, int H, int W) {
   float acc[8][9];
 #pragma unroll
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __rest
     for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
   const int half = blockIdx.y;
   const long long total = (long long)N * H * W;
-  for (long long i = blockIdx.x * 128LL + threadIdx.x; i < total; i += (long long)gridDim.x * 128) {
+#pragma unroll 2
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int xx = (int)(i % W), yy = (int)((i / W) % H);
     const float* base = x + (i - (long long)yy * W - xx);
     float v[9], g[8];
@@ -209,13 +210,24 @@ __global__ void __launch_bounds__(128, 4) wgrad_first_kernel(const float* __rest
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], v[t], acc[c][t]);
   }
+  // block reduction (fixed order inside the block), then ONE atomic per value and block: 72 same-address atomics per warp
+  // of 1184 blocks used to serialise in L2 for ~0.25 ms.
+  __shared__ float s_red[8][72];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float r = warp_sum(acc[c][t]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(dw + (half * 8 + c) * 9 + t, r);
+      if (lane == 0) s_red[warp][c * 9 + t] = r;
     }
+  __syncthreads();
+  if (threadIdx.x < 72) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_red[w][threadIdx.x];
+    atomicAdd(dw + half * 72 + threadIdx.x, r);
+  }
 }
 
 // ================================================================================================
@@ -1098,10 +1110,10 @@ WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, vo
 
 WSL_API int wsl_wgrad_first(const float* x, const void* dy, int dtype, float* dw, int N, int H, int W, int Cout, cudaStream_t stream) {
   WSL_REQUIRE(Cout == 16, "wsl_wgrad_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
-  long long b = ((long long)N * H * W + 128 * 16 - 1) / (128 * 16);
-  if (b > 148 * 4) b = 148 * 4;
+  long long b = ((long long)N * H * W + 256 * 16 - 1) / (256 * 16);
+  if (b > 148) b = 148;                      // x 2 channel halves x 2 resident blocks per SM = one wave
   if (b < 1) b = 1;
-  WSL_DISPATCH_T(dtype, wgrad_first_kernel<T><<<dim3((int)b, 2), 128, 0, stream>>>(x, (const T*)dy, dw, N, H, W));
+  WSL_DISPATCH_T(dtype, wgrad_first_kernel<T><<<dim3((int)b, 2), 256, 0, stream>>>(x, (const T*)dy, dw, N, H, W));
   return wsl_check_launch("wgrad_first");
 }
 
