@@ -507,9 +507,8 @@ __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = ss[c0 + j]; sh[j] = ss[C + c0 + j]; }
-  auto act8 = [&](int p, float (&o)[8]) {
-    float v[8];
-    ld8(y + (long long)p * C + c0, v);
+  // loads are issued for all pixels of an iteration before the first use (the dropout branch would otherwise serialise them)
+  auto act8 = [&](int p, const float (&v)[8], float (&o)[8]) {
     const uint32_t kb = keep_bits8(dc, (long long)p * C + c0, (uint32_t)p * cg + g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -519,23 +518,36 @@ __global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(
     }
   };
   if (pooled == nullptr) {
-    const int P = N * H * W;
-    for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
-      float o[8];
-      act8(p, o);
+    const int P = N * H * W, stride = gridDim.x * rows;
+    int p = blockIdx.x * rows + r;
+    for (; p + stride < P; p += 2 * stride) {
+      float v0[8], v1[8], o0[8], o1[8];
+      ld8(y + (long long)p * C + c0, v0);
+      ld8(y + (long long)(p + stride) * C + c0, v1);
+      act8(p, v0, o0);
+      act8(p + stride, v1, o1);
+      st8(act + (long long)p * C + c0, o0);
+      st8(act + (long long)(p + stride) * C + c0, o1);
+    }
+    if (p < P) {
+      float v[8], o[8];
+      ld8(y + (long long)p * C + c0, v);
+      act8(p, v, o);
       st8(act + (long long)p * C + c0, o);
     }
   } else {
     const int Hp = H >> 1, Wp = W >> 1, Q = N * Hp * Wp;
     for (int q = blockIdx.x * rows + r; q < Q; q += gridDim.x * rows) {
       const int xp = q % Wp, t = q / Wp, yp = t % Hp, n = t / Hp;
-      float best[8];
+      float best[8], v[4][8];
       int arg[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ld8(y + (long long)((n * H + yp * 2 + (k >> 1)) * W + xp * 2 + (k & 1)) * C + c0, v[k]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int p = (n * H + yp * 2 + (k >> 1)) * W + xp * 2 + (k & 1);
         float o[8];
-        act8(p, o);
+        act8(p, v[k], o);
         st8(act + (long long)p * C + c0, o);
         round8<T>(o);     // pool over the activations exactly as stored
 #pragma unroll
@@ -592,20 +604,25 @@ __device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs<T>& a) {
 }
 
 // dz (gradient w.r.t. the BN output z) and the raw conv output y of 8 channels of pixel p
-template <typename T>
-__device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&dz)[8], float (&yv)[8]) {
-  float g[8];
+// MODE 0: the single gradient source g0 (straight-line code: the two-pixel unrolled callers get all loads in flight at once);
+// MODE 1: any combination of sources (uniform runtime branches).
+template <int MODE, typename T>
+__device__ __forceinline__ void bn_bwd_gather8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&g)[8], float (&yv)[8]) {
   const long long off = (long long)p * a.C + t.c0;
   ld8(a.y + off, yv);
+  if (MODE == 0) {
+    ld8(a.g0 + off, g);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  if (a.g0) {
-    float v[8];
-    ld8(a.g0 + off, v);
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    if (a.g0) {
+      float v[8];
+      ld8(a.g0 + off, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += v[j];
+      for (int j = 0; j < 8; ++j) g[j] += v[j];
+    }
   }
-  if (a.g1 || a.gp) {
+  if (MODE != 0 && (a.g1 || a.gp)) {
     const int x = p % a.W, r = p / a.W, yy = r % a.H, n = r / a.H;
     if (a.g1) {
       float v[8];
@@ -633,16 +650,21 @@ __device__ __forceinline__ void bn_bwd_dz8(const BnBwdArgs<T>& a, const BnBwdThr
       }
     }
   }
-  const uint32_t kb = keep_bits8(t.dc, off, (uint32_t)p * t.cg + t.g);
+}
+
+// summed incoming gradient g -> dz: dropout mask (regenerated) and LeakyReLU derivative; in place
+template <typename T>
+__device__ __forceinline__ void bn_bwd_finish8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&g)[8], const float (&yv)[8]) {
+  const uint32_t kb = keep_bits8(t.dc, (long long)p * a.C + t.c0, (uint32_t)p * t.cg + t.g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float z = fmaf(yv[j], t.sc[j], t.sh[j]);
     const float d = g[j] * (z > 0.f ? 1.f : a.slope);
-    dz[j] = ((kb >> j) & 1u) ? d * t.dc.inv_keep : 0.f;
+    g[j] = ((kb >> j) & 1u) ? d * t.dc.inv_keep : 0.f;
   }
 }
 
-template <typename T>
+template <int MODE, typename T>
 __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
                                                                float* partials, unsigned* ticket, int accumulate) {
@@ -651,17 +673,30 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, f
   const int C = a.C, cg = t.cg, rows = TPB / cg;
   const int P = a.N * a.H * a.W;
   const int r = threadIdx.x / cg;
-  float xa[8], xb[8];     // xhat = y*xa + xb
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { xa[j] = a.save[C + t.c0 + j]; xb[j] = -a.save[t.c0 + j] * xa[j]; }
+  // accumulate sum(dz) and sum(dz*y) on the RAW conv output; sum(dz*xhat) = invstd*(sum(dz*y) - mean*sum(dz)) is formed per
+  // block below (keeps 16 registers free for the second pixel in flight)
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
-    float dz[8], yv[8];
-    bn_bwd_dz8(a, t, p, dz, yv);
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + stride < P; p += 2 * stride) {
+    float dz0[8], y0[8], dz1[8], y1[8];
+    bn_bwd_gather8<MODE>(a, t, p, dz0, y0);            // all loads of both pixels are issued before the first use
+    bn_bwd_gather8<MODE>(a, t, p + stride, dz1, y1);
+    bn_bwd_finish8(a, t, p, dz0, y0);
+    bn_bwd_finish8(a, t, p + stride, dz1, y1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], fmaf(yv[j], xa[j], xb[j]), s2[j]); }
+    for (int j = 0; j < 8; ++j) { s1[j] += dz0[j]; s2[j] = fmaf(dz0[j], y0[j], s2[j]); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += dz1[j]; s2[j] = fmaf(dz1[j], y1[j], s2[j]); }
+  }
+  if (p < P) {
+    float dz[8], yv[8];
+    bn_bwd_gather8<MODE>(a, t, p, dz, yv);
+    bn_bwd_finish8(a, t, p, dz, yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], yv[j], s2[j]); }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
@@ -671,7 +706,7 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, f
     float x = 0.f, y = 0.f;
     for (int rr = 0; rr < rows; ++rr) { x += s_red[(rr * cg + gg) * 16 + j]; y += s_red[(rr * cg + gg) * 16 + 8 + j]; }
     partials[((size_t)blockIdx.x * 2 + 0) * C + c] = x;
-    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = y;
+    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = a.save[C + c] * (y - a.save[c] * x);      // sum(dz * xhat)
   }
   __shared__ bool s_last;
   __threadfence();
@@ -696,7 +731,7 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, f
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-template <typename T>
+template <int MODE, typename T>
 __global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs<T> a, const float* __restrict__ coef,
                                                               T* __restrict__ dy) {
   const BnBwdThread t = bn_bwd_thread(a);
@@ -706,9 +741,26 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs<T> a, co
   float kb_[8], kd_[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { kb_[j] = coef[t.c0 + j]; kd_[j] = coef[C + t.c0 + j]; }
-  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + stride < P; p += 2 * stride) {
+    float dz0[8], y0[8], dz1[8], y1[8], o0[8], o1[8];
+    bn_bwd_gather8<MODE>(a, t, p, dz0, y0);
+    bn_bwd_gather8<MODE>(a, t, p + stride, dz1, y1);
+    bn_bwd_finish8(a, t, p, dz0, y0);
+    bn_bwd_finish8(a, t, p + stride, dz1, y1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o0[j] = fmaf(dz0[j], t.sc[j], fmaf(y0[j], kb_[j], kd_[j]));
+      o1[j] = fmaf(dz1[j], t.sc[j], fmaf(y1[j], kb_[j], kd_[j]));
+    }
+    st8(dy + (long long)p * C + t.c0, o0);
+    st8(dy + (long long)(p + stride) * C + t.c0, o1);
+  }
+  if (p < P) {
     float dz[8], yv[8], o[8];
-    bn_bwd_dz8(a, t, p, dz, yv);
+    bn_bwd_gather8<MODE>(a, t, p, dz, yv);
+    bn_bwd_finish8(a, t, p, dz, yv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(dz[j], t.sc[j], fmaf(yv[j], kb_[j], kd_[j]));
     st8(dy + (long long)p * C + t.c0, o);
@@ -1027,10 +1079,13 @@ static int bn_bwd_launch(const void* y, const float* ss, const float* save, cons
   a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
   const long long P = (long long)N * H * W;
   const int grid = bn_grid(P, C);
-  bn_bwd_reduce_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws), accumulate);
+  const bool single = g0 != nullptr && g1 == nullptr && gpool == nullptr;
+  if (single) bn_bwd_reduce_kernel<0, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws), accumulate);
+  else        bn_bwd_reduce_kernel<1, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws), accumulate);
   int rc = wsl_check_launch("bn_bwd_reduce");
   if (rc) return rc;
-  bn_bwd_apply_kernel<T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
+  if (single) bn_bwd_apply_kernel<0, T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
+  else        bn_bwd_apply_kernel<1, T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
   return wsl_check_launch("bn_bwd_apply");
 }
 
