@@ -287,13 +287,13 @@ def main():
             if meta is not None:
                 d["flops"] += meta[2] * cnt
                 d["bytes"] += meta[3] * cnt
-        detail = sorted(((name, meta[0], meta[1], cnt, ms / cnt, meta[2] / (ms / cnt * 1e-3) / 1e12)
+        detail = sorted(((name, meta[0], meta[1], cnt, ms / cnt, meta[2] / (ms / cnt * 1e-3) / 1e12, meta[3] / (ms / cnt * 1e-3) / 1e9)
                          for (name, meta), (cnt, ms) in agg.items() if meta is not None), key=lambda r: -r[3] * r[4])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "kernel_detail.txt"), "w") as f:
-            f.write("entry kind layer launches avg_ms TFLOP/s\n")
+            f.write("entry kind layer launches avg_ms TFLOP/s algorithmic_GB/s\n")
             for r in detail:
-                f.write(f"{r[0]} {r[1]} {r[2]} {r[3] // n_prof} {r[4]:.4f} {r[5]:.1f}\n")
+                f.write(f"{r[0]} {r[1]} {r[2]} {r[3] // n_prof} {r[4]:.4f} {r[5]:.1f} {r[6]:.0f}\n")
         tot = sum(d["ms"] for d in byname.values())
         launches_per_step = sum(d["launches"] for d in byname.values()) // n_prof
         table = {k: {"launches_per_step": v["launches"] // n_prof, "ms_per_step": round(v["ms"] / n_prof, 4),

@@ -420,16 +420,42 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(
 }
 
 // finalize-only variant: partial rows [nrows][2][C] produced by the convolution epilogue (conv_tc.cu)
+// One block per 16 channels, 16 threads per channel walking the partial rows (fixed order -> deterministic); a single block
+// for all channels took 12 us per layer on the forward critical path.
 __global__ void __launch_bounds__(TPB) bn_finalize_kernel(const float* __restrict__ partials, int nrows, long long P, int C,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* running_mean, float* running_var, long long* nbt, float momentum,
                                                           float eps, float* __restrict__ save, float* __restrict__ ss) {
-  __shared__ double s_fin[2 * 256];
+  constexpr int CB = 16, PARTS = TPB / CB;
   __shared__ double s_part[TPB * 2];
-  bn_finalize_partials(partials, nrows, C, s_fin, s_part);
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    const double mean = s_fin[c] / (double)P;
-    double var = s_fin[C + c] / (double)P - mean * mean;
+  const int cl = threadIdx.x % CB, part = threadIdx.x / CB;
+  const int c = blockIdx.x * CB + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    int bl = part;
+    for (; bl + 7 * PARTS < nrows; bl += 8 * PARTS) {
+      float va[8], vb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        va[u] = __ldcg(&partials[((size_t)(bl + u * PARTS) * 2 + 0) * C + c]);
+        vb[u] = __ldcg(&partials[((size_t)(bl + u * PARTS) * 2 + 1) * C + c]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a += (double)va[u]; b += (double)vb[u]; }
+    }
+    for (; bl < nrows; bl += PARTS) {
+      a += (double)__ldcg(&partials[((size_t)bl * 2 + 0) * C + c]);
+      b += (double)__ldcg(&partials[((size_t)bl * 2 + 1) * C + c]);
+    }
+  }
+  s_part[threadIdx.x * 2 + 0] = a;
+  s_part[threadIdx.x * 2 + 1] = b;
+  __syncthreads();
+  if (threadIdx.x < CB && c < C) {
+    double x = 0.0, y = 0.0;
+    for (int q = 0; q < PARTS; ++q) { x += s_part[(q * CB + cl) * 2]; y += s_part[(q * CB + cl) * 2 + 1]; }
+    const double mean = x / (double)P;
+    double var = y / (double)P - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     save[c] = (float)mean;
@@ -443,7 +469,7 @@ __global__ void __launch_bounds__(TPB) bn_finalize_kernel(const float* __restric
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
     }
   }
-  if (threadIdx.x == 0 && nbt) *nbt += 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
 }
 
 // eval mode: scale/shift from running statistics
@@ -603,26 +629,57 @@ __device__ __forceinline__ BnBwdThread bn_bwd_thread(const BnBwdArgs<T>& a) {
   return t;
 }
 
-// dz (gradient w.r.t. the BN output z) and the raw conv output y of 8 channels of pixel p
-// MODE 0: the single gradient source g0 (straight-line code: the two-pixel unrolled callers get all loads in flight at once);
-// MODE 1: any combination of sources (uniform runtime branches).
+// summed incoming gradient g and the raw conv output y of 8 channels of pixel p.
+// MODE bit 0: g1 present (channel-scaled by cs1 when given), bit 1: pooled gradient present; g0 is required -> straight-line
+// code, so the two-pixel unrolled callers get every load of both pixels in flight before the first use.
+// MODE 4: any combination including a missing g0 (uniform runtime branches).
 template <int MODE, typename T>
 __device__ __forceinline__ void bn_bwd_gather8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&g)[8], float (&yv)[8]) {
   const long long off = (long long)p * a.C + t.c0;
   ld8(a.y + off, yv);
-  if (MODE == 0) {
+  if (MODE < 4) {
     ld8(a.g0 + off, g);
-  } else {
+    if (MODE != 0) {
+      const int x = p % a.W, r = p / a.W, yy = r % a.H, n = r / a.H;
+      float v1[8], vp[8];
+      float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0;
+      uint2 ai = make_uint2(0u, 0u);
+      const long long q = ((long long)(n * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (x >> 1)) * a.C + t.c0;
+      if (MODE & 1) {
+        ld8(a.g1 + off, v1);
+        if (a.cs1) {
+          s0 = *reinterpret_cast<const float4*>(a.cs1 + (long long)n * a.C + t.c0);
+          s1 = *reinterpret_cast<const float4*>(a.cs1 + (long long)n * a.C + t.c0 + 4);
+        }
+      }
+      if (MODE & 2) {
+        ai = *reinterpret_cast<const uint2*>(a.pool_idx + q);
+        ld8(a.gp + q, vp);
+      }
+      if (MODE & 1) {
+        g[0] = fmaf(v1[0], s0.x, g[0]); g[1] = fmaf(v1[1], s0.y, g[1]); g[2] = fmaf(v1[2], s0.z, g[2]); g[3] = fmaf(v1[3], s0.w, g[3]);
+        g[4] = fmaf(v1[4], s1.x, g[4]); g[5] = fmaf(v1[5], s1.y, g[5]); g[6] = fmaf(v1[6], s1.z, g[6]); g[7] = fmaf(v1[7], s1.w, g[7]);
+      }
+      if (MODE & 2) {
+        const int k = ((yy & 1) << 1) | (x & 1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.f;
-    if (a.g0) {
-      float v[8];
-      ld8(a.g0 + off, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] += v[j];
+        for (int j = 0; j < 8; ++j) {
+          const int aj = (j < 4 ? (ai.x >> (8 * j)) : (ai.y >> (8 * (j - 4)))) & 0xff;
+          if (aj == k) g[j] += vp[j];
+        }
+      }
     }
+    return;
   }
-  if (MODE != 0 && (a.g1 || a.gp)) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (a.g0) {
+    float v[8];
+    ld8(a.g0 + off, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += v[j];
+  }
+  if (a.g1 || a.gp) {
     const int x = p % a.W, r = p / a.W, yy = r % a.H, n = r / a.H;
     if (a.g1) {
       float v[8];
@@ -665,7 +722,7 @@ __device__ __forceinline__ void bn_bwd_finish8(const BnBwdArgs<T>& a, const BnBw
 }
 
 template <int MODE, typename T>
-__global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, float* __restrict__ dgamma,
+__global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_reduce_kernel(BnBwdArgs<T> a, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
                                                                float* partials, unsigned* ticket, int accumulate) {
   extern __shared__ float s_red[];
@@ -732,7 +789,7 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(BnBwdArgs<T> a, f
 }
 
 template <int MODE, typename T>
-__global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(BnBwdArgs<T> a, const float* __restrict__ coef,
+__global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_apply_kernel(BnBwdArgs<T> a, const float* __restrict__ coef,
                                                               T* __restrict__ dy) {
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, rows = TPB / t.cg;
@@ -1079,13 +1136,28 @@ static int bn_bwd_launch(const void* y, const float* ss, const float* save, cons
   a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
   const long long P = (long long)N * H * W;
   const int grid = bn_grid(P, C);
-  const bool single = g0 != nullptr && g1 == nullptr && gpool == nullptr;
-  if (single) bn_bwd_reduce_kernel<0, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws), accumulate);
-  else        bn_bwd_reduce_kernel<1, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, reinterpret_cast<unsigned*>(ws), accumulate);
+  const int mode = (g0 == nullptr) ? 4 : ((g1 ? 1 : 0) | (gpool ? 2 : 0));
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws);
+#define WSL_BN_RED(M) bn_bwd_reduce_kernel<M, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, ticket, accumulate)
+#define WSL_BN_APP(M) bn_bwd_apply_kernel<M, T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy)
+  switch (mode) {
+    case 0: WSL_BN_RED(0); break;
+    case 1: WSL_BN_RED(1); break;
+    case 2: WSL_BN_RED(2); break;
+    case 3: WSL_BN_RED(3); break;
+    default: WSL_BN_RED(4); break;
+  }
   int rc = wsl_check_launch("bn_bwd_reduce");
   if (rc) return rc;
-  if (single) bn_bwd_apply_kernel<0, T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
-  else        bn_bwd_apply_kernel<1, T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy);
+  switch (mode) {
+    case 0: WSL_BN_APP(0); break;
+    case 1: WSL_BN_APP(1); break;
+    case 2: WSL_BN_APP(2); break;
+    case 3: WSL_BN_APP(3); break;
+    default: WSL_BN_APP(4); break;
+  }
+#undef WSL_BN_RED
+#undef WSL_BN_APP
   return wsl_check_launch("bn_bwd_apply");
 }
 
@@ -1182,7 +1254,7 @@ WSL_API int wsl_bn_finalize(const float* partials, int nrows, long long P, int C
                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                             float* save, float* ss, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && C <= 256, "wsl_bn_finalize: unsupported channel count %d", C);
-  bn_finalize_kernel<<<1, TPB, 0, stream>>>(partials, nrows, P, C, gamma, beta, running_mean, running_var, num_batches_tracked,
+  bn_finalize_kernel<<<(C + 15) / 16, TPB, 0, stream>>>(partials, nrows, P, C, gamma, beta, running_mean, running_var, num_batches_tracked,
                                             momentum, eps, save, ss);
   return wsl_check_launch("bn_finalize");
 }

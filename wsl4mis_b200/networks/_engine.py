@@ -224,6 +224,11 @@ class UNetExecutor:
                 byts = 2.0 * (cin + cout) * H * W * N
             _lib.PROFILE.meta = (kind, L.name, flops, byts)
 
+    def _tag_bytes(self, kind, L, byts):
+        """Label a bandwidth-bound launch with its algorithmic bytes (bench.py prints GB/s for it)."""
+        if _lib.PROFILE is not None:
+            _lib.PROFILE.meta = (kind, L.name, 0.0, float(byts))
+
     def _untag(self):
         if _lib.PROFILE is not None:
             _lib.PROFILE.meta = None
@@ -327,8 +332,11 @@ class UNetExecutor:
             call("wsl_bn_eval_prepare", bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), C, ss)
         p = L.drop_p if training else 0.0
         seed = self._layer_seed(L)
+        esz = 2 if self.dt == 0 else 4
+        self._tag_bytes("bn_act", L, N * H * W * C * esz * (2.25 if pooled is not None else 2.0))
         call("wsl_bn_act_fwd", y, self.dt, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
              act, pooled, pool_idx)
+        self._untag()
         return save, ss
 
     def bn_bwd(self, L: ConvLayer, y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, dy, N, H, W, slot, tag):
@@ -336,9 +344,13 @@ class UNetExecutor:
         C = L.Cout
         coef = self.buf(slot, tag + ".coef", (2 * C,), torch.float32)
         p = L.drop_p
+        esz = 2 if self.dt == 0 else 4
+        nsrc = (g0 is not None) + (g1 is not None) + 0.25 * (gpool is not None)
+        self._tag_bytes("bn_bwd", L, N * H * W * C * esz * (2 * (1 + nsrc) + 1))      # reduce: y + sources; apply: again + dY
         call("wsl_bn_bwd", y, self.dt, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
              self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
              self.gview(bn.bias), coef, dy, self._ws("bn"), 1 if self._accumulate else 0)
+        self._untag()
 
     def _layer_seed(self, L):
         return (self.layers.index(L) + 1) * 0x9E3779B1
@@ -447,7 +459,9 @@ class UNetExecutor:
                 t = self.buf(slot, f"dec{di}.up{j}.t", (N, hh, ww, C2))
                 self.conv_fwd(c1, [xlow], t, 0, N, hh, ww, C2)
                 u = self.buf(slot, f"dec{di}.up{j}.u", (N, 2 * hh, 2 * ww, C2))
+                self._tag_bytes("up_fwd", c1, N * hh * ww * C2 * (2 if self.dt == 0 else 4) * 5)
                 call("wsl_upsample2x_fwd", t, self.dt, N, hh, ww, C2, u)
+                self._untag()
                 hh, ww = 2 * hh, 2 * ww
                 r = run_block(f"dec{di}.up{j}", blk, [skip, u], hh, ww, None, pool=False)
                 r["xlow"] = xlow
@@ -543,7 +557,9 @@ class UNetExecutor:
                 skip_grads[lvl].append((dskip, drec["cs"][lvl] if drec["cs"] else None))
                 hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
                 dt = B(f"dec{di}.up{j}.dt", (N, hh, ww, C2))
+                self._tag_bytes("up_bwd", c1, N * hh * ww * C2 * (2 if self.dt == 0 else 4) * 5)
                 call("wsl_upsample2x_bwd", du, self.dt, N, hh, ww, C2, dt)
+                self._untag()
                 with self.on_side():
                     self.conv_wgrad(c1, [r["xlow"]], dt, N, hh, ww)
                 da = B(f"dec{di}.up{j}.dxlow", (N, hh, ww, c1.Cin))
