@@ -844,18 +844,41 @@ __global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const T* __restrict
   const int g = threadIdx.x % cg, r = threadIdx.x / cg, c0 = g * 8;
   const int P = N * H * W;
   const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+  auto src = [&](int p, const T*& pa, const T*& pb, const T*& pc, const T*& pd, float& lx, float& ly) {
     const int x = p % W, q = p / W, y = q % H, n = q / H;
     const float sy = ry * (float)y, sx = rx * (float)x;
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
-    const float ly = sy - (float)y0, lx = sx - (float)x0;
-    float a[8], b[8], c[8], d[8], o[8];
+    ly = sy - (float)y0;
+    lx = sx - (float)x0;
     const T* base = t + (long long)n * h * w * C + c0;
-    ld8(base + (y0 * w + x0) * C, a);
-    ld8(base + (y0 * w + x1) * C, b);
-    ld8(base + (y1 * w + x0) * C, c);
-    ld8(base + (y1 * w + x1) * C, d);
+    pa = base + (y0 * w + x0) * C; pb = base + (y0 * w + x1) * C; pc = base + (y1 * w + x0) * C; pd = base + (y1 * w + x1) * C;
+  };
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + stride < P; p += 2 * stride) {      // two output pixels per iteration, all eight loads issued first
+    const T *a0, *b0, *c0p, *d0, *a1, *b1, *c1p, *d1;
+    float lx0, ly0, lx1, ly1;
+    src(p, a0, b0, c0p, d0, lx0, ly0);
+    src(p + stride, a1, b1, c1p, d1, lx1, ly1);
+    float a[8], b[8], c[8], d[8], e[8], f[8], gg[8], hh[8], o[8];
+    ld8(a0, a); ld8(b0, b); ld8(c0p, c); ld8(d0, d);
+    ld8(a1, e); ld8(b1, f); ld8(c1p, gg); ld8(d1, hh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly0) * ((1.f - lx0) * a[j] + lx0 * b[j]) + ly0 * ((1.f - lx0) * c[j] + lx0 * d[j]);
+    st8(u + (long long)p * C + c0, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly1) * ((1.f - lx1) * e[j] + lx1 * f[j]) + ly1 * ((1.f - lx1) * gg[j] + lx1 * hh[j]);
+    st8(u + (long long)(p + stride) * C + c0, o);
+  }
+  if (p < P) {
+    const T *a0, *b0, *c0p, *d0;
+    float lx, ly;
+    src(p, a0, b0, c0p, d0, lx, ly);
+    float a[8], b[8], c[8], d[8], o[8];
+    ld8(a0, a); ld8(b0, b); ld8(c0p, c); ld8(d0, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
@@ -863,7 +886,20 @@ __global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const T* __restrict
   }
 }
 
-// gather form of the transpose: each low-res pixel collects from the <=7x7 high-res pixels that can touch it
+// gather form of the transpose (deterministic): a low-res pixel collects from the <= 5 x 5 high-res pixels whose bilinear
+// footprint touches it.  The first contributing row / column is searched with the forward index arithmetic itself, the five
+// column weights live in registers and the five loads of a row are issued together.
+__device__ __forceinline__ float up_weight(int Q, int in, int out, int i) {
+  if (Q < 0 || Q >= out) return 0.f;
+  int q0, q1;
+  float l;
+  up_src(Q, in, out, q0, q1, l);
+  float wgt = 0.f;
+  if (q0 == i) wgt += 1.f - l;
+  if (q1 == i) wgt += l;
+  return wgt;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const T* __restrict__ du, int N, int h, int w, int C,
                                                              T* __restrict__ dt) {
@@ -874,30 +910,28 @@ __global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const T* __restrict
     const int c0 = (int)(i - p * cg) * 8;
     const int xi = (int)(p % w), yi = (int)((p / w) % h);
     const long long n = p / ((long long)w * h);
+    int Xs = max(0, 2 * xi - 3), Ys = max(0, 2 * yi - 3);
+    for (int k = 0; k < 6 && up_weight(Xs, w, W, xi) == 0.f; ++k) ++Xs;
+    for (int k = 0; k < 6 && up_weight(Ys, h, H, yi) == 0.f; ++k) ++Ys;
+    float wx[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) wx[d] = up_weight(Xs + d, w, W, xi);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int Y = max(0, 2 * yi - 3); Y <= min(H - 1, 2 * yi + 3); ++Y) {
-      int y0, y1;
-      float ly;
-      up_src(Y, h, H, y0, y1, ly);
-      float wy = 0.f;
-      if (y0 == yi) wy += 1.f - ly;
-      if (y1 == yi) wy += ly;
+#pragma unroll 1
+    for (int dy = 0; dy < 5; ++dy) {
+      const float wy = up_weight(Ys + dy, h, H, yi);
       if (wy == 0.f) continue;
-      for (int X = max(0, 2 * xi - 3); X <= min(W - 1, 2 * xi + 3); ++X) {
-        int x0, x1;
-        float lx;
-        up_src(X, w, W, x0, x1, lx);
-        float wx = 0.f;
-        if (x0 == xi) wx += 1.f - lx;
-        if (x1 == xi) wx += lx;
-        if (wx == 0.f) continue;
-        float g[8];
-        ld8(du + ((n * H + Y) * (long long)W + X) * C + c0, g);
-        const float ww = wy * wx;
+      const T* row = du + ((n * H + (Ys + dy)) * (long long)W) * C + c0;
+      float g[5][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, g[j], acc[j]);
+      for (int d = 0; d < 5; ++d) ld8(row + (long long)min(Xs + d, W - 1) * C, g[d]);   // weight 0 where clamped
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const float ww = wy * wx[d];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, g[d][j], acc[j]);
       }
     }
     st8(dt + p * C + c0, acc);

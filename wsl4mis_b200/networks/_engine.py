@@ -137,9 +137,10 @@ class UNetExecutor:
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
-        self._side = None
-        self._on_side = False
-        self._side_dirty = False
+        self._sides = {}                 # named side streams
+        self._side_stack = []            # names of the side streams we are currently issuing on (innermost last)
+        self._side_dirty = set()
+        self.bwd_streams = os.environ.get("WSL4MIS_BWD_STREAMS", "1") != "0"   # aux decoder backward chain on its own stream
         self._stat_bufs = {}
         self._stat_rows = ctypes.c_int(0)
         self._accumulate = False
@@ -170,11 +171,11 @@ class UNetExecutor:
         return self.grads()[1][id(p)]
 
     def _ws(self, tag):
-        return workspace(tag + ("" if not self._on_side else ".side"), self.dev)
+        return workspace(tag + ("" if not self._side_stack else "." + self._side_stack[-1]), self.dev)
 
     def _stat_scratch(self):
         """per-stream scratch for the conv-epilogue BatchNorm partial rows"""
-        key = "side" if self._on_side else "main"
+        key = self._side_stack[-1] if self._side_stack else "main"
         if key not in self._stat_bufs or self._stat_bufs[key].device != self.dev:
             self._stat_bufs[key] = torch.zeros(592 * 2 * 256 + 64, dtype=torch.float32, device=self.dev)   # + ticket word
         return self._stat_bufs[key]
@@ -184,34 +185,41 @@ class UNetExecutor:
     # tensor-core kernels of the other: (a) the aux decoder's forward runs beside the main decoder's, (b) every
     # weight-gradient kernel runs beside the data-gradient -> BatchNorm-backward chain.  Inside a captured CUDA
     # graph the fork/join events become graph edges.
-    def _side_stream(self):
-        if self._side is None or self._side.device != self.dev:
-            self._side = torch.cuda.Stream(device=self.dev)
-        return self._side
+    def _side_stream(self, name="side"):
+        st = self._sides.get(name)
+        if st is None or st.device != self.dev:
+            st = self._sides[name] = torch.cuda.Stream(device=self.dev)
+        return st
 
     @contextlib.contextmanager
-    def on_side(self):
+    def on_side(self, name="side"):
+        """Issue the enclosed launches on the named side stream, ordered after everything issued so far on the CURRENT stream
+        (which may itself be a side stream: weight gradients of the aux-decoder chain fork from that chain)."""
         if not self.multi_stream:
             yield
             return
-        side = self._side_stream()
+        side = self._side_stream(name)
         ev = torch.cuda.Event()
-        ev.record()                      # everything issued so far on the main stream ...
-        side.wait_event(ev)              # ... is visible to the side stream
-        self._on_side = True
+        ev.record()
+        side.wait_event(ev)
+        self._side_stack.append(name)
         try:
             with torch.cuda.stream(side):
                 yield
         finally:
-            self._on_side = False
-            self._side_dirty = True
+            self._side_stack.pop()
+            self._side_dirty.add(name)
 
-    def join_side(self):
-        if self.multi_stream and self._side_dirty:
-            ev = torch.cuda.Event()
-            ev.record(self._side_stream())
-            torch.cuda.current_stream().wait_event(ev)
-            self._side_dirty = False
+    def join_side(self, name=None):
+        """Make the current stream wait for the named side stream (default: all of them)."""
+        if not self.multi_stream:
+            return
+        for nm in ([name] if name is not None else sorted(self._side_dirty)):
+            if nm in self._side_dirty:
+                ev = torch.cuda.Event()
+                ev.record(self._side_stream(nm))
+                torch.cuda.current_stream().wait_event(ev)
+                self._side_dirty.discard(nm)
 
     # ---------------------------------------------------------------- primitive launches
     def _tag(self, kind, L, N, H, W, cin, cout):
@@ -534,11 +542,8 @@ class UNetExecutor:
 
         # ---- decoders ----
         skip_grads = [[] for _ in range(5)]   # per encoder level: list of (grad, cs or None)
-        for di, (ups, oc) in enumerate(self.dec):
-            g = grad_logits[di]
-            drec = rec["dec"][di]
-            if g is None:
-                continue
+
+        def decoder_bwd(di, ups, oc, g, drec):
             if isinstance(g, tuple):                      # ("nhwc16", tensor): already in the executor's layout
                 dl = g[1]
             else:
@@ -565,6 +570,23 @@ class UNetExecutor:
                 da = B(f"dec{di}.up{j}.dxlow", (N, hh, ww, c1.Cin))
                 self.conv_dgrad(c1, 0, dt, da, N, hh, ww)
             skip_grads[4].append((da, drec["cs"][4] if drec["cs"] else None))
+
+        # aux decoder chains run on their own streams beside the main decoder's (HBM-bound BatchNorm backward of one chain
+        # overlaps the tensor-core data gradients of the other); the encoder needs all of them
+        chains = []
+        for di, (ups, oc) in enumerate(self.dec):
+            g = grad_logits[di]
+            if g is None:
+                continue
+            if di > 0 and self.bwd_streams and self.multi_stream:
+                nm = f"dec{di}"
+                with self.on_side(nm):
+                    decoder_bwd(di, ups, oc, g, rec["dec"][di])
+                chains.append(nm)
+            else:
+                decoder_bwd(di, ups, oc, g, rec["dec"][di])
+        for nm in chains:
+            self.join_side(nm)
 
         # ---- encoder ----
         gpool = None
