@@ -121,6 +121,13 @@ int wsl_overlap_counts(const uint8_t* pred, const uint8_t* gt, long long n, int 
 int wsl_rot90(const float* src, long long planes, int S, int k, int accumulate, float* dst, cudaStream_t stream);
 int wsl_ema_update(float* ema, const float* param, long long n, float alpha, cudaStream_t stream);
 
+/* Input pipeline (dataloaders/dataset_semi.py:126-171, RandomGenerator): rot90+flip | rotate(order 0) followed by
+ * zoom(order 0) to OH x OW for B samples read from a resident ragged slice store; `table` holds B rows of
+ * wsl_augment_sample_bytes() bytes: {int64 off; int32 h, w, mode, k, axis, lab_cval; double m00, m01, m10, m11, o0, o1}. */
+int wsl_augment_sample_bytes(void);
+int wsl_augment_batch(const float* images, const uint8_t* labels, const void* table, int B, int OH, int OW, float* out_img,
+                      uint8_t* out_lab, cudaStream_t stream);
+
 /* ---- network operators (networks/unet.py) ---------------------------------------------------------------- */
 
 /* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the

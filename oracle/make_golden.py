@@ -210,9 +210,39 @@ def net_golden(cct, n=2, hw=32, pseed=11, mseed=5, cseed=9):
     print(name, "loss", out["loss"], "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def augment_golden(n=36, out_hw=(48, 56), seed=2022):
+    """Training-sample transform of the reference (dataloaders/dataset_semi.py:146-171) on seeded ragged slices.  The
+    module imports h5py at the top (absent here, unused by the transform): an empty stub module stands in for it."""
+    import random
+    import types
+
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    import warnings
+    warnings.filterwarnings("ignore")
+    from dataloaders import dataset_semi as D
+    import augment_oracle as A
+
+    ims, lbs = A.synth_slices(n, seed)
+    tf = D.RandomGenerator(out_hw)
+    out_i, out_l = [], []
+    for i, (im, lb) in enumerate(zip(ims, lbs)):
+        random.seed(1000 + i)
+        np.random.seed(1000 + i)
+        r = tf({"image": im, "label": lb})
+        out_i.append(r["image"].numpy()[0])
+        out_l.append(r["label"].numpy())
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), n=n, seed=seed, out_hw=np.array(out_hw),
+                        image=np.stack(out_i).astype(np.float32), label=np.stack(out_l).astype(np.uint8))
+    print("augment.npz:", np.stack(out_i).shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "augment":
+        augment_golden()
+        sys.exit(0)
     losses_kat()
     net_golden(False)
     net_golden(True)
+    augment_golden()
