@@ -8,8 +8,9 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-struct Cfg { int m, n, ts, sw, reps, ctas_per_sm, mn; };
+struct Cfg { int m, n, ts, sw, reps, ctas_per_sm, mn, nacc; };
 
+template <int NACC>
 __global__ void __launch_bounds__(128) mma_rate_kernel(Cfg c, uint32_t idesc, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(Cfg c, uint32_t idesc, lo
           } else {
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                         ::"r"(tmu), "l"(ad + koff), "l"(bd + koff), "r"(idesc), "r"((r | k) ? 1u : 0u) : "memory");
+                         ::"r"(tmu + (uint32_t)((k % NACC) * 128)), "l"(ad + koff), "l"(bd + koff), "r"(idesc), "r"((r | k) ? 1u : 0u) : "memory");
           }
         }
       }
@@ -88,7 +89,9 @@ int main() {
   long long* out;
   cudaMalloc(&out, 1024 * sizeof(long long));
   const int smem_bytes = (16 + 32 + 1) * 1024;
-  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaFuncSetAttribute(mma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaFuncSetAttribute(mma_rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaFuncSetAttribute(mma_rate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   printf("mode sw M N ctas/SM cycles/MMA floor(128*N/256) bytes/MMA smemB/clk\n");
   const int ns[] = {16, 32, 64, 128, 256};
   for (int per_sm = 1; per_sm <= 1; ++per_sm)
@@ -97,8 +100,8 @@ int main() {
         for (int m : {128, 64})
           for (int n : ns) {
             if (sw == 32 && n > 64) continue;
-            Cfg c{m, n, ts, sw, 4096, per_sm, 0};
-            mma_rate_kernel<<<148 * per_sm, 128, smem_bytes>>>(c, idesc_bf16(m, n), out);
+            Cfg c{m, n, ts, sw, 4096, per_sm, 0, 1};
+            mma_rate_kernel<1><<<148 * per_sm, 128, smem_bytes>>>(c, idesc_bf16(m, n), out);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s (ts=%d sw=%d m=%d n=%d)\n", cudaGetErrorString(e), ts, sw, m, n); return 1; }
             long long h[1024];
@@ -110,10 +113,23 @@ int main() {
             const double bytes = (ts ? 0 : m * 32) + n * 32;
             printf("%s %3d %3d %3d %d %8.1f %6.1f %6.0f %6.1f issue %6.1f\n", ts ? "TS" : "SS", sw, m, n, per_sm, avg, 128.0 * n / 256, bytes, bytes / avg, iss);
           }
+  for (int nacc : {2, 4})
+    for (int n : {16, 32, 64, 128}) {
+      Cfg c{128, n, 0, 128, 4096, 1, 0, nacc};
+      if (nacc == 2) mma_rate_kernel<2><<<148, 128, smem_bytes>>>(c, idesc_bf16(128, n, 0), out);
+      else mma_rate_kernel<4><<<148, 128, smem_bytes>>>(c, idesc_bf16(128, n, 0), out);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s (nacc)\n", cudaGetErrorString(e)); return 1; }
+      long long h[1024];
+      cudaMemcpy(h, out, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+      double avg = 0;
+      for (int i = 0; i < 148; ++i) avg += (double)h[i];
+      printf("SS accumulators %d M 128 N %3d cycles/MMA %8.1f\n", nacc, n, avg / (148.0 * c.reps));
+    }
   for (int sw : {32, 64, 128})
     for (int n : {16, 32, 64, 128}) {
-      Cfg c{128, n, 0, sw, 4096, 1, 1};
-      mma_rate_kernel<<<148, 128, smem_bytes>>>(c, idesc_bf16(128, n, 1), out);
+      Cfg c{128, n, 0, sw, 4096, 1, 1, 1};
+      mma_rate_kernel<1><<<148, 128, smem_bytes>>>(c, idesc_bf16(128, n, 1), out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error %s (mn sw=%d n=%d)\n", cudaGetErrorString(e), sw, n); return 1; }
       long long h[1024];

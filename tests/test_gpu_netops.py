@@ -47,6 +47,9 @@ CONV_CASES = [
     (2, 64, 32, 16, 0, 16, 3), (1, 64, 64, 16, 16, 16, 3), (2, 32, 16, 32, 0, 64, 3), (1, 32, 32, 32, 32, 32, 3),
     (2, 32, 32, 64, 0, 128, 3), (1, 16, 16, 256, 0, 256, 3), (1, 32, 32, 128, 128, 128, 3), (1, 64, 64, 16, 0, 4, 3),
     (2, 16, 16, 256, 0, 128, 1), (2, 64, 64, 32, 0, 16, 1),
+    # rows of >= 128 pixels with 16 / 32 (4) output channels: the row kernel (filter rows in the MMA's N dimension)
+    (2, 32, 128, 16, 0, 16, 3), (1, 64, 256, 16, 16, 16, 3), (3, 16, 128, 32, 0, 32, 3), (1, 32, 128, 32, 32, 32, 3),
+    (2, 48, 256, 16, 0, 4, 3), (1, 32, 128, 16, 0, 32, 3), (5, 32, 256, 32, 0, 16, 3),
 ]
 
 
