@@ -1362,14 +1362,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
     // costs a few hundred cycles per TMA instruction, and this kernel issues one or two per 128 pixels)
     const uint32_t elected = elect_one();
     const uint32_t a_u = uniform(smem_u32(a_smem)), full_u = uniform(smem_u32(a_full));
-    int q = 0;
+    int s = 0;
+    uint32_t sph = 1;                    // parity to wait for on a_empty[s] (fresh barrier: passes)
     for (int it = 0; it < my_items; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int seg = item % segs, t1 = item / segs, strip = t1 % strips, n = t1 / strips;
       const int y0 = seg * RS, x0 = strip * ROW_PX;
-      for (int i = 0; i < rows_in; ++i, ++q) {
-        const int s = q % STAGES;
-        mbar_wait(&a_empty[s], ((q / STAGES) & 1) ^ 1);
+      for (int i = 0; i < rows_in; ++i) {
+        mbar_wait(&a_empty[s], sph);
         if (elected) {
           const uint32_t bar = full_u + (uint32_t)(s * 8);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(KB * 130 * 32)) : "memory");
@@ -1384,6 +1384,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
           }
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; sph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -1395,10 +1396,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
     const uint32_t w_lo0 = (uniform(smem_u32(w_smem)) >> 4) | 0x10000u;
     mbar_wait(w_bar, 0);
     const int total_rows = my_items * rows_in;
+    int s = 0, slot = 0;
+    uint32_t sph = 0, rph = 1;           // parities: a_full[s] (first completion), e_empty[slot] (fresh barrier passes)
     for (int q = 0; q < total_rows; ++q) {
-      const int s = q % STAGES, slot = q % RING;
-      mbar_wait(&e_empty[slot], ((q / RING) & 1) ^ 1);
-      mbar_wait(&a_full[s], (q / STAGES) & 1);
+      mbar_wait(&e_empty[slot], rph);
+      mbar_wait(&a_full[s], sph);
       tc_fence_after();
       if (elected) {
         const uint32_t d = tmem_u + (uint32_t)(slot * NG);
@@ -1413,6 +1415,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
         umma_commit(&e_full[slot]);
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; sph ^= 1u; }
+      if (++slot == RING) { slot = 0; rph ^= 1u; }
     }
   } else {
     // EW epilogue warps: warp%4 selects the TMEM lane quarter (= 32-pixel group of the strip), (warp-2)/4 the set of output
