@@ -1036,7 +1036,7 @@ struct Wgrad3Params {
 };
 
 template <int CWB, int CWN, int NBOX, int STAGES, bool DYN>
-__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_dy,
+__global__ void __launch_bounds__(NUM_THREADS, (DYN && CWN <= 32) ? 2 : 1) wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_dy,
                                                                    const __grid_constant__ CUtensorMap map_x0,
                                                                    const __grid_constant__ CUtensorMap map_x1, const Wgrad3Params p) {
   using S = Wgrad3Smem<CWB, CWN, NBOX, STAGES, DYN>;
@@ -1171,7 +1171,9 @@ int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensor
     attr = true;
   }
   const int gy = n_tiles * (p.k_tiles0 + p.k_tiles1);
-  int splits = (148 + gy - 1) / gy;
+  // narrow layers are bounded by the per-CTA rate of 32/64-byte TMA rows: two CTAs per SM (TMEM and smem allow it)
+  constexpr int per_sm = (DYN && CWN <= 32 && S::TOTAL <= 100 * 1024) ? 2 : 1;
+  int splits = (148 * per_sm + gy - 1) / gy;
   if (splits > p.nchunks) splits = p.nchunks;
   if (splits < 1) splits = 1;
   dim3 grid(splits, gy);

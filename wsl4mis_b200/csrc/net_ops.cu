@@ -1074,11 +1074,11 @@ inline int grid_for(long long items) {
   return (int)b;
 }
 
-inline int bn_grid(long long P, int C) {
+inline int bn_grid(long long P, int C, int per_sm = 3) {
   // every block should stream >= ~96 KB so that the fixed-order finalize (one pass over all partials) stays negligible
   long long b = (P * C * 2 + 96 * 1024 - 1) / (96 * 1024);
   if (b < 1) b = 1;
-  if (b > 148 * 3) b = 148 * 3;      // one full wave at 3 resident blocks / SM (80 registers, 256 threads)
+  if (b > 148 * per_sm) b = 148 * per_sm;      // one full wave: 3 resident blocks / SM at 80 registers, 2 for the multi-source variants
   return (int)b;
 }
 
@@ -1169,11 +1169,11 @@ static int bn_bwd_launch(const void* y, const float* ss, const float* save, cons
   a.cs1 = cs1; a.gp = (const T*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
   a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
   const long long P = (long long)N * H * W;
-  const int grid = bn_grid(P, C);
   const int mode = (g0 == nullptr) ? 4 : ((g1 ? 1 : 0) | (gpool ? 2 : 0));
+  const int grid = bn_grid(P, C, (mode == 0 || mode == 4) ? 3 : 2);
   unsigned* ticket = reinterpret_cast<unsigned*>(ws);
 #define WSL_BN_RED(M) bn_bwd_reduce_kernel<M, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, ticket, accumulate)
-#define WSL_BN_APP(M) bn_bwd_apply_kernel<M, T><<<bn_grid(P, C), TPB, 0, stream>>>(a, coef, (T*)dy)
+#define WSL_BN_APP(M) bn_bwd_apply_kernel<M, T><<<grid, TPB, 0, stream>>>(a, coef, (T*)dy)
   switch (mode) {
     case 0: WSL_BN_RED(0); break;
     case 1: WSL_BN_RED(1); break;
