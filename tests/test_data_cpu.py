@@ -52,3 +52,18 @@ def test_rotation_matrix_is_scipys():
         a = ndimage.affine_transform(x, rot, off, x.shape, order=0)
         b = ndimage.rotate(x, angle, order=0, reshape=False)
         assert np.array_equal(a, b), angle
+
+
+def test_loader_shards_like_distributed_sampler():
+    """rank::world_size shares of one permutation: disjoint, equal length, together cover every slice (padding by wrapping)."""
+    import torch
+    from torch.utils.data.distributed import DistributedSampler
+    from wsl4mis_b200.dataloaders.dataset import GpuLoader
+    order = torch.randperm(21, generator=torch.Generator().manual_seed(3)).tolist()
+    shares = [GpuLoader.shard(order, r, 4) for r in range(4)]
+    assert all(len(s) == 6 for s in shares)
+    assert set(sum(shares, [])) == set(range(21))
+    ds = list(range(21))
+    for r in range(4):     # same partition rule as torch's sampler applied to the identity permutation
+        want = list(DistributedSampler(ds, num_replicas=4, rank=r, shuffle=False))
+        assert GpuLoader.shard(ds, r, 4) == want

@@ -134,12 +134,25 @@ class GpuLoader:
     """Replaces ``DataLoader(db_train, batch_size, shuffle=True)`` + ``RandomGenerator`` for the training split: yields
     ``{'image': [B,1,H,W] fp32 cuda, 'label': [B,H,W] uint8 cuda, 'idx': [...]}`` (script keys, dataset_semi.py:120-124)."""
 
-    def __init__(self, store, batch_size, output_size=(256, 256), shuffle=True, drop_last=False):
+    def __init__(self, store, batch_size, output_size=(256, 256), shuffle=True, drop_last=False, rank=0, world_size=1):
+        """`batch_size` is per rank.  With world_size > 1 every rank walks the SAME permutation (all ranks seed torch alike, as
+        the scripts do with args.seed) and takes the strided share rank::world_size of it, like DistributedSampler."""
         self.store, self.batch_size, self.shuffle, self.drop_last = store, int(batch_size), shuffle, drop_last
+        self.rank, self.world_size = int(rank), int(world_size)
+        assert 0 <= self.rank < self.world_size
         self.transform = RandomGenerator(output_size)
 
+    @staticmethod
+    def shard(order, rank, world_size):
+        """DistributedSampler's partition: pad the permutation by wrapping to a multiple of world_size, then stride."""
+        if world_size == 1:
+            return list(order)
+        total = (len(order) + world_size - 1) // world_size * world_size
+        padded = list(order) + list(order)[: total - len(order)]
+        return padded[rank:total:world_size]
+
     def __len__(self):
-        n = len(self.store)
+        n = (len(self.store) + self.world_size - 1) // self.world_size
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
@@ -151,6 +164,8 @@ class GpuLoader:
             order = torch.randperm(n, generator=g).tolist()
         else:
             order = list(range(n))
+        order = self.shard(order, self.rank, self.world_size)
+        n = len(order)
         for s in range(0, n, self.batch_size):
             idx = order[s:s + self.batch_size]
             if len(idx) < self.batch_size and self.drop_last:
