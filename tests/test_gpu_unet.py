@@ -256,3 +256,55 @@ def test_rng_dropout_is_fresh_each_step_and_eval_is_deterministic():
     with torch.no_grad():
         c, d = m(x), m(x)
     assert torch.equal(c, d)
+
+
+def test_wide_rows_take_the_row_kernel_and_match_the_oracle():
+    """2 x 1 x 32 x 128: rows of 128 pixels route the full-resolution 16-channel layers (forward with fused statistics, data
+    gradients, out_conv) through conv_row; the whole step is checked against the bf16-storage-emulating oracle."""
+    torch.manual_seed(5)
+    N, H, W = 2, 32, 128
+    p = O.synth_params(1, 4, ("main_decoder", "aux_decoder1"), 21)
+    m = UNet_CCT(1, 4)
+    m.load_state_dict(p)
+    m = m.to(DEV)
+    m.dropout_masks = {i: torch.ones(N, H >> i, W >> i, O.FT[i], dtype=torch.uint8, device=DEV) for i in range(5)}
+    keep = [(torch.arange(c) % 3 != 0).to(torch.uint8).repeat(N, 1) for c in O.FT]
+    m.channel_keep = [k.to(DEV) for k in keep]
+    image, label = O.synth_batch(N, H, W, seed=12, frac=0.05)
+    m.train()
+    o1, o2 = m(image.to(DEV))
+    ce1, s1 = Fn.softmax_pce(o1, label.to(DEV))
+    ce2, s2 = Fn.softmax_pce(o2, label.to(DEV))
+    loss = 0.5 * (ce1 + ce2)
+    loss.backward()
+    torch.cuda.synchronize()
+    names = ["encoder.in_conv.conv_conv.3"] + [f"encoder.down{j}.maxpool_conv.1.conv_conv.3" for j in range(1, 5)]
+    masks = {k: torch.ones(N, O.FT[i], H >> i, W >> i, dtype=torch.uint8) for i, k in enumerate(names)}
+
+    def oracle():
+        leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+        a, b = O.unet_cct_forward(leaves, image, True, masks, keep)
+        l = 0.5 * (O.pce_loss(a, label) + O.pce_loss(b, label))
+        ks = [k for k, v in leaves.items() if v.requires_grad]
+        return a.detach(), b.detach(), l.detach(), dict(zip(ks, torch.autograd.grad(l, [leaves[k] for k in ks])))
+
+    O.QUANT = True
+    try:
+        a, b, lq, gq = oracle()
+    finally:
+        O.QUANT = None
+    for mine, ref in ((o1, a), (o2, b)):
+        err = (mine.detach().float().cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < LOGIT_TOL_Q, err
+    assert abs(loss.item() - lq.item()) < 0.03 * abs(lq.item())
+    named = dict(m.named_parameters())
+    worst = {}
+    for k, ref in gq.items():
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue
+        worst[k] = cosine(named[k].grad.detach().cpu(), ref)
+    # convolution weights: tight; BatchNorm affine gradients are cancelling sums over a 2-image batch and sit at 0.90-0.93 on
+    # this input with either convolution kernel (WSL4MIS_CONV_ROW=0 gives the same numbers), so they get the looser bound
+    bad = {k: round(v, 4) for k, v in worst.items() if v <= (GRAD_COS_Q if named[k].dim() == 4 else 0.85)}
+    print("worst cosines:", sorted(worst.items(), key=lambda kv: kv[1])[:6])
+    assert not bad, bad
