@@ -1309,13 +1309,17 @@ int conv2_dispatch_nt(int nt, const CUtensorMap& a0, const CUtensorMap& a1, cons
 //   warp 1: MMA issuer;  warps 2..5: epilogue (lane = pixel; 1 KB contiguous bf16 per warp and output row).
 // Work item = (image, 128-pixel column strip, segment of RS output rows); persistent CTAs walk the items.
 // ================================================================================================
-constexpr int ROW_PX = 128, ROW_ABYTES = 17 * 256;      // 130 halo pixels x 32 B = 4160 B, padded to a swizzle-atom multiple
+constexpr int ROW_PX = 128;
+// bytes of one input-row buffer: 130 halo pixels x KBW channels, padded to a multiple of the 8-row swizzle atom
+__host__ __device__ constexpr int row_abytes(int kbw) { return ((130 * kbw * 2 + 255) / 256) * 256; }
 
-template <int NT, int RING, int EW>
+template <int NT, int RING, int EW, int KBW>
 __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                                                        const __grid_constant__ CUtensorMap map_b, const ConvV2Params p, const int KB,
                                                        const int RS, const int w_bytes, const int STAGES) {
   constexpr int NG = 3 * NT;                              // accumulator columns of one input row (three filter rows)
+  constexpr int SWB = KBW * 2, ROW_ABYTES = row_abytes(KBW);   // channel block = swizzle span: 32 B (16 ch) or 64 B (32 ch)
+  // (a 64-byte block halves the number of TMA rows per box: the producer is bounded by ~5 cycles per TMA row and CTA)
   constexpr uint32_t TMEM_COLS = (RING * NG <= 256) ? 256 : 512;
   static_assert(RING * NG <= 512 && RING >= 4, "TMEM ring");
   extern __shared__ uint8_t smem_raw[];
@@ -1331,7 +1335,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb0 = p.C0 / 16;
+  const int kb0 = p.C0 / KBW;
   const int strips = p.W / ROW_PX, segs = p.H / RS;
   const int items = p.N * strips * segs;
   const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -1353,11 +1357,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(w_bar, (uint32_t)(KB * 9 * NT * 32));
+      mbar_expect_tx(w_bar, (uint32_t)(KB * 9 * NT * SWB));
       for (int kb = 0; kb < KB; ++kb)
         for (int dx = 0; dx < 3; ++dx)
           for (int dy = 0; dy < 3; ++dy)
-            tma_load_3d(&map_b, w_bar, w_smem + (((kb * 3 + dx) * 3 + dy) * NT) * 32, kb * 16, 0, dy * 3 + dx);
+            tma_load_3d(&map_b, w_bar, w_smem + (((kb * 3 + dx) * 3 + dy) * NT) * SWB, kb * KBW, 0, dy * 3 + dx);
     }
     __syncwarp();
     // row loop: the warp stays converged, one elected lane issues with warp-uniform operands (a divergent lane-0 branch
@@ -1374,11 +1378,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
         mbar_wait(&a_empty[s], sph);
         if (elected) {
           const uint32_t bar = full_u + (uint32_t)(s * 8);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(KB * 130 * 32)) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(KB * 130 * SWB)) : "memory");
           for (int kb = 0; kb < KB; ++kb) {
             const uint32_t dst = a_u + (uint32_t)((s * KB + kb) * ROW_ABYTES);
             const CUtensorMap* mp = (kb < kb0) ? &map_a0 : &map_a1;
-            const int c0 = (kb < kb0 ? kb : kb - kb0) * 16;
+            const int c0 = (kb < kb0 ? kb : kb - kb0) * KBW;
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                 ::"r"(dst), "l"((uint64_t)mp), "r"(bar), "r"(c0), "r"(x0 - 1), "r"(y0 - 1 + i), "r"(n)
@@ -1391,7 +1395,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(NG);
-    constexpr uint32_t d_hi = desc_hi<32>(256);
+    constexpr uint32_t d_hi = desc_hi<SWB>(8 * SWB);
     const uint32_t elected = elect_one();
     const uint32_t tmem_u = uniform(tmem_base);
     const uint32_t a_lo0 = (uniform(smem_u32(a_smem)) >> 4) | 0x10000u;
@@ -1408,10 +1412,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
         const uint32_t d = tmem_u + (uint32_t)(slot * NG);
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t a_lo = a_lo0 + (uint32_t)((s * KB + kb) * (ROW_ABYTES >> 4));
-          const uint32_t w_lo = w_lo0 + (uint32_t)(kb * 3 * ((NG * 32) >> 4));
+          const uint32_t w_lo = w_lo0 + (uint32_t)(kb * 3 * ((NG * SWB) >> 4));
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx)
-            umma_f16_w(d, a_lo + (uint32_t)(dx * 2), d_hi, w_lo + (uint32_t)(dx * ((NG * 32) >> 4)), d_hi, idesc, (kb > 0 || dx > 0) ? 1u : 0u);
+          for (int ks = 0; ks < KBW / 16; ++ks) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              umma_f16_w(d, a_lo + (uint32_t)(dx * (SWB >> 4) + ks * 2), d_hi, w_lo + (uint32_t)(dx * ((NG * SWB) >> 4) + ks * 2), d_hi, idesc,
+                         (kb > 0 || ks > 0 || dx > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&a_empty[s]);
         umma_commit(&e_full[slot]);
@@ -1525,15 +1533,15 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int NT, int RING, int EW>
+template <int NT, int RING, int EW, int KBW>
 int launch_conv_row_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvV2Params& p, int KB, int RS,
                         int STAGES, cudaStream_t stream) {
-  const int w_bytes = ((KB * 9 * NT * 32 + 1023) / 1024) * 1024;
-  const int smem = w_bytes + STAGES * KB * ROW_ABYTES + 1024 + 256;
+  const int w_bytes = ((KB * 9 * NT * KBW * 2 + 1023) / 1024) * 1024;
+  const int smem = w_bytes + STAGES * KB * row_abytes(KBW) + 1024 + 256;
   if (smem > 220 * 1024) { wsl_set_error("conv_row: %d bytes of shared memory needed", smem); return -6; }
   static int attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<NT, RING, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<NT, RING, EW, KBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { wsl_set_error("conv_row: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return -5; }
     attr_bytes = smem;
   }
@@ -1543,23 +1551,24 @@ int launch_conv_row_cfg(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   int gx = 148 * occ;
   if (gx > items) gx = items;
   g_conv2_last_rows = gx;
-  conv_row_kernel<NT, RING, EW><<<gx, 64 + 32 * EW, smem, stream>>>(a0, a1, b, p, KB, RS, w_bytes, STAGES);
+  conv_row_kernel<NT, RING, EW, KBW><<<gx, 64 + 32 * EW, smem, stream>>>(a0, a1, b, p, KB, RS, w_bytes, STAGES);
   return wsl_check_launch("conv_row");
 }
 
 template <int NT>
-int launch_conv_row(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvV2Params& p, int KB, int RS,
+int launch_conv_row(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvV2Params& p, int KB, int RS, int kbw,
                     cudaStream_t stream) {
   // NT = 16: either one CTA per SM owning the whole TMEM (ring of 10 row accumulators, 12 epilogue warps) or two CTAs with
-  // half of it each (ring of 5, 8 epilogue warps); NT = 32: one CTA (ring of 5 x 96 columns), 8 epilogue warps
-  // shared memory in flight: ~80 KB of row buffers per SM are needed to cover the HBM latency at full bandwidth
+  // half of it each (ring of 5, 8 epilogue warps); NT = 32: one CTA (ring of 5 x 96 columns), 8 epilogue warps.
+  // KB counts channel blocks of kbw channels.  Row buffers in flight: ~80 KB per SM cover the HBM latency.
   static const int cfg = [] { const char* e = getenv("WSL4MIS_ROW_CFG"); return e ? atoi(e) : 1; }();
   static const int st_env = [] { const char* e = getenv("WSL4MIS_ROW_STAGES"); return e ? atoi(e) : 0; }();
   if constexpr (NT == 16) {
-    if (cfg == 1 && KB <= 2) return launch_conv_row_cfg<16, 5, 8>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB == 1 ? 10 : 6), stream);
-    return launch_conv_row_cfg<16, 10, 12>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB <= 2 ? 12 : 8), stream);
+    if (cfg == 1 && KB <= 2) return launch_conv_row_cfg<16, 5, 8, 16>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB == 1 ? 10 : 6), stream);
+    return launch_conv_row_cfg<16, 10, 12, 16>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB <= 2 ? 12 : 8), stream);
   } else {
-    return launch_conv_row_cfg<32, 5, 8>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB == 1 ? 16 : KB == 2 ? 12 : 8), stream);
+    if (kbw == 32) return launch_conv_row_cfg<32, 5, 8, 32>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB == 1 ? 12 : 8), stream);
+    return launch_conv_row_cfg<32, 5, 8, 16>(a0, a1, b, p, KB, RS, st_env ? st_env : (KB == 1 ? 16 : KB == 2 ? 12 : 8), stream);
   }
 }
 
@@ -1674,29 +1683,32 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc2: CoutP must be a multiple of 16");
   {   // narrow outputs at >= 128-pixel rows: the row kernel (filter rows in N) is 1.8-2.3x faster per pixel
     static const bool row_on = [] { const char* e = getenv("WSL4MIS_CONV_ROW"); return !(e && e[0] == '0'); }();
-    const int KB = (C0 + C1) / 16;
+    static const bool wide_on = [] { const char* e = getenv("WSL4MIS_ROW_KBW32"); return !(e && e[0] == '0'); }();
+    // channel block per TMA box / swizzle span: 32 channels (64 B) when every source allows it and the output is 32 wide
+    const int kbw = (wide_on && CoutP == 32 && C0 % 32 == 0 && C1 % 32 == 0) ? 32 : 16;
+    const int KB = (C0 + C1) / kbw;
     // row segments of 32 output rows (6 % halo re-reads) unless that leaves fewer than ~4 work items per SM
     const int RS = (H % 32 == 0 && (long long)N * (W / ROW_PX) * (H / 32) >= 4 * 148) ? 32 : 16;
-    if (row_on && ksize == 3 && (CoutP == 16 || CoutP == 32) && W % ROW_PX == 0 && H % 16 == 0 && KB <= 4) {
+    if (row_on && ksize == 3 && (CoutP == 16 || CoutP == 32) && W % ROW_PX == 0 && H % 16 == 0 && (C0 + C1) <= 64) {
       CUtensorMap a0, a1, b;
       {
         long long d[4] = {C0, W, H, N};
-        int bx[4] = {16, 130, 1, 1};
-        int rc = get_map(src0, 4, d, bx, 16, &a0);
+        int bx[4] = {kbw, 130, 1, 1};
+        int rc = get_map(src0, 4, d, bx, kbw, &a0);
         if (rc) return rc;
       }
       if (C1 > 0) {
         long long d[4] = {C1, W, H, N};
-        int bx[4] = {16, 130, 1, 1};
-        int rc = get_map(src1, 4, d, bx, 16, &a1);
+        int bx[4] = {kbw, 130, 1, 1};
+        int rc = get_map(src1, 4, d, bx, kbw, &a1);
         if (rc) return rc;
       } else {
         a1 = a0;
       }
       {
         long long d[3] = {C0 + C1, CoutP, 9};
-        int bx[3] = {16, CoutP, 1};
-        int rc = get_map(wpk_bf16, 3, d, bx, 16, &b);
+        int bx[3] = {kbw, CoutP, 1};
+        int rc = get_map(wpk_bf16, 3, d, bx, kbw, &b);
         if (rc) return rc;
       }
       ConvV2Params p;
@@ -1704,7 +1716,8 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
       p.tiles_x = 0; p.tiles_y = 0; p.ntiles = 0;
       p.out_mode = out_mode; p.desc_mode = 0; p.bias = bias; p.out = out;
       p.stat_partials = (out_mode == 0) ? stat_partials : nullptr;
-      const int rc = (CoutP == 16) ? launch_conv_row<16>(a0, a1, b, p, KB, RS, stream) : launch_conv_row<32>(a0, a1, b, p, KB, RS, stream);
+      const int rc = (CoutP == 16) ? launch_conv_row<16>(a0, a1, b, p, KB, RS, kbw, stream)
+                                   : launch_conv_row<32>(a0, a1, b, p, KB, RS, kbw, stream);
       if (stat_rows_host) *stat_rows_host = g_conv2_last_rows;
       return rc;
     }
