@@ -254,8 +254,8 @@ def gated_crf_loss_unfold(y, image, radius=5, sigma_xy=6.0, sigma_rgb=0.1, weigh
     N, C, H, W = y.shape
     d = 2 * radius + 1
     dt = y.dtype
-    xs = torch.arange(W, dtype=dt).view(1, 1, 1, W).expand(N, 1, H, W) / sigma_xy
-    ys = torch.arange(H, dtype=dt).view(1, 1, H, 1).expand(N, 1, H, W) / sigma_xy
+    xs = torch.arange(W, dtype=dt, device=y.device).view(1, 1, 1, W).expand(N, 1, H, W) / sigma_xy
+    ys = torch.arange(H, dtype=dt, device=y.device).view(1, 1, H, 1).expand(N, 1, H, W) / sigma_xy
     feat = torch.cat([xs, ys, F.adaptive_avg_pool2d(image.to(dt), (H, W)) / sigma_rgb], 1)
     fu = F.unfold(feat, d, 1, radius).view(N, 3, d, d, H, W)
     diff = fu - fu[:, :, radius, radius].view(N, 3, 1, 1, H, W)
