@@ -236,9 +236,47 @@ def augment_golden(n=36, out_hw=(48, 56), seed=2022):
     print("augment.npz:", np.stack(out_i).shape)
 
 
+def heads_golden(n=2, hw=32, pseed=31, mseed=6, cseed=8, nseed=77):
+    """UNet_DS (4 outputs) and UNet_CCT_3H (3 outputs) of the unmodified reference: train-mode forward, sum of the pCE of
+    every head, gradient summaries.  FeatureNoise draws from torch's global RNG: the fixture stores the seed (the only
+    torch-RNG consumers left in the patched forward are the five noise tensors, in feature order)."""
+    from networks.unet import UNet_DS, UNet_CCT_3H
+
+    image, label = O.synth_batch(n, hw, hw, seed=4, frac=0.1)
+    out = {"n": n, "hw": hw, "pseed": pseed, "mseed": mseed, "cseed": cseed, "nseed": nseed,
+           "image": image.numpy(), "label": label.numpy()}
+    ce = torch.nn.CrossEntropyLoss(ignore_index=4)
+    for name, cls, decs, ds in (("ds", UNet_DS, ("decoder",), True),
+                                ("3h", UNet_CCT_3H, ("main_decoder", "aux_decoder1", "aux_decoder2"), False)):
+        p = O.synth_params(1, 4, decs, pseed, ds=ds)
+        m = cls(1, 4)
+        assert list(m.state_dict().keys()) == list(p.keys()), name
+        m.load_state_dict(p)
+        m.train()
+        em = elem_masks(mseed, n, hw, hw)
+        with PatchedDropout(em, chan_masks(cseed, n) if name == "3h" else None):
+            torch.manual_seed(nseed)
+            outs = m(image)
+        loss = sum(ce(o, label.long()) for o in outs)
+        loss.backward()
+        out[f"{name}:loss"] = loss.item()
+        for i, o in enumerate(outs):
+            out[f"{name}:out{i}"] = o.detach().numpy()
+        named = {k: v.grad for k, v in m.named_parameters() if v.grad is not None}
+        keys, stats, _ = grad_summary(named)
+        out[f"{name}:grad_keys"] = np.array(keys)
+        out[f"{name}:grad_stats"] = stats
+        out[f"{name}:no_grad_keys"] = np.array([k for k, v in m.named_parameters() if v.grad is None])
+    np.savez_compressed(os.path.join(OUT, "unet_heads.npz"), **out)
+    print("unet_heads.npz:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if ":out" in k})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "heads":
+        heads_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "augment":
         augment_golden()
         sys.exit(0)
@@ -246,3 +284,4 @@ if __name__ == "__main__":
     net_golden(False)
     net_golden(True)
     augment_golden()
+    heads_golden()

@@ -31,7 +31,7 @@ LRELU = 0.01                           # nn.LeakyReLU default, networks/unet.py:
 # ----------------------------------------------------------------------------------------------
 # parameter construction
 # ----------------------------------------------------------------------------------------------
-def unet_param_shapes(in_chns: int, class_num: int, decoders: Sequence[str] = ("decoder",)):
+def unet_param_shapes(in_chns: int, class_num: int, decoders: Sequence[str] = ("decoder",), ds: bool = False):
     """Ordered {state_dict key: shape} for UNet (decoders=('decoder',)) or UNet_CCT
     (decoders=('main_decoder','aux_decoder1')).  Order follows module registration order in
     networks/unet.py:71-121,286-298,327-339 so it equals ``reference_model.state_dict().keys()``."""
@@ -62,11 +62,14 @@ def unet_param_shapes(in_chns: int, class_num: int, decoders: Sequence[str] = ("
             conv(f"{d}.up{j}.conv1x1", c1, c2, 1)
             block(f"{d}.up{j}.conv.conv_conv", 2 * c2, c2)
         conv(f"{d}.out_conv", FT[0], class_num, 3)
+        if ds:      # Decoder_DS registers the deep-supervision heads after out_conv (networks/unet.py:159-168); dp4 is never used
+            for lvl in (4, 3, 2, 1):
+                conv(f"{d}.out_conv_dp{lvl}", FT[lvl], class_num, 3)
     return shapes
 
 
 def synth_params(in_chns: int, class_num: int, decoders: Sequence[str], seed: int,
-                 dtype=torch.float32) -> Dict[str, torch.Tensor]:
+                 dtype=torch.float32, ds: bool = False) -> Dict[str, torch.Tensor]:
     """Deterministic, torch-RNG-independent parameters (numpy RandomState stream, stable across
     versions) so golden fixtures only need to store a seed.  Scales mimic kaiming-uniform fan-in
     init; BN affine/running stats are randomised so every term of the BN formula is exercised."""
@@ -74,7 +77,7 @@ def synth_params(in_chns: int, class_num: int, decoders: Sequence[str], seed: in
 
     rs = np.random.RandomState(seed)
     out: Dict[str, torch.Tensor] = {}
-    for k, shp in unet_param_shapes(in_chns, class_num, decoders).items():
+    for k, shp in unet_param_shapes(in_chns, class_num, decoders, ds).items():
         if k.endswith("num_batches_tracked"):
             out[k] = torch.zeros((), dtype=torch.long)
             continue
@@ -202,6 +205,49 @@ def unet_cct_forward(p, x, training=True, masks=None, chan_keep=None, new_stats=
     aux_feats = [channel_dropout(f, None if chan_keep is None else chan_keep[i]) for i, f in enumerate(feats)]
     aux = decoder_forward(p, "aux_decoder1", aux_feats, training, new_stats)
     return main, aux
+
+
+# ----------------------------------------------------------------------------------------------
+# other heads of the family (restated ahead of the product, which does not build them yet)
+# ----------------------------------------------------------------------------------------------
+def decoder_ds_forward(p, dname, feats, shape, training, new_stats=None):
+    """Decoder_DS.forward, networks/unet.py:169-190: the Decoder plus a 3x3 class head on the output of up1/up2/up3, each
+    resized to the input size with F.interpolate's default nearest mode.  Returns (dp0, dp1, dp2, dp3)."""
+    x = feats[4]
+    heads = {}
+    for j, skip in enumerate((feats[3], feats[2], feats[1], feats[0]), 1):
+        t = _q(F.conv2d(x, _qw(p[f"{dname}.up{j}.conv1x1.weight"], x), p[f"{dname}.up{j}.conv1x1.bias"]))
+        t = _q(F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True))
+        x = conv_block(p, f"{dname}.up{j}.conv.conv_conv", torch.cat([skip, t], 1), training, 0.0, None, new_stats)
+        if j < 4:
+            lvl = 4 - j                                                                   # up1 -> dp3, up2 -> dp2, up3 -> dp1
+            dp = F.conv2d(x, _qw(p[f"{dname}.out_conv_dp{lvl}.weight"], x), p[f"{dname}.out_conv_dp{lvl}.bias"], padding=1)
+            heads[lvl] = F.interpolate(dp, shape)
+    dp0 = F.conv2d(x, _qw(p[f"{dname}.out_conv.weight"], x), p[f"{dname}.out_conv.bias"], padding=1)
+    return dp0, heads[1], heads[2], heads[3]
+
+
+def unet_ds_forward(p, x, training=True, masks=None, new_stats=None):
+    """UNet_DS.forward, networks/unet.py:319-324."""
+    feats = encoder_forward(p, x, training, masks, new_stats)
+    return decoder_ds_forward(p, "decoder", feats, x.shape[2:], training, new_stats)
+
+
+def feature_noise(x, noise):
+    """FeatureNoise.forward, networks/unet.py:270-283: one uniform(-0.3, 0.3) tensor of shape x.shape[1:] shared by the batch,
+    x * noise + x.  ``noise`` is that tensor (the reference draws it from torch's global RNG)."""
+    return _q(x * noise.unsqueeze(0) + x)
+
+
+def unet_cct_3h_forward(p, x, training=True, masks=None, chan_keep=None, noises=None, new_stats=None):
+    """UNet_CCT_3H.forward, networks/unet.py:363-371, AS WRITTEN: the third head runs ``aux_decoder1`` again on the
+    noise-perturbed features (:370) -- ``aux_decoder2`` owns parameters but never runs."""
+    feats = encoder_forward(p, x, training, masks, new_stats)
+    main = decoder_forward(p, "main_decoder", feats, training, new_stats)
+    aux1 = decoder_forward(p, "aux_decoder1", [channel_dropout(f, None if chan_keep is None else chan_keep[i])
+                                               for i, f in enumerate(feats)], training, new_stats)
+    aux2 = decoder_forward(p, "aux_decoder1", [feature_noise(f, noises[i]) for i, f in enumerate(feats)], training, new_stats)
+    return main, aux1, aux2
 
 
 # ----------------------------------------------------------------------------------------------

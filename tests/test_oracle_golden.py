@@ -132,3 +132,39 @@ def test_sgd_matches_torch():
         opt.step()
         O.sgd_step(params, {"w": gr}, moms, 0.01)
         assert torch.allclose(params["w"], ref.data, atol=1e-7)
+
+
+@pytest.mark.parametrize("which", ["ds", "3h"])
+def test_other_heads_match_reference(golden_dir, which):
+    """UNet_DS (Decoder_DS, four outputs) and UNet_CCT_3H (three outputs, aux_decoder1 run twice as written) against the
+    fixture generated from the unmodified reference classes (restated ahead of the product)."""
+    from torch.distributions.uniform import Uniform
+    g = _load(golden_dir, "unet_heads.npz")
+    n, hw = int(g["n"]), int(g["hw"])
+    image, label = torch.from_numpy(g["image"]), torch.from_numpy(g["label"])
+    masks = _masks(int(g["mseed"]), n, hw, hw)
+    if which == "ds":
+        p = O.synth_params(1, 4, ("decoder",), int(g["pseed"]), ds=True)
+    else:
+        p = O.synth_params(1, 4, ("main_decoder", "aux_decoder1", "aux_decoder2"), int(g["pseed"]))
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+    if which == "ds":
+        outs = O.unet_ds_forward(leaves, image, True, masks)
+    else:
+        torch.manual_seed(int(g["nseed"]))           # the reference's FeatureNoise draws, in feature order (unet.py:369)
+        noises = [Uniform(-0.3, 0.3).sample((O.FT[i], hw >> i, hw >> i)) for i in range(5)]
+        outs = O.unet_cct_3h_forward(leaves, image, True, masks, _chan(int(g["cseed"]), n), noises)
+    assert len(outs) == (4 if which == "ds" else 3)
+    for i, o in enumerate(outs):
+        ref = torch.from_numpy(g[f"{which}:out{i}"])
+        assert (o.detach() - ref).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item()), (which, i)
+    loss = sum(O.pce_loss(o, label) for o in outs)
+    assert abs(loss.item() - float(g[f"{which}:loss"])) < 2e-5 * abs(float(g[f"{which}:loss"]))
+    keys = [str(k) for k in g[f"{which}:grad_keys"]]
+    grads = torch.autograd.grad(loss, [leaves[k] for k in keys], allow_unused=True)
+    for k, gr, (_, asum, l2) in zip(keys, grads, g[f"{which}:grad_stats"]):
+        assert gr is not None, k
+        assert abs(gr.double().norm().item() - l2) < 2e-3 * l2 + 1e-7, k
+        assert abs(gr.double().abs().sum().item() - asum) < 2e-3 * asum + 1e-6, k
+    unused = {str(k).split(".")[0] for k in g[f"{which}:no_grad_keys"]}
+    assert unused == ({"decoder"} if which == "ds" else {"aux_decoder2"})      # out_conv_dp4 / the never-run third decoder
