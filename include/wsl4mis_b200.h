@@ -121,6 +121,11 @@ int wsl_overlap_counts(const uint8_t* pred, const uint8_t* gt, long long n, int 
 int wsl_rot90(const float* src, long long planes, int S, int k, int accumulate, float* dst, cudaStream_t stream);
 int wsl_ema_update(float* ema, const float* param, long long n, float alpha, cudaStream_t stream);
 
+/* Deep-supervision heads (Decoder_DS.forward, networks/unet.py:177,181,185): F.interpolate(x, size) in its default nearest
+ * mode on fp32 [planes,h,w] -> [planes,H,W] maps, and its transpose for the backward pass. */
+int wsl_nearest_resize_fwd(const float* src, long long planes, int h, int w, int H, int W, float* dst, cudaStream_t stream);
+int wsl_nearest_resize_bwd(const float* gdst, long long planes, int h, int w, int H, int W, float* gsrc, cudaStream_t stream);
+
 /* Input pipeline (dataloaders/dataset_semi.py:126-171, RandomGenerator): rot90+flip | rotate(order 0) followed by
  * zoom(order 0) to OH x OW for B samples read from a resident ragged slice store; `table` holds B rows of
  * wsl_augment_sample_bytes() bytes: {int64 off; int32 h, w, mode, k, axis, lab_cval; double m00, m01, m10, m11, o0, o1}. */

@@ -105,3 +105,19 @@ def test_dropin_shim_exposes_the_reference_module_names():
         for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "networks" or k.startswith("networks.")]:
             sys.modules.pop(k)
         sys.modules.update(saved)
+
+
+def test_unet_ds_state_dict_layout_matches_the_reference_order():
+    """UNet_DS registers up1..up4, out_conv, out_conv_dp4..dp1 like networks/unet.py:138-168 (key order pinned through the
+    oracle's shape table, itself checked against the reference module in oracle/make_golden.py:heads_golden)."""
+    import torch
+    from wsl4mis_b200.networks.unet import UNet_DS
+    import wsl_oracle as O
+    m = UNet_DS(1, 4)
+    want = O.unet_param_shapes(1, 4, ("decoder",), ds=True)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(want.keys())
+    assert all(tuple(sd[k].shape) == tuple(v) for k, v in want.items())
+    p = O.synth_params(1, 4, ("decoder",), 3, ds=True)
+    m.load_state_dict(p)
+    assert torch.equal(m.state_dict()["decoder.out_conv_dp4.weight"], p["decoder.out_conv_dp4.weight"])

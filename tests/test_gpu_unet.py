@@ -308,3 +308,105 @@ def test_wide_rows_take_the_row_kernel_and_match_the_oracle():
     bad = {k: round(v, 4) for k, v in worst.items() if v <= (GRAD_COS_Q if named[k].dim() == 4 else 0.85)}
     print("worst cosines:", sorted(worst.items(), key=lambda kv: kv[1])[:6])
     assert not bad, bad
+
+
+def _ds_case(golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "unet_heads.npz"))
+    n, hw = int(g["n"]), int(g["hw"])
+    p = O.synth_params(1, 4, ("decoder",), int(g["pseed"]), ds=True)
+    from wsl4mis_b200.networks.unet import UNet_DS
+    m = UNet_DS(1, 4)
+    m.load_state_dict(p)
+    m = m.to(DEV)
+    if precision == "fp32":
+        m.set_precision("fp32")
+    em = elem_masks_nchw(int(g["mseed"]), n, hw, hw)
+    m.dropout_masks = {i: e.permute(0, 2, 3, 1).contiguous().to(DEV) for i, e in enumerate(em)}
+    return g, p, m, {k: e for k, e in zip(ENC_MASK_KEYS, em)}
+
+
+def test_unet_ds_fp32_mode_matches_the_reference_fixture(golden_dir):
+    """UNet_DS: four outputs, loss = sum of the heads' pCE, every parameter gradient, in the fp32 parity
+    mode against the fixture generated from the unmodified reference class."""
+    g, p, m, _ = _ds_case(golden_dir, "fp32")
+    x, lab = torch.from_numpy(g["image"]).to(DEV), torch.from_numpy(g["label"]).to(DEV)
+    m.train()
+    outs = m(x)
+    assert len(outs) == 4
+    for i, o in enumerate(outs):
+        ref = torch.from_numpy(g[f"ds:out{i}"])
+        err = (o.detach().cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-3, (i, err)
+        assert torch.equal(o.detach().cpu().argmax(1), ref.argmax(1)) or err < 1e-5
+    loss = sum(Fn.softmax_pce(o, lab)[0] for o in outs)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["ds:loss"])) < 1e-3 * abs(float(g["ds:loss"]))
+    named = dict(m.named_parameters())
+    keys = [str(k) for k in g["ds:grad_keys"]]
+    errs = {}
+    for k, (_, asum, l2) in zip(keys, g["ds:grad_stats"]):
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue
+        assert named[k].grad is not None, k
+        errs[k] = abs(named[k].grad.double().norm().item() - l2) / (l2 + 1e-12)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print("[unet_ds fp32] worst gradient-norm errors:", [(k, f"{v:.2e}") for k, v in worst])
+    # convolution weights: 2e-3; BatchNorm affine gradients (cancelling sums, formed from raw moments in bn_bwd_reduce): 1e-2
+    bad = {k: v for k, v in errs.items() if v > (2e-3 if named[k].dim() == 4 else 1e-2)}
+    assert not bad, bad
+    for k in (str(k) for k in g["ds:no_grad_keys"]):        # out_conv_dp4 never runs: no gradient, exactly like autograd
+        assert named[k].grad is None, k
+
+
+def test_unet_ds_bf16_path_matches_the_quant_oracle(golden_dir):
+    g, p, m, om = _ds_case(golden_dir, "bf16")
+    x = torch.from_numpy(g["image"])
+    m.train()
+    with torch.no_grad():
+        outs = m(x.to(DEV))
+    O.QUANT = True
+    try:
+        with torch.no_grad():
+            ref = O.unet_ds_forward(p, x, True, om)
+    finally:
+        O.QUANT = None
+    for i, (o, r) in enumerate(zip(outs, ref)):
+        err = (o.cpu() - r).abs().max().item() / r.abs().max().item()
+        assert err < LOGIT_TOL_Q, (i, err)
+
+
+def test_unet_ds_wide_input_runs_the_tensor_core_heads():
+    """64 x 128 input: the dp1 / dp2 heads take the tcgen05 kernels; outputs against the bf16-emulating oracle, backward runs."""
+    from wsl4mis_b200.networks.unet import UNet_DS
+    N, H, W = 2, 64, 128
+    p = O.synth_params(1, 4, ("decoder",), 41, ds=True)
+    m = UNet_DS(1, 4)
+    m.load_state_dict(p)
+    m = m.to(DEV)
+    m.dropout_masks = {i: torch.ones(N, H >> i, W >> i, O.FT[i], dtype=torch.uint8, device=DEV) for i in range(5)}
+    image, label = O.synth_batch(N, H, W, seed=14, frac=0.05)
+    m.train()
+    outs = m(image.to(DEV))
+    loss = sum(Fn.softmax_pce(o, label.to(DEV))[0] for o in outs)
+    loss.backward()
+    torch.cuda.synchronize()
+    masks = {k: torch.ones(N, O.FT[i], H >> i, W >> i, dtype=torch.uint8) for i, k in enumerate(ENC_MASK_KEYS)}
+    O.QUANT = True
+    try:
+        leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+        ref = O.unet_ds_forward(leaves, image, True, masks)
+        lq = sum(O.pce_loss(r, label) for r in ref)
+        ks = [k for k, v in leaves.items() if v.requires_grad and "dp4" not in k]
+        gq = dict(zip(ks, torch.autograd.grad(lq, [leaves[k] for k in ks])))
+    finally:
+        O.QUANT = None
+    for i, (o, r) in enumerate(zip(outs, ref)):
+        err = (o.detach().cpu() - r.detach()).abs().max().item() / r.detach().abs().max().item()
+        assert err < LOGIT_TOL_Q, (i, err)
+    named = dict(m.named_parameters())
+    for k, r in gq.items():
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue
+        if named[k].dim() == 4:
+            assert cosine(named[k].grad.detach().cpu(), r) > GRAD_COS_Q, k

@@ -841,6 +841,46 @@ __global__ void __launch_bounds__(TPB) ema_update_kernel(float* __restrict__ ema
     ema[i] = ema[i] * alpha + (1.f - alpha) * param[i];
 }
 
+// torch.nn.functional.interpolate(x, size) with the default mode='nearest' on fp32 [planes, h, w] maps (Decoder_DS heads,
+// networks/unet.py:177,181,185): src index = min(floor(dst * (in / out)), in - 1) with the scale in float, as ATen computes it.
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  const int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+
+__global__ void __launch_bounds__(TPB) nearest_resize_fwd_kernel(const float* __restrict__ src, long long planes, int h, int w, int H,
+                                                                 int W, float* __restrict__ dst) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const long long total = planes * H * W;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long long pl = i / ((long long)W * H);
+    dst[i] = src[(pl * h + nearest_src(y, sy, h)) * w + nearest_src(x, sx, w)];
+  }
+}
+
+// its transpose (gather form, deterministic): every source pixel sums the destination pixels that read it
+__global__ void __launch_bounds__(TPB) nearest_resize_bwd_kernel(const float* __restrict__ gdst, long long planes, int h, int w, int H,
+                                                                 int W, float* __restrict__ gsrc) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const long long total = planes * h * w;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int xs = (int)(i % w), ys = (int)((i / w) % h);
+    const long long pl = i / ((long long)w * h);
+    // candidate destination range: dst*scale in [src, src+1)  (one extra on both sides for float rounding, then tested exactly)
+    int y0 = (int)((float)ys / sy) - 1, y1 = (int)((float)(ys + 1) / sy) + 1;
+    int x0 = (int)((float)xs / sx) - 1, x1 = (int)((float)(xs + 1) / sx) + 1;
+    y0 = y0 < 0 ? 0 : y0; x0 = x0 < 0 ? 0 : x0; y1 = y1 > H - 1 ? H - 1 : y1; x1 = x1 > W - 1 ? W - 1 : x1;
+    float acc = 0.f;
+    for (int y = y0; y <= y1; ++y) {
+      if (nearest_src(y, sy, h) != ys) continue;
+      for (int x = x0; x <= x1; ++x)
+        if (nearest_src(x, sx, w) == xs) acc += gdst[(pl * H + y) * W + x];
+    }
+    gsrc[i] = acc;
+  }
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -1039,4 +1079,14 @@ WSL_API int wsl_rot90(const float* src, long long planes, int S, int k, int accu
 WSL_API int wsl_ema_update(float* ema, const float* param, long long n, float alpha, cudaStream_t stream) {
   ema_update_kernel<<<grid_for(n, TPB * 2), TPB, 0, stream>>>(ema, param, n, alpha);
   return wsl_check_launch("ema_update");
+}
+
+WSL_API int wsl_nearest_resize_fwd(const float* src, long long planes, int h, int w, int H, int W, float* dst, cudaStream_t stream) {
+  nearest_resize_fwd_kernel<<<grid_for(planes * H * W, TPB * 2), TPB, 0, stream>>>(src, planes, h, w, H, W, dst);
+  return wsl_check_launch("nearest_resize_fwd");
+}
+
+WSL_API int wsl_nearest_resize_bwd(const float* gdst, long long planes, int h, int w, int H, int W, float* gsrc, cudaStream_t stream) {
+  nearest_resize_bwd_kernel<<<grid_for(planes * h * w, TPB), TPB, 0, stream>>>(gdst, planes, h, w, H, W, gsrc);
+  return wsl_check_launch("nearest_resize_bwd");
 }

@@ -112,6 +112,7 @@ class UNetExecutor:
             cb = getattr(encoder, f"down{i}").maxpool_conv[1]
             self.enc_blocks.append(block(f"encoder.down{i}", cb.conv_conv, [ft[i - 1]]))
         self.dec = []
+        self.ds_heads = []
         for d in decoders:
             ups = []
             for j in range(1, 5):
@@ -123,8 +124,23 @@ class UNetExecutor:
             oc = ConvLayer("out_conv", d.out_conv, None, 0.0, [d.out_conv.in_channels])
             self.layers.append(oc)
             self.dec.append((ups, oc))
+            # deep-supervision heads of Decoder_DS (unet.py:159-168): a 3x3 class head on the output of up1 / up2 / up3
+            # (index j = 0, 1, 2 <-> out_conv_dp3 / dp2 / dp1); out_conv_dp4 owns parameters but never runs
+            heads = {}
+            if hasattr(d, "out_conv_dp3"):
+                for j, lvl in enumerate((3, 2, 1)):
+                    hc = getattr(d, f"out_conv_dp{lvl}")
+                    heads[j] = ConvLayer(f"out_conv_dp{lvl}", hc, None, 0.0, [hc.in_channels])
+                    self.layers.append(heads[j])
+            self.ds_heads.append(heads)
         self.n_class = decoders[0].out_conv.out_channels
         self.params = [p for p in model.parameters()]
+        used = set()
+        for L in self.layers:
+            used.update(id(t) for t in (L.conv.weight, L.conv.bias))
+            if L.bn is not None:
+                used.update(id(t) for t in (L.bn.weight, L.bn.bias))
+        self.used_param_ids = used        # parameters no launch touches (Decoder_DS.out_conv_dp4) get no gradient, like autograd
         self._gflat = None
         self._gviews = None
         self._bufs: Dict = {}
@@ -475,6 +491,12 @@ class UNetExecutor:
                 r["xlow"] = xlow
                 drec["ups"].append(r)
                 xlow = r["a2"]
+                if j in self.ds_heads[di]:       # Decoder_DS: class head on this level, nearest-resized to the input size
+                    small = self.buf(slot, f"dec{di}.dp{j}.small", (N, self.n_class, hh, ww), torch.float32)
+                    self.conv_fwd(self.ds_heads[di][j], [xlow], small, 1, N, hh, ww, self.n_class)
+                    full = torch.empty((N, self.n_class, H, W), dtype=torch.float32, device=self.dev)
+                    call("wsl_nearest_resize_fwd", small, N * self.n_class, hh, ww, H, W, full)
+                    drec.setdefault("dp", {})[j] = full
             self.conv_fwd(oc, [xlow], outs[di], 1, N, H, W, self.n_class)
             drec["xlast"] = xlow
             return drec
@@ -487,6 +509,11 @@ class UNetExecutor:
         if not (defer_join and need_grad and self.defer_aux):
             self.join_side()           # otherwise backward() joins: the aux outputs must not be read before that
         rec["dec"] = drecs
+        # deep-supervision outputs follow the decoders' main outputs: (dp1, dp2, dp3) = heads of up3, up2, up1 (unet.py:190)
+        for di, heads in enumerate(self.ds_heads):
+            if heads:
+                self.join_side()
+                outs = outs + [drecs[di]["dp"][j] for j in (2, 1, 0)]
         if need_grad:
             self._recs[slot] = rec
         return outs, slot
@@ -542,6 +569,14 @@ class UNetExecutor:
 
         # ---- decoders ----
         skip_grads = [[] for _ in range(5)]   # per encoder level: list of (grad, cs or None)
+        # gradients of the deep-supervision outputs (they follow the decoders' main outputs in forward()'s list)
+        ds_grads, nxt = {}, len(self.dec)
+        for di, heads in enumerate(self.ds_heads):
+            if heads:
+                for j in (2, 1, 0):
+                    if nxt < len(grad_logits) and grad_logits[nxt] is not None:
+                        ds_grads[(di, j)] = grad_logits[nxt]
+                    nxt += 1
 
         def decoder_bwd(di, ups, oc, g, drec):
             if isinstance(g, tuple):                      # ("nhwc16", tensor): already in the executor's layout
@@ -557,7 +592,20 @@ class UNetExecutor:
             for j in range(3, -1, -1):
                 c1, blk = ups[j]
                 r = drec["ups"][j]
-                dskip, du = block_bwd(f"dec{di}.up{j}", blk, r, da)
+                gh = ds_grads.get((di, j))
+                dh = None
+                if gh is not None:                # gradient arriving at the deep-supervision head of this level
+                    hl = self.ds_heads[di][j]
+                    hh_, ww_, Ch = r["h"], r["w"], hl.Cin
+                    gs = B(f"dec{di}.dp{j}.gs", (N, self.n_class, hh_, ww_), torch.float32)
+                    call("wsl_nearest_resize_bwd", gh.contiguous(), N * self.n_class, hh_, ww_, H, W, gs)
+                    dl16 = B(f"dec{di}.dp{j}.dl", (N, hh_, ww_, 16))
+                    call("wsl_nchw_f32_to_nhwc", gs, N, self.n_class, hh_, ww_, 16, dl16, self.dt)
+                    with self.on_side():
+                        self.conv_wgrad(hl, [r["a2"]], dl16, N, hh_, ww_)
+                    dh = B(f"dec{di}.dp{j}.dh", (N, hh_, ww_, Ch))
+                    self.conv_dgrad(hl, 0, dl16, dh, N, hh_, ww_)
+                dskip, du = block_bwd(f"dec{di}.up{j}", blk, r, da, dh)
                 lvl = 3 - j
                 skip_grads[lvl].append((dskip, drec["cs"][lvl] if drec["cs"] else None))
                 hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
@@ -576,6 +624,8 @@ class UNetExecutor:
         chains = []
         for di, (ups, oc) in enumerate(self.dec):
             g = grad_logits[di]
+            if g is None and any(k[0] == di for k in ds_grads):     # only deep-supervision heads were used in the loss
+                g = torch.zeros((N, self.n_class, H, W), dtype=torch.float32, device=self.dev)
             if g is None:
                 continue
             if di > 0 and self.bwd_streams and self.multi_stream:

@@ -119,7 +119,8 @@ class _NetFn(torch.autograd.Function):
         ex = ctx.ex
         ex.backward(ctx.slot, list(gouts))
         views = ex.grads()[1]
-        return (None, None, None, None, None, None) + tuple(views[id(p)].clone() for p in ex.params)
+        return (None, None, None, None, None, None) + tuple(views[id(p)].clone() if id(p) in ex.used_param_ids else None
+                                                            for p in ex.params)
 
 
 class _Holder:
@@ -130,12 +131,13 @@ class _Holder:
 class _PlannedNet(nn.Module):
     _decoders = ()
     _aux = ()
+    _decoder_cls = Decoder
 
     def _build(self, in_chns, class_num):
         p = _params(in_chns, class_num)
         self.encoder = Encoder(p)
         for name in self._decoders:
-            setattr(self, name, Decoder(p))
+            setattr(self, name, self._decoder_cls(p))
         self._holder = None
         self.dropout_masks = None      # {encoder level: uint8 NHWC keep-mask}  (tests / parity runs)
         self.channel_keep = None       # [five [N,C] keep masks]               (tests / parity runs)
@@ -224,16 +226,34 @@ class _OffPath(nn.Module):
         raise NotImplementedError(f"{type(self).__name__} is outside the accelerated hot path (SURVEY 8(f) rank 4)")
 
 
-class Decoder_DS(_OffPath):
-    pass
+class Decoder_DS(Decoder):
+    """reference unet.py:138-190: the Decoder plus 3x3 class heads on the outputs of up1 / up2 / up3 (out_conv_dp3 / dp2 / dp1),
+    each resized to the input size by nearest interpolation.  ``out_conv_dp4`` is registered (state_dict parity) and, as in
+    the reference, never used."""
+
+    def __init__(self, params):
+        super().__init__(params)
+        f = self.ft_chns
+        for lvl in (4, 3, 2, 1):
+            setattr(self, f"out_conv_dp{lvl}", nn.Conv2d(f[lvl], self.n_class, kernel_size=3, padding=1))
 
 
 class Decoder_URDS(_OffPath):
     pass
 
 
-class UNet_DS(_OffPath):
-    pass
+class UNet_DS(_PlannedNet):
+    """reference unet.py:306-324: forward returns (dp0, dp1, dp2, dp3), all at the input resolution."""
+    _decoders = ("decoder",)
+    _aux = (False,)
+    _decoder_cls = Decoder_DS
+
+    def __init__(self, in_chns, class_num):
+        super().__init__()
+        self._build(in_chns, class_num)
+
+    def forward(self, x):
+        return self._run(x)
 
 
 class UNet_CCT_3H(_OffPath):
