@@ -67,3 +67,11 @@ def test_loader_shards_like_distributed_sampler():
     for r in range(4):     # same partition rule as torch's sampler applied to the identity permutation
         want = list(DistributedSampler(ds, num_replicas=4, rank=r, shuffle=False))
         assert GpuLoader.shard(ds, r, 4) == want
+
+
+def test_sample_table_layout_matches_the_kernel_struct():
+    """The numpy record the host fills per sample must be byte-compatible with AugSample in csrc/data_ops.cu."""
+    from wsl4mis_b200._lib import LIB
+    from wsl4mis_b200.dataloaders.dataset import _SAMPLE
+    assert LIB.load().wsl_augment_sample_bytes() == _SAMPLE.itemsize == 80
+    assert _SAMPLE.fields["off"][1] == 0 and _SAMPLE.fields["h"][1] == 8 and _SAMPLE.fields["m00"][1] == 32
