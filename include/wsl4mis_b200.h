@@ -11,9 +11,11 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*-compatible handle), never
  *     allocates, never synchronises; the caller owns all buffers;
  *   - return 0 on success, negative on error; wsl_last_error() returns a thread-local message;
- *   - "act" tensors are channels-last (NHWC); their storage type is bf16 (`dtype` 0, the fast tensor-core path) or
- *     fp32 (`dtype` 1, the reference-accurate parity mode on the CUDA-core kernels); logits / probabilities /
- *     losses are fp32 NCHW;
+ *   - "act" tensors are channels-last (NHWC); their storage type is bf16 (`dtype` 0, the fast tensor-core path),
+ *     fp32 (`dtype` 1: the reference-accurate parity modes -- CUDA-core direct convolutions, or the fp16 hi/lo split
+ *     tensor-core convolutions wsl_conv_tc_split / wsl_wgrad_tc_split) or fp16 (`dtype` 2: same tcgen05 kind::f16 rate as
+ *     bf16 with an 11-bit mantissa; gradients then travel multiplied by a power-of-two loss scale chosen by the caller);
+ *     logits / probabilities / losses are fp32 NCHW;
  *   - `ws` is a caller-provided workspace of wsl_workspace_floats() floats, zero-initialised ONCE by the
  *     caller (kernels leave its ticket words zero again); one workspace must not be shared by two kernels
  *     that may run concurrently.
@@ -43,11 +45,11 @@ int wsl_softmax_pce_fwd(const float* logits, const uint8_t* label, float* probs,
 
 /* d(w_ce*pCE + <gprobs*gprobs_scale, softmax(logits)>)/dlogits, times *grad_out (NULL -> 1).
  * Replaces autograd through softmax / log_softmax+nll_loss.  label/gprobs may be NULL.  Either output may be NULL:
- * dlogits = fp32 NCHW (API layout), dlogits_nhwc16_bf16 = channels-last bf16 padded to 16 channels (the layout the
- * out_conv gradient kernels consume; saves a conversion pass in the fused step). */
+ * dlogits = fp32 NCHW (API layout), dlogits_nhwc16 = channels-last bf16 / fp16 (dtype16 0 / 2) padded to 16 channels (the
+ * layout the out_conv gradient kernels consume; saves a conversion pass in the fused step). */
 int wsl_head_bwd(const float* probs, const uint8_t* label, const float* ce_stats, const float* grad_out,
                  float w_ce, const float* gprobs, float gprobs_scale, int N, int C, int H, int W,
-                 int ignore_index, float* dlogits, void* dlogits_nhwc16_bf16, cudaStream_t stream);
+                 int ignore_index, float* dlogits, void* dlogits_nhwc16, int dtype16, cudaStream_t stream);
 
 /* ModelLossSemsegGatedCRF.forward(y, [{'weight':w,'xy':sxy,'rgb':srgb}], radius, image, H, W)['loss']:
  * utils/gate_crf_loss.py:20-117 (fast path: no masks, Potts).  Also emits d loss / d y into gprobs (may be
@@ -137,8 +139,9 @@ int wsl_augment_batch(const float* images, const uint8_t* labels, const void* ta
 
 /* nn.Conv2d(k=3,pad=1)/(k=1) forward on CUDA cores (unet.py:19,23,55,120); with dgrad-packed weights also the
  * data gradient.  Two channels-last sources model torch.cat([x2,x1],1) (unet.py:67).
- * out_mode 0: bf16 NHWC with CoutStore channels; 1: fp32 NCHW with CoutStore channels; 2: fp32 NHWC.
- * src_f32: sources are fp32 (a single-channel image, or fp32 NHWC activations with C %% 8 == 0). */
+ * out_mode 0: bf16 NHWC with CoutStore channels; 1: fp32 NCHW with CoutStore channels; 2: fp32 NHWC; 3: fp16 NHWC.
+ * src_f32 (a dtype code): 1 = sources are fp32 (a single-channel image, or fp32 NHWC activations with C %% 8 == 0),
+ * 0 = bf16, 2 = fp16; likewise dy_f32 of the weight gradient. */
 int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, int src_f32, const float* wpk,
                     const float* bias, void* out, int out_mode, int N, int H, int W, int CinP, int CoutP,
                     int CoutStore, int ksize, cudaStream_t stream);
@@ -154,16 +157,17 @@ int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, i
 int wsl_wgrad_first(const float* x, const void* dy, int dtype, float* dw, int N, int H, int W, int Cout,
                     cudaStream_t stream);
 
-/* tcgen05 implicit-GEMM convolution (conv_tc.cu): same contract as wsl_conv_direct for bf16 NHWC sources with
- * channel counts that are multiples of 16.  wpk_bf16: [taps][CoutP][CinP] (K-major).  Requires wsl_tc_available(). */
+/* tcgen05 implicit-GEMM convolution (conv_tc.cu): same contract as wsl_conv_direct for 16-bit NHWC sources (dtype 0 = bf16,
+ * 2 = fp16: operands, packed weights and out_mode-0 outputs all have that type) with channel counts that are multiples
+ * of 16.  wpk_bf16: [taps][CoutP][CinP] (K-major).  Requires wsl_tc_available(). */
 int wsl_tc_available(void);
 int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
-                void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
+                void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype,
                 cudaStream_t stream);
 /* v2 of the same convolution: persistent CTAs, weights resident in shared memory, one halo load per pixel tile whose
  * nine taps are row-shifted UMMA descriptor views (no reload).  Same contract; needs W % 8 == 0 and H % 16 == 0. */
 int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias,
-                 void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize,
+                 void* out, int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype,
                  float* stat_partials, int* stat_rows_host, cudaStream_t stream);
 /* stat_partials (optional, device, >= 592*2*CoutP floats): per-CTA sum / sum-of-squares rows of the stored outputs for the
  * following BatchNorm; *stat_rows_host (optional, HOST int) receives the number of rows written.  wsl_bn_finalize turns
@@ -174,13 +178,30 @@ int wsl_bn_finalize(const float* partials, int nrows, long long P, int C, const 
 /* tcgen05 weight gradient (conv_tc.cu): dw (fp32, torch layout [CoutReal][C0+C1][k][k]) += dY^T * X over all pixels.
  * Bias gradients are NOT produced here (see wsl_channel_sum). */
 int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                 int W, int CoutReal, int ksize, cudaStream_t stream);
+                 int W, int CoutReal, int ksize, int dtype, cudaStream_t stream);
 /* v2 of the 3x3 weight gradient: one halo load of X per 16x8 pixel chunk, nine row-shifted descriptor views. */
 int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                  int W, int CoutReal, int ksize, cudaStream_t stream);
+                  int W, int CoutReal, int ksize, int dtype, cudaStream_t stream);
 /* v3: filter columns ride in the MMA's M dimension (A = X halo with one-pixel group stride, B = dY, N = Cout tile). */
 int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                  int W, int CoutReal, int ksize, cudaStream_t stream);
+                  int W, int CoutReal, int ksize, int dtype, cudaStream_t stream);
+
+/* fp16 hi/lo split ("fp16x3") tensor-core parity mode: the reference computes in fp32 (unet.py:18-26); here an fp32 value
+ * travels as hi = fp16(v), lo = fp16(v - hi) and a product is a_hi*b_hi + a_lo*b_hi + a_hi*b_lo on kind::f16 with fp32
+ * accumulation (22 significant bits).  wsl_split_f32: fp32 NHWC [P][C0] (+ [P][C1] concatenated) -> fp16 [P][2*(C0+C1)]
+ * (hi plane | lo plane) of v * 2^k, k chosen per call so that max|v| * 2^k lies in [2^13, 2^14) (fp16's exponent range would
+ * otherwise cost small values their lo bits); consumers take &scale3[1] = 2^-k as inv_scale.  wsl_pack_split_weights: torch-layout fp32 weight -> f3 = fp16 [T][CoutP][3*CinP] (hi|hi|lo along
+ * K, forward) and, for the input-channel slice, d3 = fp16 [T][SliceP][3*CoutP] (taps flipped, data gradient).
+ * wsl_conv_tc_split: conv of a staged tensor with such weights, out fp32 NHWC (out_mode 2) or NCHW (1); needs W %% 16 == 0,
+ * H %% 8 == 0.  wsl_wgrad_tc_split: dw += three accumulating weight-gradient launches on the staged X / dY planes. */
+int wsl_split_f32(const float* src0, int C0, const float* src1, int C1, long long P, void* dst, float* scale3,
+                  cudaStream_t stream);   /* scale3 (3 floats): receives {2^k, 2^-k, scratch}; dst holds the planes of v * 2^k */
+int wsl_pack_split_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin, int ci_count,
+                           void* f3, void* d3, cudaStream_t stream);
+int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scale, const void* wpk3, const float* bias, float* out,
+                      int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream);
+int wsl_wgrad_tc_split(const void* x_staged, int Cin, const float* x_inv_scale, const void* dy_staged, int CoutP,
+                       const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
 /* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
 int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, cudaStream_t stream);
 
@@ -216,16 +237,18 @@ int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long* seed_pt
 int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream);
 
 /* layout helpers at the API boundary */
-int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, cudaStream_t stream);
+int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, float scale,
+                         cudaStream_t stream);   /* dst = scale * src (the loss scale of the fp16 modes; 1 otherwise) */
 int wsl_nhwc_to_nchw_f32(const void* src, int dtype, int N, int C, int H, int W, float* dst, cudaStream_t stream);
 
 /* fp32 torch-layout conv weight -> packed operands (any output may be NULL), see net_ops.cu */
 int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,
-                          int ci_count, float* wf, float* wd, void* bf, void* bd, cudaStream_t stream);
+                          int ci_count, float* wf, float* wd, void* bf, void* bd, int dtype16, cudaStream_t stream);
 
 /* all layers in one launch: table = n_entries x 13 int64 {w, wf, wd, bf, bd, Cout, Cin, T, CoutP, CinP, ci_begin,
  * ci_count, first_item} in device memory (pointers as integers), items = T*CoutP*CinP per entry */
-int wsl_pack_conv_weights_batched(const long long* table, int n_entries, long long total_items, cudaStream_t stream);
+int wsl_pack_conv_weights_batched(const long long* table, int n_entries, long long total_items, int dtype16,
+                                  cudaStream_t stream);   /* dtype16: 0 = bf16, 2 = fp16 for the 16-bit packs bf / bd */
 
 /* optim.SGD(lr, momentum, weight_decay).step() over a flat fp32 buffer (train_weakly_supervised_pCE_2D.py:79-80,104);
  * lr is read from lr_ptr (device) when non-NULL so a captured CUDA graph follows the poly schedule (:106-108);

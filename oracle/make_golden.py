@@ -86,6 +86,78 @@ def grad_summary(named_grads):
     return keys, np.asarray(stats, dtype=np.float64), small
 
 
+def script_function(script, name):
+    """A script-local function of the reference (the scripts parse argv and import tensorboardX at module level, so they cannot
+    be imported): its `def` block is cut out of the UNMODIFIED source text and exec'd in a namespace holding torch / F."""
+    import re
+    src = open(os.path.join(REF, script)).read()
+    m = re.search(r"^def %s\(.*?(?=^\S)" % name, src, flags=re.S | re.M)
+    assert m, (script, name)
+    ns = {"torch": torch, "F": F, "np": np, "nn": torch.nn}
+    exec(compile(m.group(0), script, "exec"), ns)
+    return ns[name]
+
+
+def losses_api():
+    """API-surface losses of utils/losses.py that no WSS script calls on the hot path (kept importable by wsl4mis_b200.utils.losses)."""
+    from utils import losses as RL
+    g = torch.Generator().manual_seed(4321)
+    a, b = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    tgt = torch.randint(0, 4, (2, 8, 8), generator=g)
+    out = {"a": a.numpy(), "b": b.numpy(), "target": tgt.numpy()}
+    sa, sb = torch.softmax(a, 1), torch.softmax(b, 1)
+    out["dice_loss1"] = np.float64(RL.dice_loss1(sa[:, 1], sb[:, 1]).item())
+    out["softmax_dice_loss"] = np.float64(RL.softmax_dice_loss(a, b).item())
+    out["softmax_kl_loss"] = np.float64(RL.softmax_kl_loss(a, b).item())
+    out["softmax_kl_loss_sigmoid"] = np.float64(RL.softmax_kl_loss(a, b, sigmoid=True).item())
+    out["focal"] = np.float64(RL.FocalLoss(gamma=2)(a, tgt).item())
+    out["focal_alpha_sum"] = np.float64(RL.FocalLoss(gamma=1.5, alpha=[0.1, 0.2, 0.3, 0.4], size_average=False)(a, tgt).item())
+    # SizeLoss sums over dims (2, 3) of a 5-D volume and assigns the per-sample label counts along the LAST axis
+    # (losses.py:254-260): it only runs when #distinct labels == D; reproduced as written
+    vol = torch.randn(2, 3, 4, 4, 3, generator=g)
+    vt = torch.randint(0, 3, (2, 1, 4, 4, 3), generator=g)
+    vt[:, 0, 0, 0, :3] = torch.arange(3)          # every class occurs in every sample
+    out["vol"], out["vol_target"] = vol.numpy(), vt.numpy()
+    out["size_loss"] = np.float64(RL.SizeLoss(0.1)(vol, vt).item())
+    feats = torch.nn.functional.normalize(torch.randn(6, 2, 16, generator=g), dim=2)
+    labels = torch.tensor([0, 1, 0, 2, 1, 2])
+    out["feats"], out["feat_labels"] = feats.numpy(), labels.numpy()
+    out["supcon_labels"] = np.float64(RL.SupConLoss()(feats, labels).item())
+    out["supcon_simclr"] = np.float64(RL.SupConLoss()(feats).item())
+    out["supcon_one"] = np.float64(RL.SupConLoss(contrast_mode="one")(feats, labels).item())
+    np.savez_compressed(os.path.join(OUT, "losses_api.npz"), **out)
+    print("losses_api:", {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
+
+
+def crf_general():
+    """ModelLossSemsegGatedCRF beyond the scripts' argument pattern (gate_crf_loss.py:20-188): two kernel descriptors, radius 3,
+    a modality at twice the prediction resolution (area downsampling), source / destination masks, kernel visualisation."""
+    from utils.gate_crf_loss import ModelLossSemsegGatedCRF
+    g = torch.Generator().manual_seed(99)
+    y = torch.softmax(torch.randn(2, 3, 12, 20, generator=g), 1).requires_grad_(True)
+    sample = torch.rand(2, 2, 24, 40, generator=g)
+    desc = [{"weight": 0.9, "xy": 6, "rgb": 0.1}, {"weight": 0.1, "xy": 4}]
+    ms = (torch.rand(2, 1, 12, 20, generator=g) > 0.2).float()
+    md = (torch.rand(2, 1, 24, 40, generator=g) > 0.1).float()
+    out = {"y": y.detach().numpy(), "sample": sample.numpy(), "mask_src": ms.numpy(), "mask_dst": md.numpy()}
+    m = ModelLossSemsegGatedCRF()
+    r = m(y, desc, 3, sample, 24, 40)
+    (gy,) = torch.autograd.grad(r["loss"], y)
+    out["plain:loss"], out["plain:grad"] = np.float64(r["loss"].item()), gy.numpy()
+    r = m(y, desc, 3, sample, 24, 40, mask_src=ms.clone(), mask_dst=md.clone(), out_kernels_vis=True)
+    (gy,) = torch.autograd.grad(r["loss"], y)
+    out["masked:loss"], out["masked:grad"], out["masked:vis"] = np.float64(r["loss"].item()), gy.numpy(), r["kernels_vis"].detach().numpy()
+    r = m(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 2, sample[:, :1, ::2, ::2].contiguous(), 12, 20)
+    out["r2:loss"] = np.float64(r["loss"].item())
+    try:
+        m(y, desc, 3, sample, 24, 40, compatibility=torch.ones(3, 3) - torch.eye(3))
+        out["compat:error"] = np.array("none")
+    except Exception as e:                      # gate_crf_loss.py:105 calls `.diag.sum()` on a bound method
+        out["compat:error"] = np.array(type(e).__name__)
+    np.savez_compressed(os.path.join(OUT, "crf_general.npz"), **out)
+    print("crf_general:", {k: (float(v) if np.ndim(v) == 0 and v.dtype.kind == "f" else str(v) if np.ndim(v) == 0 else v.shape) for k, v in out.items()})
+
+
 def losses_kat():
     from utils import losses as RL
     from utils.gate_crf_loss import ModelLossSemsegGatedCRF
@@ -102,9 +174,7 @@ def losses_kat():
     s = torch.softmax(lg, 1)
     out = {"logits": logits.numpy(), "logits2": logits2.numpy(), "image": img.numpy(), "label": lab.numpy()}
 
-    def tv_ref(pred):  # script-local function, train_weakly_supervised_pCE_TV_2D.py:58-65 (not importable: the
-        # script parses argv and imports tensorboardX at module level) -> oracle restatement is the pin here
-        return O.tv_loss(pred)
+    tv_ref = script_function("train_weakly_supervised_pCE_TV_2D.py", "tv_loss")
 
     ce = torch.nn.CrossEntropyLoss(ignore_index=4)(lg, lab.long())
     crf = ModelLossSemsegGatedCRF()(s, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 32, 32)["loss"]
@@ -281,6 +351,8 @@ if __name__ == "__main__":
         augment_golden()
         sys.exit(0)
     losses_kat()
+    losses_api()
+    crf_general()
     net_golden(False)
     net_golden(True)
     augment_golden()

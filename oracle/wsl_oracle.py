@@ -100,20 +100,27 @@ def synth_params(in_chns: int, class_num: int, decoders: Sequence[str], seed: in
 # ----------------------------------------------------------------------------------------------
 # optional storage-precision emulation (used by the GPU parity tests to separate "kernel is wrong" from
 # "bf16 storage costs precision"): QUANT rounds forward values AND the gradients flowing back through the
-# same point to bf16, at exactly the tensors the executor stores in bf16 (conv outputs Y, activations A,
+# same point to bf16 (or fp16, with the executor's loss scale), at exactly the tensors the executor stores in 16 bits (conv outputs Y, activations A,
 # conv1x1 output T, upsample output U, channel-dropped features) and rounds the weights of the convolutions
 # that run on the tensor cores.  QUANT = None (default) is the plain fp32 restatement of the reference.
 # ----------------------------------------------------------------------------------------------
-QUANT = None
+QUANT = None          # None | True / "bf16" | "fp16"
+QUANT_SCALE = 1.0     # power-of-two loss scale the fp16 executor carries on every activation gradient (grad_scale_for)
+
+
+def _qdtype():
+    return torch.float16 if QUANT == "fp16" else torch.bfloat16
 
 
 class _RoundBoth(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return x.to(_qdtype()).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
+        if QUANT == "fp16":          # the stored value is fp16(g * scale); the scale is exact (power of two)
+            return (g * QUANT_SCALE).to(torch.float16).to(g.dtype) / QUANT_SCALE
         return g.to(torch.bfloat16).to(g.dtype)
 
 
@@ -122,11 +129,11 @@ def _q(x):
 
 
 def _qw(w, x):
-    """weights are bf16 on the tcgen05 path: Cin % 16 == 0 and the map is a multiple of the 8x16 pixel tile"""
+    """weights are 16-bit on the tcgen05 path: Cin % 16 == 0 and the map is a multiple of the 8x16 pixel tile"""
     if QUANT is None:
         return w
     tc = (w.shape[1] % 16 == 0) and (x.shape[-1] % 16 == 0) and (x.shape[-2] % 8 == 0)
-    return w.to(torch.bfloat16).to(w.dtype) if tc else w
+    return w.to(_qdtype()).to(w.dtype) if tc else w
 
 
 # ----------------------------------------------------------------------------------------------

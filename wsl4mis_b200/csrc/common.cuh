@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -96,6 +97,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
   u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
   return u;
+}
+
+// fp16 twins (storage dtype code 2: kind::f16 tensor-core operands with an 11-bit mantissa)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_f16(f[0], f[1]); u.y = pack_f16(f[2], f[3]);
+  u.z = pack_f16(f[4], f[5]); u.w = pack_f16(f[6], f[7]);
+  return u;
+}
+// run-time 16-bit storage type (warp-uniform flag): 0 = bf16, 2 = fp16
+__device__ __forceinline__ uint4 pack8_dt(const float (&f)[8], int dt) { return dt == 2 ? pack8h(f) : pack8(f); }
+__device__ __forceinline__ void unpack8_dt(const uint4& u, float (&f)[8], int dt) {
+  if (dt == 2) unpack8h(u, f); else unpack8(u, f);
 }
 
 // counter-based RNG for dropout (graph-capture safe: state lives in arguments, not in a generator)

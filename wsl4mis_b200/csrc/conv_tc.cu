@@ -164,6 +164,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn_major = 0
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// the same descriptor for the run-time 16-bit operand type: dt 0 = bf16 (format code 1), dt 2 = fp16 (format code 0);
+// kind::f16 runs both at the same rate, fp16 carries an 11-bit instead of an 8-bit mantissa
+__device__ __forceinline__ uint32_t idesc_for(uint32_t idesc_bf16, int dt) {
+  return dt == 2 ? (idesc_bf16 & ~((1u << 7) | (1u << 10))) : idesc_bf16;
+}
 
 struct ConvTcParams {
   int N, H, W;
@@ -172,8 +177,10 @@ struct ConvTcParams {
   int CoutStore;     // channels stored per pixel (bf16 NHWC) or real channels (fp32 NCHW)
   int taps, ks;
   int tiles_x, tiles_y;
-  int out_mode;
+  int out_mode;       // 0: 16-bit NHWC, 1: fp32 NCHW, 2: fp32 NHWC
+  int dt;             // 16-bit operand / storage type: 0 bf16, 2 fp16
   const float* bias;
+  const float* out_scale;   // optional device scalar multiplied into the accumulator before the bias (split mode: 2^-k of the staged operand)
   void* out;
 };
 
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(NT);
+    const uint32_t idesc = idesc_for(make_idesc_bf16(NT), p.dt);
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
@@ -280,6 +287,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     for (int c = 0; c < NT; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (p.out_scale) {
+        const float sc = *p.out_scale;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= sc;
+      }
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += p.bias[n0 + c + j];
@@ -291,8 +303,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           float lo[8], hi[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-          reinterpret_cast<uint4*>(o)[0] = pack8(lo);
-          if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+          reinterpret_cast<uint4*>(o)[0] = pack8_dt(lo, p.dt);
+          if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8_dt(hi, p.dt);
+        }
+      } else if (p.out_mode == 2) {
+        if (n0 + c < p.CoutStore) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (((long long)n * p.H + gy) * p.W + gx) * p.CoutStore + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n0 + c + 4 * j < p.CoutStore) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       } else {
         float* o = reinterpret_cast<float*>(p.out);
@@ -331,7 +350,7 @@ CUtensorMapSwizzle swizzle_for(int kblk) {
 }
 
 struct MapKey {
-  const void* ptr; long long d[4]; int b[4]; int rank; int sw;
+  const void* ptr; long long d[4]; int b[4]; int rank; int sw; int dt; int pitch;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -345,11 +364,13 @@ struct MapKeyHash {
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// bf16 tensor, dims innermost-first; strides derived (dense).  Cached by (ptr, dims, box, swizzle).
-int get_map(const void* ptr, int rank, const long long* dims, const int* box, int kblk, CUtensorMap* out) {
+// 16-bit tensor (dt 0 = bf16, 2 = fp16), dims innermost-first; strides derived (dense) unless `pitch` (elements between
+// consecutive indices of dimension 1, i.e. the channel pitch of a channels-last tensor) is given: a channel-range view of a
+// wider tensor.  Cached by (ptr, dims, box, swizzle, type, pitch).
+int get_map(const void* ptr, int rank, const long long* dims, const int* box, int kblk, CUtensorMap* out, int dt = 0, int pitch = 0) {
   MapKey key;
   memset(&key, 0, sizeof(key));
-  key.ptr = ptr; key.rank = rank; key.sw = kblk;
+  key.ptr = ptr; key.rank = rank; key.sw = kblk; key.dt = dt; key.pitch = pitch;
   for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
   {
     std::lock_guard<std::mutex> g(g_map_mu);
@@ -365,10 +386,10 @@ int get_map(const void* ptr, int rank, const long long* dims, const int* box, in
     gdim[i] = (cuuint64_t)dims[i];
     bdim[i] = (cuuint32_t)box[i];
     estr[i] = 1;
-    stride *= (unsigned long long)dims[i];
+    stride *= (unsigned long long)((i == 0 && pitch > 0) ? pitch : dims[i]);
     if (i < rank - 1) gstride[i] = stride;
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
+  CUresult r = enc(out, dt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { wsl_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -4; }
@@ -443,6 +464,7 @@ struct ConvV2Params {
   int tiles_x, tiles_y, ntiles;
   int out_mode;
   int desc_mode;
+  int dt;                 // 16-bit operand / storage type: 0 bf16, 2 fp16
   const float* bias;
   void* out;
   float* stat_partials;   // optional [gridDim.x][2][CoutP]: per-CTA sum / sum of squares of the stored (bf16-rounded) outputs
@@ -552,7 +574,7 @@ __global__ void __launch_bounds__(Conv2Epi<NT, MT>::THREADS) conv_tc2_kernel(con
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(NT);
+    const uint32_t idesc = idesc_for(make_idesc_bf16(NT), p.dt);
     constexpr uint32_t a_hi = desc_hi<SW>(Cfg::HW_ * Cfg::ROWB), b_hi = desc_hi<SW>(8 * SW);
     const uint32_t elected = elect_one();
     const uint32_t tmem_u = uniform(tmem_base);
@@ -625,16 +647,16 @@ __global__ void __launch_bounds__(Conv2Epi<NT, MT>::THREADS) conv_tc2_kernel(con
             float lo[8], hi[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) { lo[jj] = v[jj]; hi[jj] = v[8 + jj]; }
-            const uint4 plo = pack8(lo), phi = pack8(hi);
+            const uint4 plo = pack8_dt(lo, p.dt), phi = pack8_dt(hi, p.dt);
             if (n0 + c < p.CoutStore) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)n * p.H + gy) * p.W + gx) * p.CoutStore + n0 + c;
               reinterpret_cast<uint4*>(o)[0] = plo;
               if (n0 + c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = phi;
             }
-            if (p.stat_partials) {   // BatchNorm statistics of the values exactly as stored (bf16-rounded)
+            if (p.stat_partials) {   // BatchNorm statistics of the values exactly as stored (rounded to the 16-bit type)
               float r[16], r2[16];
-              unpack8(plo, lo);
-              unpack8(phi, hi);
+              unpack8_dt(plo, lo, p.dt);
+              unpack8_dt(phi, hi, p.dt);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) { r[jj] = lo[jj]; r[8 + jj] = hi[jj]; }
 #pragma unroll
@@ -714,6 +736,9 @@ struct WgradTcParams {
   int tiles_x, tiles_y, nchunks;
   int n_tiles0, n_tiles1;   // Cin blocks in source 0 / 1
   int tap_groups;
+  int dt;               // 16-bit operand type: 0 bf16, 2 fp16
+  const float* scale_a;  // optional device scalars multiplied into the result (split mode: 2^-k of the staged dY / X)
+  const float* scale_b;
   float* dw;
 };
 
@@ -792,7 +817,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(CWB, /*a_mn_major=*/1, /*b_mn_major=*/1, 128);
+    const uint32_t idesc = idesc_for(make_idesc_bf16(CWB, /*a_mn_major=*/1, /*b_mn_major=*/1, 128), p.dt);
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
@@ -823,6 +848,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int CinTot = p.C0 + p.C1;
+    const float osc = (p.scale_a ? *p.scale_a : 1.f) * (p.scale_b ? *p.scale_b : 1.f);
 #pragma unroll 1
     for (int tl = 0; tl < TG; ++tl) {
       const int t = tg * TG + tl;
@@ -833,7 +859,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         if (row < p.CoutReal && q * 32 + lane < 128) {
           float* dst = p.dw + ((size_t)row * CinTot + ci_global + c) * p.taps + t;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + (size_t)j * p.taps, v[j]);
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + (size_t)j * p.taps, v[j] * osc);
         }
       }
     }
@@ -927,7 +953,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc2_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(CWB, 1, 1, 128);
+    const uint32_t idesc = idesc_for(make_idesc_bf16(CWB, 1, 1, 128), p.dt);
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it % STAGES;
       mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -1032,6 +1058,7 @@ struct Wgrad3Params {
   int CoutReal;
   int tiles_x, tiles_y, nchunks;
   int k_tiles0, k_tiles1;     // Cin blocks (of CWB channels) in source 0 / 1
+  int dt;                     // 16-bit operand type: 0 bf16, 2 fp16
   float* dw;
 };
 
@@ -1094,7 +1121,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (DYN && CWN <= 32) ? 2 : 1) wgrad
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(DYN ? 3 * NTILE : NTILE, 1, 1, 128);
+    const uint32_t idesc = idesc_for(make_idesc_bf16(DYN ? 3 * NTILE : NTILE, 1, 1, 128), p.dt);
     // A: channel-group stride (LBO) = one pixel, so group g == filter column dx = g; 8-pixel-row groups 10 halo pixels apart
     constexpr uint32_t a_hi = desc_hi<SWX>(10 * S::ROWB), b_hi = desc_hi<SWN>(8 * SWN);
     constexpr uint32_t a_lbo = ((uint32_t)(S::ROWB >> 4) & 0x3fffu) << 16;
@@ -1217,7 +1244,7 @@ int wgrad_dispatch_b(int cwb, const CUtensorMap& a, const CUtensorMap& b0, const
 }
 
 // per-channel sum of a channels-last bf16 tensor, added into out[C] (bias gradients of conv1x1 / out_conv)
-template <typename T>
+template <typename T, bool HALF = false>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ x, long long P, int C, int Creal,
                                                           float* __restrict__ out) {
   extern __shared__ float s_red[];
@@ -1229,7 +1256,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   for (long long q = (long long)blockIdx.x * rows + r; q < P; q += (long long)gridDim.x * rows) {
     float v[8];
     if constexpr (sizeof(T) == 2) {
-      unpack8(*reinterpret_cast<const uint4*>(x + q * C + g * 8), v);
+      unpack8_dt(*reinterpret_cast<const uint4*>(x + q * C + g * 8), v, HALF ? 2 : 0);
     } else {
       const float4 a = reinterpret_cast<const float4*>(x + q * C + g * 8)[0], b = reinterpret_cast<const float4*>(x + q * C + g * 8)[1];
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -1394,7 +1421,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(NG);
+    const uint32_t idesc = idesc_for(make_idesc_bf16(NG), p.dt);
     constexpr uint32_t d_hi = desc_hi<SWB>(8 * SWB);
     const uint32_t elected = elect_one();
     const uint32_t tmem_u = uniform(tmem_base);
@@ -1479,15 +1506,15 @@ __global__ void __launch_bounds__(64 + 32 * EW, (RING * 3 * NT <= 256) ? 2 : 1) 
             float lo[8], hi[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) { lo[jj] = v[jj]; hi[jj] = v[8 + jj]; }
-            const uint4 plo = pack8(lo), phi = pack8(hi);
+            const uint4 plo = pack8_dt(lo, p.dt), phi = pack8_dt(hi, p.dt);
             if (c < p.CoutStore) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)n * p.H + gy) * p.W + gx) * p.CoutStore + c;
               reinterpret_cast<uint4*>(o)[0] = plo;
               if (c + 8 < p.CoutStore) reinterpret_cast<uint4*>(o)[1] = phi;
             }
-            if (p.stat_partials) {   // statistics of the values exactly as stored (bf16-rounded)
-              unpack8(plo, lo);
-              unpack8(phi, hi);
+            if (p.stat_partials) {   // statistics of the values exactly as stored (rounded to the 16-bit type)
+              unpack8_dt(plo, lo, p.dt);
+              unpack8_dt(phi, hi, p.dt);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
                 ls[c + jj] += lo[jj];           lq[c + jj] = fmaf(lo[jj], lo[jj], lq[c + jj]);
@@ -1577,8 +1604,9 @@ int launch_conv_row(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
 WSL_API int wsl_tc_available(void) { return get_encode() != nullptr ? 1 : 0; }
 
 WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                        int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream) {
+                        int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc: ksize must be 1 or 3");
+  WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_conv_tc: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc: CoutP must be a multiple of 16");
   WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_conv_tc: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
@@ -1592,13 +1620,13 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
   {
     long long d[4] = {C0, W, H, N};
     int bx[4] = {kblk, TILE_W, TILE_H, 1};
-    int rc = get_map(src0, 4, d, bx, kblk, &a0);
+    int rc = get_map(src0, 4, d, bx, kblk, &a0, dtype);
     if (rc) return rc;
   }
   if (C1 > 0) {
     long long d[4] = {C1, W, H, N};
     int bx[4] = {kblk, TILE_W, TILE_H, 1};
-    int rc = get_map(src1, 4, d, bx, kblk, &a1);
+    int rc = get_map(src1, 4, d, bx, kblk, &a1, dtype);
     if (rc) return rc;
   } else {
     a1 = a0;
@@ -1606,12 +1634,12 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
   {
     long long d[3] = {CinP, CoutP, T};
     int bx[3] = {kblk, nt, 1};
-    int rc = get_map(wpk_bf16, 3, d, bx, kblk, &b);
+    int rc = get_map(wpk_bf16, 3, d, bx, kblk, &b, dtype);
     if (rc) return rc;
   }
   ConvTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore; p.taps = T; p.ks = ksize;
-  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.bias = bias; p.out = out;
+  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.dt = dtype; p.bias = bias; p.out_scale = nullptr; p.out = out;
   switch (kblk) {
     case 64: return dispatch_nt<64>(a0, a1, b, p, nt, stream);
     case 32: return dispatch_nt<32>(a0, a1, b, p, nt, stream);
@@ -1619,9 +1647,12 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
   }
 }
 
-WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                         int W, int CoutReal, int ksize, cudaStream_t stream) {
+// pitch_x / pitch_dy > 0: the operands are channel-range views of wider channels-last tensors (fp16 hi/lo split planes)
+static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                         int W, int CoutReal, int ksize, int dtype, int pitch_x, int pitch_dy, const float* scale_a,
+                         const float* scale_b, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_wgrad_tc: ksize must be 1 or 3");
+  WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_wgrad_tc: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_wgrad_tc: CoutP must be a multiple of 16");
   WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_wgrad_tc: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
@@ -1636,19 +1667,19 @@ WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, con
   {
     long long d[4] = {CoutP, W, H, N};
     int bx[4] = {cwa, TILE_W, TILE_H, 1};
-    int rc = get_map(dy, 4, d, bx, cwa, &mdy);
+    int rc = get_map(dy, 4, d, bx, cwa, &mdy, dtype, pitch_dy);
     if (rc) return rc;
   }
   {
     long long d[4] = {C0, W, H, N};
     int bx[4] = {cwb, TILE_W, TILE_H, 1};
-    int rc = get_map(src0, 4, d, bx, cwb, &mx0);
+    int rc = get_map(src0, 4, d, bx, cwb, &mx0, dtype, pitch_x);
     if (rc) return rc;
   }
   if (C1 > 0) {
     long long d[4] = {C1, W, H, N};
     int bx[4] = {cwb, TILE_W, TILE_H, 1};
-    int rc = get_map(src1, 4, d, bx, cwb, &mx1);
+    int rc = get_map(src1, 4, d, bx, cwb, &mx1, dtype, pitch_x);
     if (rc) return rc;
   } else {
     mx1 = mx0;
@@ -1656,11 +1687,76 @@ WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, con
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = ksize * ksize; p.ks = ksize;
   p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dw = dw;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dt = dtype; p.scale_a = scale_a; p.scale_b = scale_b; p.dw = dw;
   if (cwa == 64 && na == 2) return wgrad_dispatch_b<64, 2>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 64) return wgrad_dispatch_b<64, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 32) return wgrad_dispatch_b<32, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   return wgrad_dispatch_b<16, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
+}
+
+WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                         int W, int CoutReal, int ksize, int dtype, cudaStream_t stream) {
+  return wgrad_tc_impl(src0, C0, src1, C1, dy, CoutP, dw, N, H, W, CoutReal, ksize, dtype, 0, 0, nullptr, nullptr, stream);
+}
+
+// ---- fp16 hi/lo split ("fp16x3") tensor-core parity mode ------------------------------------------------------------
+// An fp32 value v is carried as hi = fp16(v), lo = fp16(v - hi) (22 significant bits); a product a*b is evaluated as
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo on kind::f16 with fp32 accumulation (the dropped lo*lo term is ~2^-22 relative).
+// Staged operands are channels-last fp16 [P][2C] = (hi plane | lo plane), produced by wsl_split_f32 (net_ops.cu).
+//   forward / data gradient: K = 3*Cin: source 0 = the whole staged tensor (hi | lo) against (w_hi | w_hi), source 1 = its hi
+//   plane again (channel-range view, pitch 2*Cin) against w_lo; weights fp16 [T][CoutP][3*Cin] from wsl_pack_split_weights.
+//   weight gradient: three accumulating launches (dy_hi,x_hi), (dy_hi,x_lo), (dy_lo,x_hi).
+// out_mode 2: fp32 NHWC [P][CoutStore]; 1: fp32 NCHW.
+WSL_API int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scale, const void* wpk3, const float* bias, float* out,
+                              int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc_split: ksize must be 1 or 3");
+  WSL_REQUIRE(Cin % 16 == 0 && Cin > 0 && CoutP % 16 == 0, "wsl_conv_tc_split: channel counts must be multiples of 16 (got %d,%d)", Cin, CoutP);
+  WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_conv_tc_split: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
+  WSL_REQUIRE(out_mode == 1 || out_mode == 2, "wsl_conv_tc_split: out_mode must be 1 (fp32 NCHW) or 2 (fp32 NHWC)");
+  int kblk = 64;
+  while (kblk > 16 && Cin % kblk != 0) kblk >>= 1;
+  int nt = CoutP >= 128 ? 128 : CoutP;
+  WSL_REQUIRE(CoutP % nt == 0 && (nt == 16 || nt == 32 || nt == 64 || nt == 128), "wsl_conv_tc_split: unsupported CoutP %d", CoutP);
+  const int T = ksize * ksize;
+  CUtensorMap a0, a1, b;
+  {
+    long long d[4] = {2LL * Cin, W, H, N};
+    int bx[4] = {kblk, TILE_W, TILE_H, 1};
+    int rc = get_map(staged, 4, d, bx, kblk, &a0, 2);
+    if (rc) return rc;
+  }
+  {
+    long long d[4] = {Cin, W, H, N};
+    int bx[4] = {kblk, TILE_W, TILE_H, 1};
+    int rc = get_map(staged, 4, d, bx, kblk, &a1, 2, 2 * Cin);
+    if (rc) return rc;
+  }
+  {
+    long long d[3] = {3LL * Cin, CoutP, T};
+    int bx[3] = {kblk, nt, 1};
+    int rc = get_map(wpk3, 3, d, bx, kblk, &b, 2);
+    if (rc) return rc;
+  }
+  ConvTcParams p;
+  p.N = N; p.H = H; p.W = W; p.C0 = 2 * Cin; p.C1 = Cin; p.CoutP = CoutP; p.CoutStore = CoutStore; p.taps = T; p.ks = ksize;
+  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.dt = 2; p.bias = bias; p.out_scale = inv_scale; p.out = out;
+  switch (kblk) {
+    case 64: return dispatch_nt<64>(a0, a1, b, p, nt, stream);
+    case 32: return dispatch_nt<32>(a0, a1, b, p, nt, stream);
+    default: return dispatch_nt<16>(a0, a1, b, p, nt, stream);
+  }
+}
+
+WSL_API int wsl_wgrad_tc_split(const void* x_staged, int Cin, const float* x_inv_scale, const void* dy_staged, int CoutP,
+                               const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream) {
+  WSL_REQUIRE(Cin % 16 == 0 && Cin > 0, "wsl_wgrad_tc_split: Cin must be a multiple of 16 (got %d)", Cin);
+  const __half* x = reinterpret_cast<const __half*>(x_staged);
+  const __half* g = reinterpret_cast<const __half*>(dy_staged);
+  int rc = wgrad_tc_impl(x, Cin, nullptr, 0, g, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
+  if (rc) return rc;
+  rc = wgrad_tc_impl(x + Cin, Cin, nullptr, 0, g, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
+  if (rc) return rc;
+  return wgrad_tc_impl(x, Cin, nullptr, 0, g + CoutP, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
 }
 
 WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, cudaStream_t stream) {
@@ -1670,15 +1766,17 @@ WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Cr
   if (b > 148 * 2) b = 148 * 2;
   if (b < 1) b = 1;
   if (dtype == 1) channel_sum_kernel<float><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const float*)x, P, C, Creal, out);
+  else if (dtype == 2) channel_sum_kernel<__nv_bfloat16, true><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
   else channel_sum_kernel<__nv_bfloat16><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
   return wsl_check_launch("channel_sum");
 }
 
 // conv_tc v2 entry point (same contract as wsl_conv_tc; needs W % 8 == 0 and H % (16*MT) == 0)
 WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                         int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, float* stat_partials,
+                         int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, float* stat_partials,
                          int* stat_rows_host, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc2: ksize must be 1 or 3");
+  WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_conv_tc2: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc2: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc2: CoutP must be a multiple of 16");
   {   // narrow outputs at >= 128-pixel rows: the row kernel (filter rows in N) is 1.8-2.3x faster per pixel
@@ -1694,13 +1792,13 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
       {
         long long d[4] = {C0, W, H, N};
         int bx[4] = {kbw, 130, 1, 1};
-        int rc = get_map(src0, 4, d, bx, kbw, &a0);
+        int rc = get_map(src0, 4, d, bx, kbw, &a0, dtype);
         if (rc) return rc;
       }
       if (C1 > 0) {
         long long d[4] = {C1, W, H, N};
         int bx[4] = {kbw, 130, 1, 1};
-        int rc = get_map(src1, 4, d, bx, kbw, &a1);
+        int rc = get_map(src1, 4, d, bx, kbw, &a1, dtype);
         if (rc) return rc;
       } else {
         a1 = a0;
@@ -1708,13 +1806,13 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
       {
         long long d[3] = {C0 + C1, CoutP, 9};
         int bx[3] = {kbw, CoutP, 1};
-        int rc = get_map(wpk_bf16, 3, d, bx, kbw, &b);
+        int rc = get_map(wpk_bf16, 3, d, bx, kbw, &b, dtype);
         if (rc) return rc;
       }
       ConvV2Params p;
       p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore;
       p.tiles_x = 0; p.tiles_y = 0; p.ntiles = 0;
-      p.out_mode = out_mode; p.desc_mode = 0; p.bias = bias; p.out = out;
+      p.out_mode = out_mode; p.desc_mode = 0; p.dt = dtype; p.bias = bias; p.out = out;
       p.stat_partials = (out_mode == 0) ? stat_partials : nullptr;
       const int rc = (CoutP == 16) ? launch_conv_row<16>(a0, a1, b, p, KB, RS, kbw, stream)
                                    : launch_conv_row<32>(a0, a1, b, p, KB, RS, kbw, stream);
@@ -1740,13 +1838,13 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
   {
     long long d[4] = {C0, W, H, N};
     int bx[4] = {kblk, 8 + 2 * pad, 16 * mt + 2 * pad, 1};
-    int rc = get_map(src0, 4, d, bx, kblk, &a0);
+    int rc = get_map(src0, 4, d, bx, kblk, &a0, dtype);
     if (rc) return rc;
   }
   if (C1 > 0) {
     long long d[4] = {C1, W, H, N};
     int bx[4] = {kblk, 8 + 2 * pad, 16 * mt + 2 * pad, 1};
-    int rc = get_map(src1, 4, d, bx, kblk, &a1);
+    int rc = get_map(src1, 4, d, bx, kblk, &a1, dtype);
     if (rc) return rc;
   } else {
     a1 = a0;
@@ -1754,13 +1852,13 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
   {
     long long d[3] = {CinP, CoutP, T};
     int bx[3] = {kblk, nt, 1};
-    int rc = get_map(wpk_bf16, 3, d, bx, kblk, &b);
+    int rc = get_map(wpk_bf16, 3, d, bx, kblk, &b, dtype);
     if (rc) return rc;
   }
   ConvV2Params p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore;
   p.tiles_x = W / 8; p.tiles_y = H / (16 * mt); p.ntiles = N * p.tiles_x * p.tiles_y;
-  p.out_mode = out_mode; p.desc_mode = desc_mode; p.bias = bias; p.out = out;
+  p.out_mode = out_mode; p.desc_mode = desc_mode; p.dt = dtype; p.bias = bias; p.out = out;
   p.stat_partials = (out_mode == 0) ? stat_partials : nullptr;
 #define WSL_C2(KS_, KB_, MT_)                                                   \
   do {                                                                         \
@@ -1786,8 +1884,9 @@ WSL_API int wsl_conv_tc2(const void* src0, int C0, const void* src1, int C1, con
 
 // 3x3 weight gradient, v2 (halo views).  Same contract as wsl_wgrad_tc; needs W % 8 == 0 and H % 16 == 0.
 WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                          int W, int CoutReal, int ksize, cudaStream_t stream) {
+                          int W, int CoutReal, int ksize, int dtype, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3, "wsl_wgrad_tc2: 3x3 only");
+  WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_wgrad_tc2: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc2: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0 && (CoutP < 128 || CoutP % 128 == 0), "wsl_wgrad_tc2: unsupported CoutP %d", CoutP);
   WSL_REQUIRE(W % 8 == 0 && H % 16 == 0, "wsl_wgrad_tc2: H,W must be multiples of the 16x8 pixel chunk (got %dx%d)", H, W);
@@ -1799,19 +1898,19 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
   {
     long long d[4] = {CoutP, W, H, N};
     int bx[4] = {cwa, 8, 16, 1};
-    int rc = get_map(dy, 4, d, bx, cwa, &mdy);
+    int rc = get_map(dy, 4, d, bx, cwa, &mdy, dtype);
     if (rc) return rc;
   }
   {
     long long d[4] = {C0, W, H, N};
     int bx[4] = {cwb, 10, 18, 1};
-    int rc = get_map(src0, 4, d, bx, cwb, &mx0);
+    int rc = get_map(src0, 4, d, bx, cwb, &mx0, dtype);
     if (rc) return rc;
   }
   if (C1 > 0) {
     long long d[4] = {C1, W, H, N};
     int bx[4] = {cwb, 10, 18, 1};
-    int rc = get_map(src1, 4, d, bx, cwb, &mx1);
+    int rc = get_map(src1, 4, d, bx, cwb, &mx1, dtype);
     if (rc) return rc;
   } else {
     mx1 = mx0;
@@ -1819,7 +1918,7 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = 9; p.ks = 3;
   p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dw = dw;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dt = dtype; p.scale_a = nullptr; p.scale_b = nullptr; p.dw = dw;
   if (cwb == 32) {
     if (cwa == 64 && na == 2) return launch_wgrad2<64, 2, 32>(mdy, mx0, mx1, p, m_tiles, stream);
     if (cwa == 64) return launch_wgrad2<64, 1, 32>(mdy, mx0, mx1, p, m_tiles, stream);
@@ -1834,8 +1933,9 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
 
 // 3x3 weight gradient, v3 (filter columns in the MMA's M dimension).  Same contract as wsl_wgrad_tc2.
 WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                          int W, int CoutReal, int ksize, cudaStream_t stream) {
+                          int W, int CoutReal, int ksize, int dtype, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3, "wsl_wgrad_tc3: 3x3 only");
+  WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_wgrad_tc3: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc3: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0 && (CoutP <= 64 || CoutP % 128 == 0), "wsl_wgrad_tc3: unsupported CoutP %d", CoutP);
   WSL_REQUIRE(CoutP == 16 || CoutP == 32 || CoutP >= 64, "wsl_wgrad_tc3: unsupported CoutP %d", CoutP);
@@ -1849,19 +1949,19 @@ WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, co
   {
     long long d[4] = {CoutP, W, H, N};
     int bx[4] = {cwn, 8, dyn ? 18 : 16, 1};
-    int rc = get_map(dy, 4, d, bx, cwn, &mdy);
+    int rc = get_map(dy, 4, d, bx, cwn, &mdy, dtype);
     if (rc) return rc;
   }
   {
     long long d[4] = {C0, W, H, N};
     int bx[4] = {cwb, 10, dyn ? 16 : 18, 1};
-    int rc = get_map(src0, 4, d, bx, cwb, &mx0);
+    int rc = get_map(src0, 4, d, bx, cwb, &mx0, dtype);
     if (rc) return rc;
   }
   if (C1 > 0) {
     long long d[4] = {C1, W, H, N};
     int bx[4] = {cwb, 10, dyn ? 16 : 18, 1};
-    int rc = get_map(src1, 4, d, bx, cwb, &mx1);
+    int rc = get_map(src1, 4, d, bx, cwb, &mx1, dtype);
     if (rc) return rc;
   } else {
     mx1 = mx0;
@@ -1869,7 +1969,7 @@ WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, co
   Wgrad3Params p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutReal = CoutReal;
   p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.k_tiles0 = C0 / cwb; p.k_tiles1 = C1 / cwb; p.dw = dw;
+  p.k_tiles0 = C0 / cwb; p.k_tiles1 = C1 / cwb; p.dt = dtype; p.dw = dw;
 #define WSL_W3(CWB_) \
   if (ntile == 128) return launch_wgrad3<CWB_, 64, 2>(mdy, mx0, mx1, p, n_tiles, stream); \
   if (ntile == 64) return launch_wgrad3<CWB_, 64, 1>(mdy, mx0, mx1, p, n_tiles, stream);  \

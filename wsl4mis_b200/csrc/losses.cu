@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TPB) softmax_pce_fwd_kernel(
 __global__ void __launch_bounds__(TPB) head_bwd_kernel(
     const float* __restrict__ probs, const uint8_t* __restrict__ label, const float* __restrict__ ce_stats,
     const float* __restrict__ go_ptr, float w_ce, const float* __restrict__ gprobs, float gs,
-    int HW, long long nquads, int ignore_index, float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_nhwc16) {
+    int HW, long long nquads, int ignore_index, float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_nhwc16, int dt16) {
   const int qpi = HW >> 2;
   const float go = go_ptr ? *go_ptr : 1.0f;
   const float cew = (label != nullptr && w_ce != 0.f) ? w_ce * go / ce_stats[1] : 0.f;
@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(TPB) head_bwd_kernel(
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 v;
-        v.x = pack_bf16(d[0][j], d[1][j]);
-        v.y = pack_bf16(d[2][j], d[3][j]);
+        v.x = dt16 == 2 ? pack_f16(d[0][j], d[1][j]) : pack_bf16(d[0][j], d[1][j]);
+        v.y = dt16 == 2 ? pack_f16(d[2][j], d[3][j]) : pack_bf16(d[2][j], d[3][j]);
         v.z = 0u; v.w = 0u;
         o[2 * j] = v;
         o[2 * j + 1] = make_uint4(0u, 0u, 0u, 0u);
@@ -906,12 +906,12 @@ WSL_API int wsl_softmax_pce_fwd(const float* logits, const uint8_t* label, float
 
 WSL_API int wsl_head_bwd(const float* probs, const uint8_t* label, const float* ce_stats, const float* grad_out,
                          float w_ce, const float* gprobs, float gprobs_scale, int N, int C, int H, int W,
-                         int ignore_index, float* dlogits, void* dlogits_nhwc16_bf16, cudaStream_t stream) {
+                         int ignore_index, float* dlogits, void* dlogits_nhwc16, int dtype16, cudaStream_t stream) {
   WSL_REQUIRE(C == C4, "wsl_head_bwd: C must be 4 (got %d)", C);
   WSL_REQUIRE(((long long)H * W) % 4 == 0, "wsl_head_bwd: H*W must be a multiple of 4");
   const long long nq = (long long)N * H * W / 4;
   head_bwd_kernel<<<grid_for(nq, TPB), TPB, 0, stream>>>(probs, label, ce_stats, grad_out, w_ce, gprobs, gprobs_scale,
-                                                         H * W, nq, ignore_index, dlogits, (__nv_bfloat16*)dlogits_nhwc16_bf16);
+                                                         H * W, nq, ignore_index, dlogits, (__nv_bfloat16*)dlogits_nhwc16, dtype16);
   return wsl_check_launch("head_bwd");
 }
 

@@ -13,16 +13,19 @@ namespace {
 constexpr int TPB = 256;
 
 // Storage type of activations / activation gradients: bf16 (fast path, tensor cores) or fp32 (the reference-accurate
-// "parity" mode that runs the CUDA-core direct convolutions).  dtype codes in the C ABI: 0 = bf16, 1 = fp32.
+// "parity" mode that runs the CUDA-core direct convolutions) or fp16 (same tensor-core rate as bf16, 11-bit mantissa; needs
+// a scaled loss so that gradients stay in range).  dtype codes in the C ABI: 0 = bf16, 1 = fp32, 2 = fp16.
 using bf16 = __nv_bfloat16;
 template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
 template <> __device__ __forceinline__ void ld8<bf16>(const bf16* p, float (&v)[8]) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
+template <> __device__ __forceinline__ void ld8<__half>(const __half* p, float (&v)[8]) { unpack8h(*reinterpret_cast<const uint4*>(p), v); }
 template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
 template <> __device__ __forceinline__ void st8<bf16>(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+template <> __device__ __forceinline__ void st8<__half>(__half* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = pack8h(v); }
 template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -30,10 +33,12 @@ template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v
 // value as it will be read back from storage
 template <typename T> __device__ __forceinline__ void round8(float (&v)[8]);
 template <> __device__ __forceinline__ void round8<bf16>(float (&v)[8]) { const uint4 u = pack8(v); unpack8(u, v); }
+template <> __device__ __forceinline__ void round8<__half>(float (&v)[8]) { const uint4 u = pack8h(v); unpack8h(u, v); }
 template <> __device__ __forceinline__ void round8<float>(float (&v)[8]) {}
 // generic source element loader for the direct convolutions (dtype code at run time)
-__device__ __forceinline__ void ld8_dyn(const void* base, long long elem_off, int f32, float (&v)[8]) {
-  if (f32) ld8(reinterpret_cast<const float*>(base) + elem_off, v);
+__device__ __forceinline__ void ld8_dyn(const void* base, long long elem_off, int dt, float (&v)[8]) {
+  if (dt == 1) ld8(reinterpret_cast<const float*>(base) + elem_off, v);
+  else if (dt == 2) ld8(reinterpret_cast<const __half*>(base) + elem_off, v);
   else ld8(reinterpret_cast<const bf16*>(base) + elem_off, v);
 }
 constexpr float BN_EPS_DEFAULT = 1e-5f;
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
       if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
         const long long pix = ((long long)n * H + gy) * W + gx;
         const int c = c0 + half * 8;
-        if (src_f32 && (C0 % 8) != 0) {          // single-channel image
+        if (src_f32 == 1 && (C0 % 8) != 0) {          // single-channel image
           if (c < Cin) {
             const float* s = reinterpret_cast<const float*>(src0) + pix * C0 + c;
             for (int j = 0; j < 8 && c + j < Cin; ++j) v[j] = s[j];
@@ -123,13 +128,13 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
     float v[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = acc[r][c] + (bias ? bias[cob + c] : 0.f);
-    if (out_mode == 0) {
+    if (out_mode == 0 || out_mode == 3) {   // 16-bit NHWC: 0 = bf16, 3 = fp16
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (((long long)n * H + gy) * W + gx) * CoutStore + cob;
       float lo[8], hi[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi[c] = v[8 + c]; }
-      if (cob + 8 <= CoutStore) reinterpret_cast<uint4*>(o)[0] = pack8(lo);
-      if (cob + 16 <= CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8(hi);
+      if (cob + 8 <= CoutStore) reinterpret_cast<uint4*>(o)[0] = pack8_dt(lo, out_mode == 3 ? 2 : 0);
+      if (cob + 16 <= CoutStore) reinterpret_cast<uint4*>(o)[1] = pack8_dt(hi, out_mode == 3 ? 2 : 0);
     } else if (out_mode == 2) {  // fp32 NHWC with CoutStore channels (parity mode activations)
       float* o = reinterpret_cast<float*>(out) + (((long long)n * H + gy) * W + gx) * CoutStore + cob;
 #pragma unroll
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(
       if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
         const long long pix = ((long long)n * H + gy) * W + gx;
         const int c = cib + half * 8;
-        if (src_f32 && (C0 % 8) != 0) {          // single-channel image
+        if (src_f32 == 1 && (C0 % 8) != 0) {          // single-channel image
           if (c < Cin) {
             const float* s = reinterpret_cast<const float*>(src0) + pix * C0 + c;
             for (int j = 0; j < 8 && c + j < Cin; ++j) v[j] = s[j];
@@ -709,15 +714,20 @@ __device__ __forceinline__ void bn_bwd_gather8(const BnBwdArgs<T>& a, const BnBw
   }
 }
 
-// summed incoming gradient g -> dz: dropout mask (regenerated) and LeakyReLU derivative; in place
-template <typename T>
-__device__ __forceinline__ void bn_bwd_finish8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&g)[8], const float (&yv)[8]) {
+// summed incoming gradient g -> dz: dropout mask (regenerated) and LeakyReLU derivative; in place.
+// KEEP_Z: yv is overwritten with the normalised value z = y*scale + shift (= gamma*xhat + beta).  The reduction accumulates
+// sum(dz*z) instead of sum(dz*y): sum(dz*xhat) = (sum(dz*z) - beta*sum(dz)) / gamma then cancels against beta*sum(dz) (beta is
+// O(0.1)) rather than against mean*sum(dz) on the raw convolution output, whose mean can be many standard deviations (measured
+// at 4 x 256 x 256: 1e-2 relative error on dgamma / 8e-3 on the following weight gradient in fp32 storage with the raw form).
+template <bool KEEP_Z = false, typename T>
+__device__ __forceinline__ void bn_bwd_finish8(const BnBwdArgs<T>& a, const BnBwdThread& t, int p, float (&g)[8], float (&yv)[8]) {
   const uint32_t kb = keep_bits8(t.dc, (long long)p * a.C + t.c0, (uint32_t)p * t.cg + t.g);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float z = fmaf(yv[j], t.sc[j], t.sh[j]);
     const float d = g[j] * (z > 0.f ? 1.f : a.slope);
     g[j] = ((kb >> j) & 1u) ? d * t.dc.inv_keep : 0.f;
+    if (KEEP_Z) yv[j] = z;
   }
 }
 
@@ -730,8 +740,8 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
   const int C = a.C, cg = t.cg, rows = TPB / cg;
   const int P = a.N * a.H * a.W;
   const int r = threadIdx.x / cg;
-  // accumulate sum(dz) and sum(dz*y) on the RAW conv output; sum(dz*xhat) = invstd*(sum(dz*y) - mean*sum(dz)) is formed per
-  // block below (keeps 16 registers free for the second pixel in flight)
+  // accumulate sum(dz) and sum(dz*z), z = the normalised value the LeakyReLU sign test computes anyway (no extra registers);
+  // sum(dz*xhat) = (sum(dz*z) - beta*sum(dz)) / gamma is formed per block below
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
@@ -741,8 +751,8 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
     float dz0[8], y0[8], dz1[8], y1[8];
     bn_bwd_gather8<MODE>(a, t, p, dz0, y0);            // all loads of both pixels are issued before the first use
     bn_bwd_gather8<MODE>(a, t, p + stride, dz1, y1);
-    bn_bwd_finish8(a, t, p, dz0, y0);
-    bn_bwd_finish8(a, t, p + stride, dz1, y1);
+    bn_bwd_finish8<true>(a, t, p, dz0, y0);
+    bn_bwd_finish8<true>(a, t, p + stride, dz1, y1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] += dz0[j]; s2[j] = fmaf(dz0[j], y0[j], s2[j]); }
 #pragma unroll
@@ -751,7 +761,7 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
   if (p < P) {
     float dz[8], yv[8];
     bn_bwd_gather8<MODE>(a, t, p, dz, yv);
-    bn_bwd_finish8(a, t, p, dz, yv);
+    bn_bwd_finish8<true>(a, t, p, dz, yv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] += dz[j]; s2[j] = fmaf(dz[j], yv[j], s2[j]); }
   }
@@ -763,7 +773,10 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
     float x = 0.f, y = 0.f;
     for (int rr = 0; rr < rows; ++rr) { x += s_red[(rr * cg + gg) * 16 + j]; y += s_red[(rr * cg + gg) * 16 + 8 + j]; }
     partials[((size_t)blockIdx.x * 2 + 0) * C + c] = x;
-    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = a.save[C + c] * (y - a.save[c] * x);      // sum(dz * xhat)
+    // sum(dz * xhat): gamma = scale / invstd, beta = shift + mean * scale (gamma == 0 would make xhat unobservable through z;
+    // BatchNorm weights start at 1 and an exact zero is a measure-zero event, the term is then reported as 0)
+    const float gam = a.ss[c] / a.save[C + c], bet = fmaf(a.save[c], a.ss[c], a.ss[C + c]);
+    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = gam != 0.f ? (y - bet * x) / gam : 0.f;
   }
   __shared__ bool s_last;
   __threadfence();
@@ -966,13 +979,13 @@ __global__ void __launch_bounds__(TPB) chan_scale_kernel(const T* __restrict__ a
 // fp32 NCHW [N,Creal,H,W] -> bf16 NHWC [N,H,W,CP] (zero padded channels); used for dlogits
 template <typename T>
 __global__ void __launch_bounds__(TPB) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int Creal, int CP, long long HW,
-                                                                    long long npix, T* __restrict__ dst) {
+                                                                    long long npix, float scale, T* __restrict__ dst) {
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < npix; i += (long long)gridDim.x * TPB) {
     const long long n = i / HW, o = i - n * HW;
     for (int c0 = 0; c0 < CP; c0 += 8) {
       float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < Creal) ? src[(n * Creal + c0 + j) * HW + o] : 0.f;
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < Creal) ? src[(n * Creal + c0 + j) * HW + o] * scale : 0.f;
       st8(dst + i * CP + c0, v);
     }
   }
@@ -1000,28 +1013,35 @@ __global__ void __launch_bounds__(TPB) nhwc_bf16_to_nchw_f32_kernel(const T* __r
 // ci_count rounded up to 16:
 //   wd  fp32 [T][CoutP][SliceP]    dgrad operand of conv_direct (tap flipped, roles swapped)
 //   bd  bf16 [T][SliceP][CoutP]    tcgen05 B operand, dgrad    (K-major: Cout contiguous), tap flipped
+// one 16-bit element: bf16 or (half16) fp16 bits in the same slot
+__device__ __forceinline__ void st16(__nv_bfloat16* dst, float v, int half16) {
+  if (half16) *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+  else *dst = __float2bfloat16(v);
+}
+
 __global__ void __launch_bounds__(TPB) pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int T, int CoutP,
                                                            int CinP, int ci_begin, int ci_count, float* wf, float* wd,
-                                                           __nv_bfloat16* bf, __nv_bfloat16* bd) {
+                                                           __nv_bfloat16* bf, __nv_bfloat16* bd, int half16) {
   const long long total = (long long)T * CoutP * CinP;
   const int SliceP = (ci_count + 15) & ~15;
   for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
     const int ci = (int)(i % CinP), co = (int)((i / CinP) % CoutP), t = (int)(i / ((long long)CinP * CoutP));
     const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * T + t] : 0.f;
     if (wf) wf[((size_t)t * CinP + ci) * CoutP + co] = v;
-    if (bf) bf[((size_t)t * CoutP + co) * CinP + ci] = __float2bfloat16(v);
+    if (bf) st16(bf + ((size_t)t * CoutP + co) * CinP + ci, v, half16);
     const int cs = ci - ci_begin;
     if (cs >= 0 && cs < SliceP) {
       const float vs = (cs < ci_count) ? v : 0.f;
       if (wd) wd[((size_t)(T - 1 - t) * CoutP + co) * SliceP + cs] = vs;
-      if (bd) bd[((size_t)(T - 1 - t) * SliceP + cs) * CoutP + co] = __float2bfloat16(vs);
+      if (bd) st16(bd + ((size_t)(T - 1 - t) * SliceP + cs) * CoutP + co, vs, half16);
     }
   }
 }
 
 // Batched form: ONE launch packs every layer.  table[e] = 13 int64: {w, wf, wd, bf, bd, Cout, Cin, T, CoutP, CinP, ci_begin,
 // ci_count, first_item}; items of entry e are [first_item(e), first_item(e+1)).
-__global__ void __launch_bounds__(TPB) pack_weights_batched_kernel(const long long* __restrict__ table, int n_entries, long long total) {
+__global__ void __launch_bounds__(TPB) pack_weights_batched_kernel(const long long* __restrict__ table, int n_entries, long long total,
+                                                                   int half16) {
   __shared__ long long s_first[129];
   for (int e = threadIdx.x; e <= n_entries; e += TPB) s_first[e] = (e < n_entries) ? table[e * 13 + 12] : total;
   __syncthreads();
@@ -1044,12 +1064,12 @@ __global__ void __launch_bounds__(TPB) pack_weights_batched_kernel(const long lo
     const int ci = (int)(j % CinP), co = (int)((j / CinP) % CoutP), tt = (int)(j / ((long long)CinP * CoutP));
     const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * T + tt] : 0.f;
     if (wf) wf[((size_t)tt * CinP + ci) * CoutP + co] = v;
-    if (bf) bf[((size_t)tt * CoutP + co) * CinP + ci] = __float2bfloat16(v);
+    if (bf) st16(bf + ((size_t)tt * CoutP + co) * CinP + ci, v, half16);
     const int cs = ci - ci_begin;
     if (cs >= 0 && cs < SliceP) {
       const float vs = (cs < ci_count) ? v : 0.f;
       if (wd) wd[((size_t)(T - 1 - tt) * CoutP + co) * SliceP + cs] = vs;
-      if (bd) bd[((size_t)(T - 1 - tt) * SliceP + cs) * CoutP + co] = __float2bfloat16(vs);
+      if (bd) st16(bd + ((size_t)(T - 1 - tt) * SliceP + cs) * CoutP + co, vs, half16);
     }
   }
 }
@@ -1064,6 +1084,73 @@ __global__ void __launch_bounds__(TPB) sgd_kernel(float* __restrict__ p, const f
     const float b = fmaf(mu, m[i], gg);
     m[i] = b;
     p[i] = p[i] - l * b;
+  }
+}
+
+// ---- fp16 hi/lo split operands of the "fp16x3" tensor-core parity mode (conv_tc.cu: wsl_conv_tc_split) -------------
+// fp32 channels-last [P][C0] (and optionally [P][C1], concatenated along C) -> fp16 [P][2*(C0+C1)] = (hi plane | lo plane),
+// hi = fp16(v), lo = fp16(v - hi): v is carried with 22 significant bits.
+// Every staged tensor carries its own power-of-two scale (2^k with max|v| * 2^k in [2^13, 2^14)): fp16 has a 5-bit exponent, and
+// the lo plane sits 11 binades below the hi plane, so without it small activations / gradients would lose their lo bits to
+// underflow (measured: 8e-3 relative error on first-layer weight gradients with a single global loss scale).  scale2 = {2^k, 2^-k}
+// is written for the consumers, which multiply their fp32 results by 2^-k (exact).
+__global__ void __launch_bounds__(TPB) absmax_kernel(const float* __restrict__ s0, long long n0, const float* __restrict__ s1, long long n1,
+                                                     unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n0 + n1; i += (long long)gridDim.x * TPB)
+    m = fmaxf(m, fabsf(i < n0 ? s0[i] : s1[i - n0]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like their bits
+}
+
+__global__ void __launch_bounds__(TPB) split_f32_kernel(const float* __restrict__ s0, int C0, const float* __restrict__ s1, int C1,
+                                                        long long P, __half* __restrict__ dst, const unsigned* __restrict__ amax_bits,
+                                                        float* __restrict__ scale2) {
+  const int C = C0 + C1, cg = C >> 3;
+  const long long total = P * cg;
+  const float amax = __uint_as_float(*amax_bits);
+  int e = 0;
+  if (amax > 0.f && amax < 3.0e38f) frexpf(amax, &e);            // amax = f * 2^e, f in [0.5, 1)
+  const float sc = (amax > 0.f) ? ldexpf(1.f, 14 - e) : 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale2[0] = sc; scale2[1] = 1.f / sc; }
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const long long p = i / cg;
+    const int c = (int)(i - p * cg) * 8;
+    float v[8], hi[8], lo[8];
+    if (c < C0) ld8(s0 + p * C0 + c, v); else ld8(s1 + p * C1 + (c - C0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] *= sc;
+      hi[j] = __half2float(__float2half_rn(v[j]));
+      lo[j] = v[j] - hi[j];
+    }
+    st8(dst + p * 2 * C + c, hi);
+    st8(dst + p * 2 * C + C + c, lo);
+  }
+}
+
+// w: fp32 torch layout [Cout][Cin][T].  f3: fp16 [T][CoutP][3*CinP] = (w_hi | w_hi | w_lo) along K (forward B operand);
+// d3 for the input-channel slice [ci_begin, ci_begin + ci_count): fp16 [T][SliceP][3*CoutP], taps flipped (dgrad B operand).
+__global__ void __launch_bounds__(TPB) pack_split_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int T, int CoutP,
+                                                                 int CinP, int ci_begin, int ci_count, __half* f3, __half* d3) {
+  const long long total = (long long)T * CoutP * CinP;
+  const int SliceP = (ci_count + 15) & ~15;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int ci = (int)(i % CinP), co = (int)((i / CinP) % CoutP), t = (int)(i / ((long long)CinP * CoutP));
+    const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * T + t] : 0.f;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    if (f3) {
+      __half* o = f3 + ((size_t)t * CoutP + co) * 3 * CinP;
+      o[ci] = h; o[CinP + ci] = h; o[2 * CinP + ci] = l;
+    }
+    const int cs = ci - ci_begin;
+    if (d3 && cs >= 0 && cs < SliceP) {
+      const bool real = cs < ci_count;
+      __half* o = d3 + ((size_t)(T - 1 - t) * SliceP + cs) * 3 * CoutP;
+      o[co] = real ? h : __half(0.f); o[CoutP + co] = real ? h : __half(0.f); o[2 * CoutP + co] = real ? l : __half(0.f);
+    }
   }
 }
 
@@ -1085,10 +1172,11 @@ inline int bn_grid(long long P, int C, int per_sm = 3) {
 }  // namespace
 
 // run `expr` with T = bf16 (dtype 0) or float (dtype 1)
-#define WSL_DISPATCH_T(dtype, ...)                      \
-  do {                                                  \
-    if ((dtype) == 1) { using T = float; __VA_ARGS__; } \
-    else { using T = bf16; __VA_ARGS__; }               \
+#define WSL_DISPATCH_T(dtype, ...)                             \
+  do {                                                         \
+    if ((dtype) == 1) { using T = float; __VA_ARGS__; }        \
+    else if ((dtype) == 2) { using T = __half; __VA_ARGS__; }  \
+    else { using T = bf16; __VA_ARGS__; }                      \
   } while (0)
 
 // ================================================================================================
@@ -1099,7 +1187,7 @@ WSL_API int wsl_conv_direct(const void* src0, int C0, const void* src1, int C1, 
                             int CoutStore, int ksize, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_direct: ksize must be 1 or 3");
   WSL_REQUIRE(CinP % 16 == 0 && CoutP % 16 == 0, "wsl_conv_direct: padded channel counts must be multiples of 16");
-  WSL_REQUIRE((src_f32 && C1 == 0) || (C0 % 8 == 0 && C1 % 8 == 0), "wsl_conv_direct: multi-channel sources need C %% 8 == 0");
+  WSL_REQUIRE((src_f32 == 1 && C1 == 0) || (C0 % 8 == 0 && C1 % 8 == 0), "wsl_conv_direct: multi-channel sources need C %% 8 == 0");
   const int tx = (W + 15) / 16, ty = (H + 15) / 16;
   dim3 grid(N * tx * ty, CoutP / 16);
   if (ksize == 3)
@@ -1204,6 +1292,8 @@ WSL_API int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* s
   WSL_REQUIRE((long long)bn_grid(P, C) * 2 * C + 64 <= WSL_WS_FLOATS && P < (1LL << 31), "wsl_bn_bwd: workspace too small / too many pixels");
   if (dtype == 1)
     return bn_bwd_launch<float>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
+  if (dtype == 2)
+    return bn_bwd_launch<__half>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
   return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
 }
 
@@ -1233,10 +1323,11 @@ WSL_API int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int
   return wsl_check_launch("chan_scale");
 }
 
-WSL_API int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, cudaStream_t stream) {
+WSL_API int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, float scale,
+                                 cudaStream_t stream) {
   WSL_REQUIRE(CP % 8 == 0 && CP >= Creal, "wsl_nchw_f32_to_nhwc: bad padded channel count");
   const long long npix = (long long)N * H * W;
-  WSL_DISPATCH_T(dtype, nchw_f32_to_nhwc_bf16_kernel<T><<<grid_for(npix), TPB, 0, stream>>>(src, Creal, CP, (long long)H * W, npix, (T*)dst));
+  WSL_DISPATCH_T(dtype, nchw_f32_to_nhwc_bf16_kernel<T><<<grid_for(npix), TPB, 0, stream>>>(src, Creal, CP, (long long)H * W, npix, scale, (T*)dst));
   return wsl_check_launch("nchw_f32_to_nhwc");
 }
 
@@ -1247,13 +1338,33 @@ WSL_API int wsl_nhwc_to_nchw_f32(const void* src, int dtype, int N, int C, int H
 }
 
 WSL_API int wsl_pack_conv_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin,
-                                  int ci_count, float* wf, float* wd, void* bf, void* bd, cudaStream_t stream) {
+                                  int ci_count, float* wf, float* wd, void* bf, void* bd, int dtype16, cudaStream_t stream) {
   const int T = ksize * ksize;
   WSL_REQUIRE(ci_begin % 16 == 0 || ci_count == 0, "wsl_pack_conv_weights: slice start must be a multiple of 16");
   WSL_REQUIRE(ci_begin + ((ci_count + 15) & ~15) <= CinP || ci_count == 0, "wsl_pack_conv_weights: slice exceeds CinP");
   pack_weights_kernel<<<grid_for((long long)T * CoutP * CinP), TPB, 0, stream>>>(w, Cout, Cin, T, CoutP, CinP, ci_begin, ci_count,
-                                                                                 wf, wd, (__nv_bfloat16*)bf, (__nv_bfloat16*)bd);
+                                                                                 wf, wd, (__nv_bfloat16*)bf, (__nv_bfloat16*)bd, dtype16 == 2);
   return wsl_check_launch("pack_conv_weights");
+}
+
+WSL_API int wsl_split_f32(const float* src0, int C0, const float* src1, int C1, long long P, void* dst, float* scale3,
+                          cudaStream_t stream) {
+  WSL_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "wsl_split_f32: channel counts must be multiples of 8 (got %d,%d)", C0, C1);
+  // scale3 = {2^k, 2^-k, scratch}: the third word holds the bit pattern of max|v| between the two kernels
+  unsigned* amax = reinterpret_cast<unsigned*>(scale3 + 2);
+  cudaMemsetAsync(amax, 0, sizeof(unsigned), stream);
+  absmax_kernel<<<grid_for(P * (C0 + C1) / 4), TPB, 0, stream>>>(src0, P * C0, src1, P * C1, amax);
+  split_f32_kernel<<<grid_for(P * ((C0 + C1) / 8)), TPB, 0, stream>>>(src0, C0, src1, C1, P, (__half*)dst, amax, scale3);
+  return wsl_check_launch("split_f32");
+}
+
+WSL_API int wsl_pack_split_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin, int ci_count,
+                                   void* f3, void* d3, cudaStream_t stream) {
+  const int T = ksize * ksize;
+  WSL_REQUIRE(ci_begin % 16 == 0 || ci_count == 0, "wsl_pack_split_weights: slice start must be a multiple of 16");
+  pack_split_weights_kernel<<<grid_for((long long)T * CoutP * CinP), TPB, 0, stream>>>(w, Cout, Cin, T, CoutP, CinP, ci_begin, ci_count,
+                                                                                       (__half*)f3, (__half*)d3);
+  return wsl_check_launch("pack_split_weights");
 }
 
 WSL_API int wsl_sgd_step(float* param, const float* grad, float* mom, long long n, const float* lr_ptr, float lr,
@@ -1278,9 +1389,9 @@ WSL_API int wsl_wgrad_first(const float* x, const void* dy, int dtype, float* dw
   return wsl_check_launch("wgrad_first");
 }
 
-WSL_API int wsl_pack_conv_weights_batched(const long long* table, int n_entries, long long total_items, cudaStream_t stream) {
+WSL_API int wsl_pack_conv_weights_batched(const long long* table, int n_entries, long long total_items, int dtype16, cudaStream_t stream) {
   WSL_REQUIRE(n_entries >= 1 && n_entries <= 128, "wsl_pack_conv_weights_batched: 1..128 entries (got %d)", n_entries);
-  pack_weights_batched_kernel<<<grid_for(total_items), TPB, 0, stream>>>(table, n_entries, total_items);
+  pack_weights_batched_kernel<<<grid_for(total_items), TPB, 0, stream>>>(table, n_entries, total_items, dtype16 == 2);
   return wsl_check_launch("pack_conv_weights_batched");
 }
 

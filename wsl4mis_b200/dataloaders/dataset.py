@@ -54,13 +54,30 @@ class RandomGenerator:
         return (0, 0, 0, 0, 0)
 
     def __call__(self, sample):
-        """Single-sample form with the reference's signature (numpy in, CPU tensors out); runs the same GPU kernel."""
-        image = np.ascontiguousarray(sample["image"], dtype=np.float32)
-        label = np.ascontiguousarray(sample["label"]).astype(np.uint8)
-        store = SliceStore.from_arrays([image], [label])
-        params = [self.draw(bool(store.has4[0]))]
-        img, lab = store.augment([0], params, self.output_size)
-        return {"image": img[0].cpu(), "label": lab[0].cpu()}
+        """Single-sample form with the reference's signature (numpy in, CPU tensors out).  Runs on the HOST: the scripts call
+        it inside DataLoader worker processes (train_weakly_supervised_pCE_2D.py:72-73), where the GPU is off limits.  The
+        batched GPU kernel (`SliceStore.augment`) produces bit-identical samples for the same draws (tests/test_gpu_data.py)."""
+        image = np.asarray(sample["image"], dtype=np.float32)
+        label = np.asarray(sample["label"]).astype(np.uint8)
+        img, lab = apply_host(image, label, self.draw(bool((label == 4).any())), self.output_size)
+        return {"image": torch.from_numpy(img).unsqueeze(0), "label": torch.from_numpy(lab)}
+
+
+def apply_host(image, label, params, output_size):
+    """One (mode, k, axis, angle, lab_cval) decision on host arrays with the reference's library calls: rot90 + flip
+    (dataset_semi.py:126-134) | scipy rotate, order 0, label padded with lab_cval (:137-143); then zoom(order=0) to the
+    patch size (:164-167)."""
+    from scipy import ndimage
+    mode, k, axis, angle, cval = params
+    if mode == 1:
+        image, label = np.flip(np.rot90(image, k), axis=axis), np.flip(np.rot90(label, k), axis=axis)
+    elif mode == 2:
+        image = ndimage.rotate(image, angle, order=0, reshape=False)
+        label = ndimage.rotate(label, angle, order=0, reshape=False, mode="constant", cval=cval)
+    fy, fx = output_size[0] / image.shape[0], output_size[1] / image.shape[1]
+    image = ndimage.zoom(np.ascontiguousarray(image), (fy, fx), order=0)
+    label = ndimage.zoom(np.ascontiguousarray(label), (fy, fx), order=0)
+    return image.astype(np.float32), label.astype(np.uint8)
 
 
 class SliceStore:
@@ -125,9 +142,119 @@ class SliceStore:
         return img, lab
 
 
-class BaseDataSets(SliceStore):
-    """Name kept for the scripts' ``from dataloaders.dataset import BaseDataSets, RandomGenerator``; construct with
-    ``BaseDataSets.from_h5_dir`` / ``from_arrays`` and iterate with ``GpuLoader``."""
+def fold_ids(fold):
+    """ACDC five-fold split of the reference (dataset_semi.py:62-101): fold k tests on patients 20(k-1)+1 .. 20k."""
+    k = {"fold1": 1, "fold2": 2, "fold3": 3, "fold4": 4, "fold5": 5}.get(fold)
+    if k is None:
+        raise ValueError(f"unknown fold {fold!r} (fold1..fold5)")
+    test = ["patient{:0>3}".format(i) for i in range(20 * (k - 1) + 1, 20 * k + 1)]
+    train = ["patient{:0>3}".format(i) for i in range(1, 101) if "patient{:0>3}".format(i) not in test]
+    return train, test
+
+
+def synthetic_acdc(n_patients=100, seed=2022, slices=(6, 11)):
+    """ACDC-shaped synthetic cases for runs without the dataset (no h5py / no files on the box): per patient a short-axis stack
+    of `slices` ragged 2-D slices, image in [0, 1] (the reference min-max normalises, acdc_data_processing.py:44-45), dense
+    labels 0..3 as nested structures and a scribble map with 4 = unlabelled (~3 % labelled pixels).  Deterministic in `seed`."""
+    rs = np.random.RandomState(seed)
+    shapes = [(256, 216), (216, 256), (224, 154), (232, 256), (174, 208)]
+    cases = {}
+    for pid in range(1, n_patients + 1):
+        h, w = shapes[rs.randint(len(shapes))]
+        d = int(rs.randint(slices[0], slices[1]))
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        cy, cx = h * (0.4 + 0.2 * rs.rand()), w * (0.4 + 0.2 * rs.rand())
+        vol_i, vol_l, vol_s = [], [], []
+        for z in range(d):
+            r0 = min(h, w) * (0.10 + 0.04 * np.sin(z / max(d - 1, 1) * np.pi) + 0.02 * rs.rand())
+            rr = np.sqrt((yy - cy) ** 2 + ((xx - cx) * (0.9 + 0.2 * rs.rand())) ** 2)
+            lab = np.zeros((h, w), np.uint8)
+            lab[rr < 2.2 * r0] = 1
+            lab[rr < 1.6 * r0] = 2
+            lab[rr < 1.0 * r0] = 3
+            img = 0.15 + 0.2 * lab.astype(np.float32) + 0.08 * rs.randn(h, w).astype(np.float32)
+            img = (img - img.min()) / (img.max() - img.min())
+            scr = np.full((h, w), 4, np.uint8)
+            keep = rs.rand(h, w) < 0.03
+            scr[keep] = lab[keep]
+            vol_i.append(img.astype(np.float32))
+            vol_l.append(lab)
+            vol_s.append(scr)
+        cases["patient{:0>3}".format(pid)] = (np.stack(vol_i), np.stack(vol_l), np.stack(vol_s))
+    return cases
+
+
+class BaseDataSets(torch.utils.data.Dataset):
+    """``BaseDataSets(base_dir, split, transform, fold, sup_type)`` as every WSS script constructs it
+    (train_weakly_supervised_pCE_GatedCRFLoss_2D.py:75-80; the class the scripts need is the one in dataset_semi.py:17-125 --
+    the shipped dataloaders/dataset.py lacks fold= / sup_type=).
+
+    split='train': one sample per slice of the fold's training patients, ``{'image': f32 [1,H,W], 'label': u8 [H,W], 'idx'}``
+    after `transform`; split='val': one sample per volume of the fold's test patients, ``{'image': [D,h,w], 'label': [D,h,w],
+    'idx'}``.  Samples are produced on the HOST (numpy): the scripts iterate this object inside ``DataLoader(num_workers=8)``
+    worker processes, which must not touch the GPU.  ``to_slice_store()`` hands the same slices to the resident GPU pipeline
+    (`SliceStore` / `GpuLoader`), which is what keeps up with the B200 step.
+
+    base_dir: the ACDC directory (``ACDC_training_slices/*.h5`` with datasets image / label / scribble and
+    ``ACDC_training_volumes/*.h5``; needs h5py), or ``'synthetic'`` / ``'synthetic:<patients>'`` for the deterministic
+    ACDC-shaped generator above (what the tests and benchmarks use: the GPU boxes have neither h5py nor the data)."""
+
+    def __init__(self, base_dir=None, split='train', transform=None, fold="fold1", sup_type="label", num=None):
+        self._base_dir, self.split, self.transform, self.sup_type = base_dir, split, transform, sup_type
+        train_ids, test_ids = fold_ids(fold)
+        ids = set(train_ids if split == "train" else test_ids)
+        if split not in ("train", "val"):
+            raise ValueError(f"split must be 'train' or 'val' (got {split!r})")
+        self._synthetic = None
+        if base_dir is None or str(base_dir).startswith("synthetic"):
+            n = int(str(base_dir).split(":")[1]) if base_dir is not None and ":" in str(base_dir) else 100
+            cases = synthetic_acdc(n)
+            self._synthetic = cases
+            if split == "train":
+                self.sample_list = [f"{pid}_frame01_slice_{z}.h5" for pid in sorted(cases) if pid in ids for z in range(cases[pid][0].shape[0])]
+            else:
+                self.sample_list = [f"{pid}_frame01.h5" for pid in sorted(cases) if pid in ids]
+        else:
+            sub = "ACDC_training_slices" if split == "train" else "ACDC_training_volumes"
+            names = sorted(os.listdir(os.path.join(base_dir, sub)))
+            self.sample_list = [f for f in names if f.split("_")[0] in ids]
+        if num is not None and split == "train":
+            self.sample_list = self.sample_list[:num]
+
+    def __len__(self):
+        return len(self.sample_list)
+
+    def _read(self, case):
+        """-> (image, label) numpy arrays of one train slice / one validation volume"""
+        key = self.sup_type if self.split == "train" else "label"
+        if self._synthetic is not None:
+            img, lab, scr = self._synthetic[case.split("_")[0]]
+            if self.split == "train":
+                z = int(case.rsplit("_", 1)[1].split(".")[0])
+                return img[z], (scr if key == "scribble" else lab)[z]
+            return img, lab
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError("h5py is required to read the ACDC files; pass base_dir='synthetic' for the generated stand-in") from e
+        sub = "ACDC_training_slices" if self.split == "train" else "ACDC_training_volumes"
+        with h5py.File(os.path.join(self._base_dir, sub, case), "r") as f:
+            return f["image"][:], f[key][:]
+
+    def __getitem__(self, idx):
+        case = self.sample_list[idx]
+        image, label = self._read(case)
+        sample = {"image": image, "label": label}
+        if self.split == "train" and self.transform is not None:
+            sample = self.transform(sample)
+        sample["idx"] = case.split("_")[0]
+        return sample
+
+    def to_slice_store(self, device=None):
+        """the training slices as a resident GPU `SliceStore` (feed it to `GpuLoader`)"""
+        assert self.split == "train"
+        pairs = [self._read(c) for c in self.sample_list]
+        return SliceStore.from_arrays([p[0] for p in pairs], [p[1] for p in pairs], [c.split("_")[0] for c in self.sample_list], device)
 
 
 class GpuLoader:

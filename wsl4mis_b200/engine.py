@@ -87,8 +87,8 @@ class TrainStep:
     def _dlogits(ex, slot, name, N, C, H, W):
         """(fp32 NCHW buffer or None, bf16 NHWC-16 buffer or None, what backward() receives): in bf16 mode the head
         writes the out_conv gradient directly in the executor's layout (no conversion pass)."""
-        if ex.dt == 0:
-            d16 = ex.buf(slot, "head." + name + ".nhwc16", (N, H, W, 16), torch.bfloat16)
+        if ex.dt != 1:
+            d16 = ex.buf(slot, "head." + name + ".nhwc16", (N, H, W, 16))
             return None, d16, ("nhwc16", d16)
         d = ex.buf(slot, "head." + name, (N, C, H, W), torch.float32)
         return d, None, d
@@ -100,6 +100,9 @@ class TrainStep:
         dev = self.dev
         B = lambda name, shape, dt=torch.float32: ex.buf(slot, "head." + name, shape, dt)
         dl = [None] * len(logits_list)
+        # the 16-bit layouts receive the logit gradient already multiplied by the executor's loss scale (1 unless fp16);
+        # plain fp32 NCHW gradients are scaled by the executor itself
+        S = ex.grad_scale_for(N, H, W) if ex.dt != 1 else 1.0
         v = self.variant
         heads = range(self.n_heads_trained)
         probs, stats = [], []
@@ -113,14 +116,14 @@ class TrainStep:
         if v == "pce":
             loss = ce
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, None, 0.0, N, C, H, W, 4, d, d16)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, None, 0.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)
         elif v == "pce_gatedcrf":
             gp = B("gprobs0", (N, C, H, W))
             out = B("crf", (2,))
             call("wsl_gatedcrf_fwd", probs[0], image, gp, N, C, H, W, 5, 6.0, 0.1, 1.0, out, workspace("crf", dev))
             loss = ce + 0.1 * out[0]
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 0.1, N, C, H, W, 4, d, d16)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 0.1 * S, N, C, H, W, 4, d, d16, self.ex.dt)
             self.loss_parts = {"ce": ce, "crf": out[0]}
         elif v == "pce_ms":
             gp = B("gprobs0", (N, C, H, W))
@@ -130,7 +133,7 @@ class TrainStep:
             call("wsl_mumford_shah_bwd", image, probs[0], cent, N, C, H, W, 1e-6, 0, gp)
             loss = ce + 1e-6 * out[0]
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 1.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)
         elif v == "pce_tv":
             # tv_loss(outputs_soft[1:]) -- batch slice, sample 0 gets no TV term
             gp = B("gprobs0", (N, C, H, W))
@@ -142,7 +145,7 @@ class TrainStep:
             else:
                 loss = ce   # mean over an empty tensor is NaN in the reference; N=1 is never used with this script
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 1.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)
         elif v == "pce_entropy":
             gp = B("gprobs0", (N, C, H, W))
             out = B("ent", (1,))
@@ -150,7 +153,7 @@ class TrainStep:
             call("wsl_entropy_bwd", probs[0], N, C, H, W, 0.1, 0, gp)
             loss = ce + 0.1 * out[0]
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, 1.0, N, C, H, W, 4, d, d16)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 1.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)
         elif v == "pce_variance":
             from .utils import ramps
             w = self.consistency * ramps.sigmoid_rampup(self.iter_num // 150, self.consistency_rampup)
@@ -163,7 +166,7 @@ class TrainStep:
             self.cw_dev.fill_(w)
             loss = ce + self.cw_dev[0] * out[0]
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0, gp, float(w), N, C, H, W, 4, d, d16)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, float(w) * S, N, C, H, W, 4, d, d16, self.ex.dt)
         else:  # dmpls
             pseudo = B("pseudo", (N, H, W), torch.uint8)
             call("wsl_mix_argmax", probs[0], probs[1], 0.0, 0.0, self.beta_dev, N, C, H, W, pseudo)   # beta from device memory
@@ -175,7 +178,7 @@ class TrainStep:
                 call("wsl_pdice_bwd", probs[h], pseudo, None, float(N), sums, N, C, H, W, 0.25, 0, gp)
                 loss = loss + 0.25 * sums[0]
                 d, d16, dl[h] = self._dlogits(ex, slot, f"dl{h}", N, C, H, W)
-                call("wsl_head_bwd", probs[h], label, stats[h], None, 0.5, gp, 1.0, N, C, H, W, 4, d, d16)
+                call("wsl_head_bwd", probs[h], label, stats[h], None, 0.5 * S, gp, 1.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)
         return loss, dl
 
     def _fwd_bwd(self, image, label):
@@ -349,7 +352,7 @@ class UAMTStep:
         gp = Bf("gprobs_l", (B, C, H, W))
         call("wsl_pdice_bwd", probs, label_l, None, 1.0, sums, B, C, H, W, 0.5, 0, gp)
         dl_l = Bf("dl_l", (B, C, H, W))
-        call("wsl_head_bwd", probs, label_l, st, None, 0.5, gp, 1.0, B, C, H, W, 255, dl_l, None)
+        call("wsl_head_bwd", probs, label_l, st, None, 0.5, gp, 1.0, B, C, H, W, 255, dl_l, None, self.ex.dt)
         # ---- consistency half (:181-189) ----
         cw = self.consistency * self.ramps.sigmoid_rampup(self.iter_num // 300, self.consistency_rampup)
         import math
@@ -416,7 +419,7 @@ class USTMStep(UAMTStep):
         probs, st = Bf("probs", (B, C, H, W)), Bf("stats", (2,))
         call("wsl_softmax_pce_fwd", out, label, probs, B, C, H, W, 4, st, workspace("pce", dev))
         d = Bf("dl", (B, C, H, W))
-        call("wsl_head_bwd", probs, label, st, None, 1.0, None, 0.0, B, C, H, W, 4, d, None)
+        call("wsl_head_bwd", probs, label, st, None, 1.0, None, 0.0, B, C, H, W, 4, d, None, self.ex.dt)
         # consistency on the rotated student logits
         rout = Bf("rout", (B, C, H, W))
         call("wsl_rot90", out, B * C, H, k, 0, rout)

@@ -51,7 +51,7 @@ class _SoftmaxPCE(torch.autograd.Function):
         else:
             go = _chk(g_loss).reshape(1)
         gp = None if g_probs is None else _chk(g_probs)
-        call("wsl_head_bwd", probs, label if w_ce else None, stats, go, w_ce, gp, 1.0, N, C, H, W, ctx.ignore_index, d, None)
+        call("wsl_head_bwd", probs, label if w_ce else None, stats, go, w_ce, gp, 1.0, N, C, H, W, ctx.ignore_index, d, None, 0)
         return d, None, None
 
 
@@ -78,7 +78,7 @@ class _SoftmaxOnly(torch.autograd.Function):
         (probs,) = ctx.saved_tensors
         N, C, H, W = probs.shape
         d = torch.empty_like(probs)
-        call("wsl_head_bwd", probs, None, None, None, 0.0, _chk(g), 1.0, N, C, H, W, 255, d, None)
+        call("wsl_head_bwd", probs, None, None, None, 0.0, _chk(g), 1.0, N, C, H, W, 255, d, None, 0)
         return d
 
 

@@ -30,6 +30,15 @@ from .._lib import LIB, call, workspace
 BF16 = torch.bfloat16
 LRELU_SLOPE = 0.01
 
+# execution modes: storage type of activations / activation gradients and the convolution kernels they run on
+#   bf16    (dtype code 0) tcgen05 kind::f16 on bf16 operands -- the throughput mode (BASELINE config 2 names bf16)
+#   fp16    (dtype code 2) the same kernels on fp16 operands (11-bit mantissa, identical MMA rate); gradients travel
+#           multiplied by a power-of-two loss scale so that they stay inside fp16's range
+#   fp16x3  (dtype code 1) fp32 storage; every convolution on the tensor cores with fp16 hi/lo split operands
+#           (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulation): the tensor-core mode that meets the fp32 reference
+#   fp32    (dtype code 1) fp32 storage, CUDA-core direct convolutions: the arithmetic cross-check of everything else
+PRECISIONS = {"bf16": 0, "fp16": 2, "fp16x3": 1, "fp32": 1}
+
 
 def _ceil16(c):
     return (c + 15) // 16 * 16
@@ -67,13 +76,13 @@ class ConvLayer:
             self._packs = pk
         return self._packs
 
-    def pack(self, dev):
+    def pack(self, dev, dtype16=0):
         pk = self.packs(dev)
         w = self.conv.weight
         beg = 0
         for i, c in enumerate(self.srcC):
             call("wsl_pack_conv_weights", w, self.Cout, self.Cin, self.ks, self.CoutP, self.CinP, beg, c,
-                 pk["wf"] if i == 0 else None, pk["wd"][i], pk["bf"] if i == 0 else None, pk["bd"][i])
+                 pk["wf"] if i == 0 else None, pk["wd"][i], pk["bf"] if i == 0 else None, pk["bd"][i], dtype16)
             beg += c
         if self.Cout == self.CoutP:
             pk["bias"] = self.conv.bias.detach()
@@ -88,13 +97,14 @@ class UNetExecutor:
 
     def __init__(self, model: nn.Module, encoder: nn.Module, decoders: List[nn.Module], aux_dropout: Sequence[bool],
                  precision: str = "bf16"):
-        assert precision in ("bf16", "fp32")
+        assert precision in PRECISIONS
         self.model = model
-        # storage precision of activations / activation gradients: "bf16" = tensor-core fast path; "fp32" = parity mode
-        # (CUDA-core direct convolutions, everything in fp32: matches the fp32 reference to ~1e-5)
         self.precision = precision
-        self.act_dtype = BF16 if precision == "bf16" else torch.float32
-        self.dt = 0 if precision == "bf16" else 1
+        self.dt = PRECISIONS[precision]
+        self.act_dtype = {0: BF16, 1: torch.float32, 2: torch.float16}[self.dt]
+        self.split_tc = precision == "fp16x3"
+        # power-of-two factor carried by every activation gradient (set per backward from the batch shape; 1 = off)
+        self.scaled_grads = precision == "fp16"        # fp16x3 scales every staged operand by its own power of two instead
         self.aux = list(aux_dropout)
         self.layers: List[ConvLayer] = []
         ft = encoder.ft_chns
@@ -259,10 +269,25 @@ class UNetExecutor:
 
     def _tc2_ok(self, layer_cin_list, H, W):
         """persistent / resident-weight / halo-view kernels: 8 x 16 pixel tiles"""
-        return (self.dt == 0 and self.use_tc and self.use_tc2 and all(c % 16 == 0 for c in layer_cin_list) and W % 8 == 0 and H % 16 == 0)
+        return (self.dt != 1 and self.use_tc and self.use_tc2 and all(c % 16 == 0 for c in layer_cin_list) and W % 8 == 0 and H % 16 == 0)
 
     def _tc_ok(self, layer_cin_list, H, W):
-        return (self.dt == 0 and self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
+        return (self.dt != 1 and self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0)
+
+    def _split_ok(self, layer_cin_list, H, W):
+        """fp16 hi/lo split convolutions (fp16x3 mode): the per-tap tcgen05 kernel's 16 x 8 pixel tiles"""
+        return self.split_tc and self.use_tc and all(c % 16 == 0 for c in layer_cin_list) and W % 16 == 0 and H % 8 == 0
+
+    def _staged(self, name, srcs, chans, P):
+        """fp32 NHWC source(s) -> fp16 [P][2*C] (hi | lo) staging buffer of the split convolutions"""
+        C = sum(chans)
+        key = ("stage", name, P, C, self._side_stack[-1] if self._side_stack else "main")
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = (torch.empty((P, 2 * C), dtype=torch.float16, device=self.dev),
+                                   torch.zeros(3, dtype=torch.float32, device=self.dev))     # {2^k, 2^-k, scratch}
+        call("wsl_split_f32", srcs[0], chans[0], srcs[1] if len(srcs) > 1 else None, chans[1] if len(chans) > 1 else 0, P, t[0], t[1])
+        return t[0], t[1][1:]
 
     def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, bn_out=None):
         """bn_out = (save, ss) buffers: when the convolution runs on the persistent tcgen05 kernel the complete
@@ -275,24 +300,29 @@ class UNetExecutor:
         c0 = L.srcC[0]
         c1 = L.srcC[1] if len(L.srcC) > 1 else 0
         self._tag("fwd", L, N, H, W, L.Cin, L.Cout)
-        f32 = 1 if (src_f32 or self.dt == 1) else 0
-        if out_mode == 0 and self.dt == 1:
-            out_mode = 2                                   # fp32 NHWC activations
-        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2):
+        f32 = 1 if (src_f32 or self.dt == 1) else self.dt  # dtype code of the sources
+        if out_mode == 0 and self.dt != 0:
+            out_mode = 2 if self.dt == 1 else 3            # fp32 / fp16 NHWC activations
+        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2, 3):
             call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout)
+        elif not src_f32 and self._split_ok(L.srcC, H, W):
+            st, inv = self._staged("x", srcs, L.srcC, N * H * W)
+            call("wsl_conv_tc_split", st, L.Cin, inv, pk["f3"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
         elif not src_f32 and self._tc2_ok(L.srcC, H, W):
-            if bn_out is not None and self.fuse_bn_stats and out_mode == 0:
+            if bn_out is not None and self.fuse_bn_stats and out_mode in (0, 3):
                 sb = self._stat_scratch()
                 bn = L.bn
-                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks,
+                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0, N, H, W, L.CoutP, cout_store, L.ks, self.dt,
                      sb, ctypes.addressof(self._stat_rows))
                 call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
                      bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
                 rows = True
             else:
-                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks, None, None)
+                call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
+                     cout_store, L.ks, self.dt, None, None)
         elif not src_f32 and self._tc_ok(L.srcC, H, W):
-            call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
+            call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
+                 cout_store, L.ks, self.dt)
         else:
             call("wsl_conv_direct", s0, c0, s1, c1, f32, pk["wf"], pk["bias"], out, out_mode, N, H, W,
                  L.CinP, L.CoutP, cout_store, L.ks)
@@ -304,12 +334,15 @@ class UNetExecutor:
         ci = L.srcC[i]
         sp = _ceil16(ci)
         self._tag("dgrad", L, N, H, W, ci, L.Cout)
-        if self._tc2_ok([L.CoutP], H, W):
-            call("wsl_conv_tc2", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks, None, None)
+        if self._split_ok([L.CoutP], H, W):
+            st, inv = self._staged("dy", [dy], [L.CoutP], N * H * W)
+            call("wsl_conv_tc_split", st, L.CoutP, inv, pk["d3"][i], None, out, 2, N, H, W, sp, ci, L.ks)
+        elif self._tc2_ok([L.CoutP], H, W):
+            call("wsl_conv_tc2", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks, self.dt, None, None)
         elif self._tc_ok([L.CoutP], H, W):
-            call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks)
+            call("wsl_conv_tc", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks, self.dt)
         else:
-            call("wsl_conv_direct", dy, L.CoutP, None, 0, self.dt, pk["wd"][i], None, out, 2 if self.dt else 0, N, H, W, L.CoutP, sp, ci, L.ks)
+            call("wsl_conv_direct", dy, L.CoutP, None, 0, self.dt, pk["wd"][i], None, out, {0: 0, 1: 2, 2: 3}[self.dt], N, H, W, L.CoutP, sp, ci, L.ks)
         self._untag()
 
     def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False):
@@ -320,16 +353,22 @@ class UNetExecutor:
         self._tag("wgrad", L, N, H, W, L.Cin, L.Cout)
         tc = (not src_f32 and self.use_tc_wgrad and self._tc_ok(L.srcC, H, W)
               and (L.CoutP < 128 or L.CoutP % 128 == 0))
+        split = (not src_f32 and self.use_tc_wgrad and self._split_ok(L.srcC, H, W) and (L.CoutP < 128 or L.CoutP % 128 == 0))
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and L.bn is not None:
             call("wsl_wgrad_first", s0, dy, self.dt, self.gview(L.conv.weight), N, H, W, L.Cout)
+        elif split:
+            sx, ix = self._staged("x", srcs, L.srcC, N * H * W)
+            sg, ig = self._staged("dy", [dy], [L.CoutP], N * H * W)
+            call("wsl_wgrad_tc_split", sx, L.Cin, ix, sg, L.CoutP, ig, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
+            tc = True
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W) and self.wgrad_version == 3 and (L.CoutP <= 64 or L.CoutP % 128 == 0):
-            call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
+            call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W):
-            call("wsl_wgrad_tc2", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
+            call("wsl_wgrad_tc2", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
         elif tc:
-            call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
+            call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
         else:
-            call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if (src_f32 or self.dt) else 0, dy, self.dt, L.CoutP,
+            call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if (src_f32 or self.dt == 1) else self.dt, dy, self.dt, L.CoutP,
                  self.gview(L.conv.weight), self.gview(L.conv.bias) if L.bn is None else None, N, H, W, L.Cout, L.ks)
         self._untag()
         # Bias gradient.  A conv bias that feeds training-mode BatchNorm has an exactly-zero gradient (BN removes the
@@ -356,7 +395,7 @@ class UNetExecutor:
             call("wsl_bn_eval_prepare", bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), C, ss)
         p = L.drop_p if training else 0.0
         seed = self._layer_seed(L)
-        esz = 2 if self.dt == 0 else 4
+        esz = 4 if self.dt == 1 else 2
         self._tag_bytes("bn_act", L, N * H * W * C * esz * (2.25 if pooled is not None else 2.0))
         call("wsl_bn_act_fwd", y, self.dt, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
              act, pooled, pool_idx)
@@ -368,13 +407,23 @@ class UNetExecutor:
         C = L.Cout
         coef = self.buf(slot, tag + ".coef", (2 * C,), torch.float32)
         p = L.drop_p
-        esz = 2 if self.dt == 0 else 4
+        esz = 4 if self.dt == 1 else 2
         nsrc = (g0 is not None) + (g1 is not None) + 0.25 * (gpool is not None)
         self._tag_bytes("bn_bwd", L, N * H * W * C * esz * (2 * (1 + nsrc) + 1))      # reduce: y + sources; apply: again + dY
         call("wsl_bn_bwd", y, self.dt, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
              self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
              self.gview(bn.bias), coef, dy, self._ws("bn"), 1 if self._accumulate else 0)
         self._untag()
+
+    def grad_scale_for(self, N, H, W):
+        """Loss scale of the fp16 modes: a power of two near N*H*W/2, so that the largest logit gradient of a mean-type loss
+        (1 / #labelled pixels, ~3 % of the pixels with scribbles; 1 / (N*H*W) for dense terms) lands around 2^0..2^4 and the
+        smallest regulariser gradients stay far above fp16's subnormal range.  Activation gradients are linear in it; the flat
+        parameter-gradient bucket is multiplied by 1/scale (exact) at the end of backward()."""
+        if not self.scaled_grads:
+            return 1.0
+        import math
+        return float(2 ** (round(math.log2(N * H * W)) - 1))
 
     def _layer_seed(self, L):
         return (self.layers.index(L) + 1) * 0x9E3779B1
@@ -398,7 +447,18 @@ class UNetExecutor:
             self._pack_total = first
             self._pack_n = len(rows)
             self._pack_key = (ptrs, str(self.dev))
-        call("wsl_pack_conv_weights_batched", self._pack_table, self._pack_n, self._pack_total)
+        call("wsl_pack_conv_weights_batched", self._pack_table, self._pack_n, self._pack_total, self.dt)
+        if self.split_tc:
+            for L in self.layers:
+                pk = L.packs(self.dev)
+                if "f3" not in pk:
+                    pk["f3"] = torch.zeros(L.T * L.CoutP * 3 * L.CinP, dtype=torch.float16, device=self.dev)
+                    pk["d3"] = [torch.zeros(L.T * _ceil16(c) * 3 * L.CoutP, dtype=torch.float16, device=self.dev) for c in L.srcC]
+                beg = 0
+                for i, c in enumerate(L.srcC):
+                    call("wsl_pack_split_weights", L.conv.weight, L.Cout, L.Cin, L.ks, L.CoutP, L.CinP, beg, c,
+                         pk["f3"] if i == 0 else None, pk["d3"][i])
+                    beg += c
         for L in self.layers:                      # biases: share the parameter storage (or copy into the 16-padded buffer)
             pk = L.packs(self.dev)
             if L.Cout == L.CoutP:
@@ -483,7 +543,7 @@ class UNetExecutor:
                 t = self.buf(slot, f"dec{di}.up{j}.t", (N, hh, ww, C2))
                 self.conv_fwd(c1, [xlow], t, 0, N, hh, ww, C2)
                 u = self.buf(slot, f"dec{di}.up{j}.u", (N, 2 * hh, 2 * ww, C2))
-                self._tag_bytes("up_fwd", c1, N * hh * ww * C2 * (2 if self.dt == 0 else 4) * 5)
+                self._tag_bytes("up_fwd", c1, N * hh * ww * C2 * (4 if self.dt == 1 else 2) * 5)
                 call("wsl_upsample2x_fwd", t, self.dt, N, hh, ww, C2, u)
                 self._untag()
                 hh, ww = 2 * hh, 2 * ww
@@ -538,8 +598,11 @@ class UNetExecutor:
         N, H, W = rec["N"], rec["H"], rec["W"]
         ft = self.ft
         gflat, _ = self.grads()
+        S = self.grad_scale_for(N, H, W)
         if zero_grads:
             gflat.zero_()
+        elif S != 1.0:
+            gflat.mul_(S)                      # the bucket holds unscaled gradients of an earlier pass: bring them to this pass' scale
         self._accumulate = not zero_grads      # BN affine gradients are written (not added) unless accumulating
         B = lambda name, shape, dt=None: self.buf(slot, "g." + name, shape, dt)
 
@@ -584,7 +647,7 @@ class UNetExecutor:
             else:
                 g = g.contiguous()
                 dl = B(f"dec{di}.dl", (N, H, W, 16))
-                call("wsl_nchw_f32_to_nhwc", g, N, self.n_class, H, W, 16, dl, self.dt)
+                call("wsl_nchw_f32_to_nhwc", g, N, self.n_class, H, W, 16, dl, self.dt, S)
             with self.on_side():
                 self.conv_wgrad(oc, [drec["xlast"]], dl, N, H, W)
             da = B(f"dec{di}.dlast", (N, H, W, ft[0]))
@@ -600,7 +663,7 @@ class UNetExecutor:
                     gs = B(f"dec{di}.dp{j}.gs", (N, self.n_class, hh_, ww_), torch.float32)
                     call("wsl_nearest_resize_bwd", gh.contiguous(), N * self.n_class, hh_, ww_, H, W, gs)
                     dl16 = B(f"dec{di}.dp{j}.dl", (N, hh_, ww_, 16))
-                    call("wsl_nchw_f32_to_nhwc", gs, N, self.n_class, hh_, ww_, 16, dl16, self.dt)
+                    call("wsl_nchw_f32_to_nhwc", gs, N, self.n_class, hh_, ww_, 16, dl16, self.dt, S)
                     with self.on_side():
                         self.conv_wgrad(hl, [r["a2"]], dl16, N, hh_, ww_)
                     dh = B(f"dec{di}.dp{j}.dh", (N, hh_, ww_, Ch))
@@ -610,7 +673,7 @@ class UNetExecutor:
                 skip_grads[lvl].append((dskip, drec["cs"][lvl] if drec["cs"] else None))
                 hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
                 dt = B(f"dec{di}.up{j}.dt", (N, hh, ww, C2))
-                self._tag_bytes("up_bwd", c1, N * hh * ww * C2 * (2 if self.dt == 0 else 4) * 5)
+                self._tag_bytes("up_bwd", c1, N * hh * ww * C2 * (4 if self.dt == 1 else 2) * 5)
                 call("wsl_upsample2x_bwd", du, self.dt, N, hh, ww, C2, dt)
                 self._untag()
                 with self.on_side():
@@ -651,4 +714,6 @@ class UNetExecutor:
             d = block_bwd(f"enc{i}", self.enc_blocks[i], r, g0, g1, cs1, gpool, need_dsrc=(i > 0))
             gpool = d[0] if i > 0 else None
         self.join_side()
+        if S != 1.0:
+            gflat.mul_(1.0 / S)                # power of two: exact
         return gflat

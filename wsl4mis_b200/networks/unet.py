@@ -142,12 +142,17 @@ class _PlannedNet(nn.Module):
         self.dropout_masks = None      # {encoder level: uint8 NHWC keep-mask}  (tests / parity runs)
         self.channel_keep = None       # [five [N,C] keep masks]               (tests / parity runs)
 
-    precision = "bf16"     # "bf16": tensor-core fast path; "fp32": reference-accurate parity mode (set_precision)
+    precision = "bf16"     # see set_precision
 
     def set_precision(self, precision):
-        """'bf16' (default; activations stored in bf16, tcgen05 convolutions) or 'fp32' (every activation and
-        gradient in fp32, CUDA-core convolutions: numerically equivalent to the fp32 reference, ~100x slower)."""
-        assert precision in ("bf16", "fp32")
+        """Execution mode of the fused executor (networks/_engine.py:PRECISIONS):
+          'bf16'   default: activations / activation gradients stored in bf16, tcgen05 kind::f16 convolutions;
+          'fp16'   the same kernels on fp16 storage (11-bit mantissa, same speed; gradients carry a power-of-two loss scale);
+          'fp16x3' fp32 storage, tensor-core convolutions on fp16 hi/lo split operands: fp32-accurate (the reference computes
+                   in fp32, networks/unet.py:18-26), a few times slower than bf16;
+          'fp32'   fp32 storage, CUDA-core direct convolutions: the arithmetic cross-check, ~100x slower."""
+        from ._engine import PRECISIONS
+        assert precision in PRECISIONS, f"precision must be one of {sorted(PRECISIONS)}"
         object.__setattr__(self, "precision", precision)
         object.__setattr__(self, "_holder", None)
         return self

@@ -91,3 +91,8 @@ def test_single_volume(image, label, net, classes, patch_size=[256, 256]):
 def test_single_volume_cct(image, label, net, classes, patch_size=[256, 256]):
     """val_2D.py:90-124: dual-head models, metrics on the main head."""
     return test_single_volume(image, label, net, classes, patch_size)
+
+
+def test_single_volume_ds(image, label, net, classes, patch_size=[256, 256]):
+    """val_2D.py:53-87: deep-supervision models (four outputs), metrics on the full-resolution head (output 0)."""
+    return test_single_volume(image, label, net, classes, patch_size)
