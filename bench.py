@@ -5,12 +5,15 @@ batch 64 per GPU, synthetic data, random-init weights.
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # CPU restatement of the reference step on the host cores
+        bench.py --gpus N --steps K --warmup W [--scaling strong]
+    python bench.py --impl reference ...      # the reference's own modules on the host CPU (staged by oracle/build_ref.py)
 
 Prints ONE JSON line (rank 0).  value = whole-job images/sec with inputs resident in HBM;
 e2e = same step driven through the public API from pinned HOST buffers (H2D of the batch and D2H of the loss
-inside the timed region).
+inside the timed region).  Extra objects: roofline (dominant kernel) + layers (top launches against their own roofline),
+cpu_baseline (the reference on the host cores), gpu_baseline (the reference's modules as stock PyTorch on the same B200),
+parity (logit error / label mismatch of every execution mode against the fp32 CUDA-core executor), modes (step time of the
+fp16 and fp16x3 modes).
 """
 import argparse
 import json
@@ -24,8 +27,14 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "images/sec unet_cct pCE+GatedCRF 256x256 bs64"
 HW = 256
+VARIANT_LABEL = {"pce": "pCE", "pce_gatedcrf": "pCE+GatedCRF", "pce_ms": "pCE+MumfordShah", "pce_tv": "pCE+TV", "dmpls": "DMPLS (pCE + mixed pseudo-label Dice)",
+                 "pce_entropy": "pCE+EntropyMin", "pce_variance": "pCE+ClassVariance"}
+CRF_DESC = [{"weight": 1, "xy": 6, "rgb": 0.1}]
+
+
+def metric_name(args):
+    return f"images/sec {args.model} {VARIANT_LABEL.get(args.variant, args.variant)} {HW}x{HW} bs{args.batch}"
 
 
 def parse():
@@ -34,14 +43,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling) / global batch (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--model", default="unet_cct", choices=["unet", "unet_cct"])
     ap.add_argument("--variant", default="pce_gatedcrf")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp16x3", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images per CPU-baseline step")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--skip-gpu-baseline", action="store_true", help="skip the stock-PyTorch-on-B200 leg")
+    ap.add_argument("--skip-extras", action="store_true", help="skip parity / other-mode timing")
     return ap.parse_args()
 
 
@@ -53,13 +66,7 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
-# ----------------------------------------------------------------------------------------------
-# CPU baseline: the oracle restatement of the reference step (the ONLY place bench.py touches oracle/)
-# ----------------------------------------------------------------------------------------------
-def cpu_step_time(model_name, variant, n_img, steps, warmup):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import wsl_oracle as O
-    O.CRF_IMPL = "unfold"          # time the reference's own (materialising) GatedCRF formulation
+def host_cores():
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
@@ -71,44 +78,193 @@ def cpu_step_time(model_name, variant, n_img, steps, warmup):
             cores = max(1, min(cores, int(float(q) / float(per))))
     except Exception:
         pass
-    cores = min(cores, 64)   # torch CPU ops stop scaling (and start thrashing) far below 128 threads on these sizes
+    return min(cores, 64)   # torch CPU ops stop scaling (and start thrashing) far below 128 threads on these sizes
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def synth(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(n, 1, HW, HW, generator=g)
+    lab = torch.full((n, HW, HW), 4, dtype=torch.uint8)
+    m = torch.rand(n, HW, HW, generator=g) < 0.03
+    lab[m] = torch.randint(0, 4, (int(m.sum()),), generator=g, dtype=torch.uint8)
+    return img, lab
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference itself (unmodified modules staged by oracle/build_ref.py): CPU arm and stock-PyTorch-on-B200 arm.
+# The only places bench.py touches oracle/.
+# ----------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def load_reference():
+    """-> dict(UNet, UNet_CCT, losses, CRF) from the staged reference files, or None when nothing is staged"""
+    if "mods" not in _REF:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import build_ref
+        code = build_ref.extract()
+        mods = None
+        if code is not None:
+            sys.path.insert(0, code)
+            import importlib
+            unet = importlib.import_module("networks.unet")
+            crf = importlib.import_module("utils.gate_crf_loss")
+            losses = importlib.import_module("utils.losses")
+            mods = {"UNet": unet.UNet, "UNet_CCT": unet.UNet_CCT, "CRF": crf.ModelLossSemsegGatedCRF, "losses": losses, "code": code}
+        _REF["mods"] = mods
+    return _REF["mods"]
+
+
+def reference_step_fn(mods, model_name, variant, device, amp=False, channels_last=False, unet_only=False):
+    """The step body of train_weakly_supervised_pCE_GatedCRFLoss_2D.py:111-126 (or the pCE / MumfordShah variants) on the reference's
+    own modules; unet_cct under a single-head script uses main_seg."""
+    torch.manual_seed(2022)
+    model = (mods["UNet_CCT"] if model_name == "unet_cct" else mods["UNet"])(in_chns=1, class_num=4).to(device)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    ce = torch.nn.CrossEntropyLoss(ignore_index=4)
+    crf = mods["CRF"]()
+    ms = mods["losses"].MumfordShah_Loss()
+
+    def step(x, lab):
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=amp):
+            out = model(x.contiguous(memory_format=torch.channels_last) if channels_last else x)
+        out = (out[0] if isinstance(out, tuple) else out).float()
+        soft = torch.softmax(out, dim=1)
+        loss = ce(out, lab.long())
+        if not unet_only:
+            if variant == "pce_gatedcrf":
+                loss = loss + 0.1 * crf(soft, CRF_DESC, 5, x, HW, HW)["loss"]
+            elif variant == "pce_ms":
+                loss = loss + 1e-6 * ms(x, soft)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step
+
+
+def cpu_reference_time(args, n_img, steps, warmup):
+    """the reference step on the host cores; falls back to the oracle port when the reference files are not staged"""
+    cores = host_cores()
     torch.set_num_threads(cores)
-    cct = model_name == "unet_cct"
-    decs = ("main_decoder", "aux_decoder1") if cct else ("decoder",)
-    p = O.synth_params(1, 4, decs, 2022)
-    image, label = O.synth_batch(n_img, HW, HW, seed=2022)
-    moms = {}
+    mods = load_reference()
+    img, lab = synth(n_img, 2022)
+    if mods is not None:
+        step = reference_step_fn(mods, args.model, args.variant, torch.device("cpu"))
+        kind, what = "reference", "unmodified reference modules (networks/unet.py, utils/gate_crf_loss.py, utils/losses.py staged by oracle/build_ref.py) + torch CrossEntropyLoss / optim.SGD"
+        run = lambda: step(img, lab)
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import wsl_oracle as O
+        O.CRF_IMPL = "unfold"
+        cct = args.model == "unet_cct"
+        p = O.synth_params(1, 4, ("main_decoder", "aux_decoder1") if cct else ("decoder",), 2022)
+        moms = {}
+
+        def run():
+            loss, grads, _ = O.full_step(p, img, lab, args.variant, cct)
+            trainable = {k: p[k] for k in grads}
+            O.sgd_step(trainable, grads, moms, 0.01)
+            p.update(trainable)
+        kind, what = "port", "oracle/wsl_oracle.py full_step + sgd_step (reference files not staged on this box)"
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        loss, grads, _ = O.full_step(p, image, label, variant, cct)
-        trainable = {k: p[k] for k in grads}
-        O.sgd_step(trainable, grads, moms, 0.01)
-        p.update(trainable)
+        run()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     t = sum(times) / len(times)
-    return {"value": n_img / t, "unit": "images/sec", "cores": cores, "kind": "port",
-            "sample": f"{n_img} images of 1x{HW}x{HW} per step, {steps} steps after {warmup} warm-up, torch {torch.__version__} fp32, "
-                      f"oracle/wsl_oracle.py full_step + sgd_step ({model_name}, {variant})"}, t
+    return {"value": n_img / t, "unit": "images/sec", "cores": cores, "cpu": cpu_model(), "kind": kind,
+            "sample": f"{n_img} images of 1x{HW}x{HW} per step, {steps} steps after {warmup} warm-up, torch {torch.__version__} fp32, {what} "
+                      f"({args.model}, {args.variant})"}, t
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    cb, t = cpu_step_time(args.model, args.variant, args.cpu_sample, steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    cb, t = cpu_reference_time(args, args.cpu_sample, steps, warm)
+    line = {"impl": "reference", "metric": metric_name(args), "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model} {args.variant} train step, {args.cpu_sample}x1x{HW}x{HW} per step on host CPU",
-                       "note": "oracle port of the reference step (the reference is pure PyTorch; /root/reference is absent on the GPU box)"},
+            "config": {"workload": f"{args.model} {args.variant} train step, {args.cpu_sample}x1x{HW}x{HW} per step on the host CPU "
+                                   f"(bounded sample of the {args.batch}-image step: the unfold GatedCRF needs ~0.8 GB per image)",
+                       "note": "the reference is pure PyTorch: its own CPU path is the same modules on CPU tensors"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def gpu_reference_baseline(args, dev, img_d, lab_d):
+    """The reference's modules as stock PyTorch (ATen / cuDNN) on the same B200: the kernel to beat."""
+    mods = load_reference()
+    if mods is None:
+        return {"unavailable": "reference files not staged (oracle/_ref/reference_code.tar missing)"}
+    out = {"source": "unmodified reference modules on cuda (oracle/build_ref.py), torch " + torch.__version__, "runs": []}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark,
+             torch.backends.cudnn.deterministic)
+    modes = [("fp32 (scripts' --deterministic 1: cudnn.deterministic, no TF32)", dict(tf32=False, det=True, amp=False, cl=False)),
+             ("tf32 + cudnn.benchmark", dict(tf32=True, det=False, amp=False, cl=False)),
+             ("amp bf16 + channels_last + cudnn.benchmark", dict(tf32=True, det=False, amp=True, cl=True))]
+    try:
+        for name, o in modes:
+            for unet_only in (False, True):
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = o["tf32"]
+                torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic = (not o["det"]), o["det"]
+                res = None
+                for bs in (args.batch, 32, 16, 8):
+                    if bs > args.batch:
+                        continue
+                    try:
+                        torch.cuda.empty_cache()
+                        torch.cuda.reset_peak_memory_stats(dev)
+                        step = reference_step_fn(mods, args.model, args.variant, dev, o["amp"], o["cl"], unet_only)
+                        x, lab = img_d[:bs].contiguous(), lab_d[:bs].contiguous()
+                        for _ in range(3):
+                            step(x, lab)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        n = 5
+                        e0.record()
+                        for _ in range(n):
+                            loss = step(x, lab)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        ms = e0.elapsed_time(e1) / n
+                        res = {"mode": name, "step": "pCE only (U-Net fwd+bwd+SGD)" if unet_only else f"{args.variant} full step", "batch": bs,
+                               "ms_per_step": round(ms, 3), "images_per_sec": round(bs / ms * 1e3, 1),
+                               "peak_mem_GiB": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2), "loss": float(loss)}
+                        del step
+                        break
+                    except torch.cuda.OutOfMemoryError:
+                        res = None
+                        continue
+                out["runs"].append(res if res is not None else {"mode": name, "error": "out of memory at every batch size tried"})
+    finally:
+        (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark,
+         torch.backends.cudnn.deterministic) = saved
+        torch.cuda.empty_cache()
+    full = [r for r in out["runs"] if r and "images_per_sec" in r and r["step"].endswith("full step")]
+    if full:
+        best = max(full, key=lambda r: r["images_per_sec"])
+        out["best_full_step"] = {"mode": best["mode"], "images_per_sec": best["images_per_sec"], "batch": best["batch"]}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -151,6 +307,71 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def parity_report(args, dev):
+    """Every execution mode against the fp32 CUDA-core executor (itself pinned to the reference at 1e-5, tests/test_gpu_unet.py) on
+    the same weights and an 8 x 1 x 256 x 256 batch, training-mode forward with keep-all dropout masks: max |logit error| as a
+    fraction of max |logit| and the fraction of pixels whose argmax differs (north_star: 1e-3 / bit-exact)."""
+    from wsl4mis_b200.networks.unet import UNet, UNet_CCT
+    n = 8
+    img, _ = synth(n, 77)
+    x = img.to(dev)
+    ft = [16, 32, 64, 128, 256]
+    ones = {i: torch.ones(n, HW >> i, HW >> i, ft[i], dtype=torch.uint8, device=dev) for i in range(5)}
+    torch.manual_seed(2022)
+    base = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4)
+    sd = base.state_dict()
+    outs = {}
+    for prec in ("fp32", "bf16", "fp16", "fp16x3"):
+        m = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4)
+        m.load_state_dict(sd)
+        m = m.to(dev).set_precision(prec)
+        m.dropout_masks = ones
+        if args.model == "unet_cct":
+            m.channel_keep = [torch.ones(n, c, dtype=torch.uint8, device=dev) for c in ft]
+        m.train()
+        with torch.no_grad():
+            o = m(x)
+        outs[prec] = (o[0] if isinstance(o, tuple) else o).float()
+        del m
+    ref = outs["fp32"]
+    scale = ref.abs().max().item()
+    rep = []
+    for prec in ("bf16", "fp16", "fp16x3"):
+        rep.append({"mode": prec, "logit_err": float((outs[prec] - ref).abs().max().item() / scale),
+                    "label_mismatch": float((outs[prec].argmax(1) != ref.argmax(1)).float().mean().item())})
+    torch.cuda.empty_cache()
+    return {"reference": "fp32 CUDA-core executor (pinned to the reference fixtures at 1e-5)", "batch": f"{n}x1x{HW}x{HW}, train-mode forward, main_seg",
+            "tolerance": "north_star: logits within 1e-3 of scale, label maps bit-exact", "modes": rep}
+
+
+def time_other_modes(args, dev, img_d, lab_d, world):
+    """step time of the non-default precision modes (graph mode, device-resident inputs, single process)"""
+    from wsl4mis_b200.engine import TrainStep
+    from wsl4mis_b200.networks.unet import UNet, UNet_CCT
+    out = {}
+    for prec in ("bf16", "fp16", "fp16x3"):
+        if prec == args.precision:
+            continue
+        torch.manual_seed(2022)
+        m = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4).to(dev).set_precision(prec)
+        st = TrainStep(m, args.variant, graph=True, world_size=1)
+        for _ in range(4):
+            st(img_d, lab_d)
+        torch.cuda.synchronize()
+        n = 3 if prec == "fp16x3" else 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            st(img_d, lab_d)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out[prec] = {"ms_per_step": round(ms, 3), "images_per_sec": round(img_d.shape[0] / ms * 1e3, 1)}
+        del st, m
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -170,18 +391,15 @@ def main():
     from wsl4mis_b200.engine import TrainStep
     from wsl4mis_b200.networks.unet import UNet, UNet_CCT
 
-    N = args.batch
+    # weak scaling: --batch images per GPU; strong scaling: --batch images in total (config 4's sweep)
+    N = args.batch if args.scaling == "weak" else max(1, args.batch // world)
     torch.manual_seed(2022)
-    model = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4).to(dev)
+    model = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4).to(dev).set_precision(args.precision)
     step = TrainStep(model, args.variant, base_lr=0.01, max_iterations=30000, graph=not args.no_graph, world_size=world)
 
     # synthetic batch: image ~ U[0,1), ~3 % scribble pixels; different per rank
-    g = torch.Generator().manual_seed(2022 + rank)
-    img_h = torch.rand(N, 1, HW, HW, generator=g).pin_memory()
-    lab_h = torch.full((N, HW, HW), 4, dtype=torch.uint8)
-    m = torch.rand(N, HW, HW, generator=g) < 0.03
-    lab_h[m] = torch.randint(0, 4, (int(m.sum()),), generator=g, dtype=torch.uint8)
-    lab_h = lab_h.pin_memory()
+    img_h, lab_h = synth(N, 2022 + rank)
+    img_h, lab_h = img_h.pin_memory(), lab_h.pin_memory()
     img_d, lab_d = img_h.to(dev), lab_h.to(dev)
 
     def barrier():
@@ -265,9 +483,9 @@ def main():
     ms_dev, ms_e2e = t.tolist()
 
     # ---- per-kernel table (eager, CUDA events around every C-ABI launch), rank 0, outside the timed regions ----
-    table, roof, launches_per_step = None, None, None
+    table, roof, layers, launches_per_step = None, None, None, None
+    peaks = load_peaks()
     if rank == 0 and not args.no_kernel_table:
-        peaks = load_peaks()
         prof = _lib.Profiler()
         eager = TrainStep(model, args.variant, graph=False, world_size=1)
         eager.ex.multi_stream = False        # serialise: per-kernel event times are only meaningful without overlap
@@ -287,57 +505,82 @@ def main():
             if meta is not None:
                 d["flops"] += meta[2] * cnt
                 d["bytes"] += meta[3] * cnt
-        detail = sorted(((name, meta[0], meta[1], cnt, ms / cnt, meta[2] / (ms / cnt * 1e-3) / 1e12, meta[3] / (ms / cnt * 1e-3) / 1e9)
+        detail = sorted(((name, meta[0], meta[1], cnt, ms / cnt, meta[2] / (ms / cnt * 1e-3) / 1e12, meta[3] / (ms / cnt * 1e-3) / 1e9, meta[2], meta[3])
                          for (name, meta), (cnt, ms) in agg.items() if meta is not None), key=lambda r: -r[3] * r[4])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "kernel_detail.txt"), "w") as f:
             f.write("entry kind layer launches avg_ms TFLOP/s algorithmic_GB/s\n")
             for r in detail:
                 f.write(f"{r[0]} {r[1]} {r[2]} {r[3] // n_prof} {r[4]:.4f} {r[5]:.1f} {r[6]:.0f}\n")
+        # top launches, each against the roofline that bounds it (per-kernel event timing: burst tensor peak, measured copy GB/s)
+        ridge = peaks["tf_burst"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        layers = []
+        for r in detail[:12]:
+            flops, byts = r[7], r[8]
+            tensor_bound = byts > 0 and flops / byts > ridge
+            frac = (r[5] / peaks["tf_burst"]) if tensor_bound else (r[6] / peaks["hbm_gbs"])
+            layers.append({"entry": r[0], "kind": r[1], "layer": r[2], "launches_per_step": r[3] // n_prof, "us": round(r[4] * 1e3, 1),
+                           "tflops": round(r[5], 1), "algorithmic_gbs": round(r[6]), "bound": "tensor" if tensor_bound else "hbm",
+                           "frac": round(frac, 3)})
         tot = sum(d["ms"] for d in byname.values())
         launches_per_step = sum(d["launches"] for d in byname.values()) // n_prof
         table = {k: {"launches_per_step": v["launches"] // n_prof, "ms_per_step": round(v["ms"] / n_prof, 4),
                      "share": round(v["ms"] / tot, 4),
-                     **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {})}
+                     **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] else {}),
+                     **({"algorithmic_gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9)} if v["bytes"] and not v["flops"] else {})}
                  for k, v in sorted(byname.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(byname.items(), key=lambda kv: kv[1]["ms"])
         name, v = top
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("kernel") == name:
-                traffic = {"dram_MB_per_launch": round(tj["dram_bytes_per_launch_MB"], 1), "source": tj["source"]}
+        for tp in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if tj.get("kernel") == name:
+                    traffic = {"dram_MB_per_launch": round(tj["dram_bytes_per_launch_MB"], 1), "source": tj["source"]}
+                    break
         if v["flops"] > 0:
             ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
-            roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": round(ach / peaks["tf_sustained"], 4), "traffic": traffic,
+            roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                    "frac": round(ach / peaks["tf_burst"], 4), "frac_of_sustained": round(ach / peaks["tf_sustained"], 4), "traffic": traffic,
                     "algorithmic_MB_per_launch": round(v["bytes"] / v["launches"] / 1e6, 1),
-                    "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)",
+                    "peak_source": peaks["src"] + " bf16 burst (kernels timed one by one with CUDA events; the step is not power-limited)",
                     "avg_launch_ms": round(v["ms"] / v["launches"], 4), "algorithmic_flops_per_launch": v["flops"] / v["launches"]}
         else:
-            byts = 36.0 * N * HW * HW if "gatedcrf" in name else 0.0
-            ach = byts * (v["launches"]) / (v["ms"] * 1e-3) / 1e9 if byts else 0.0
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else 0.0
             roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["src"]}
+                    "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peaks["src"],
+                    "avg_launch_ms": round(v["ms"] / v["launches"], 4), "algorithmic_MB_per_launch": round(v["bytes"] / v["launches"] / 1e6, 1)}
+
+    lps, graph_on = step.launches_per_step, step.graph_enabled     # C-ABI launches per step, counted by TrainStep at capture time
+    parity = modes = gpu_base = None
+    if rank == 0 and world == 1 and not args.skip_extras:
+        parity = parity_report(args, dev)
+        modes = time_other_modes(args, dev, img_d, lab_d, world)
+    if rank == 0 and world == 1 and not args.skip_gpu_baseline:
+        del step
+        torch.cuda.empty_cache()
+        gpu_base = gpu_reference_baseline(args, dev, img_d, lab_d)
 
     if rank == 0:
-        cb = None if args.skip_cpu else cpu_step_time(args.model, args.variant, args.cpu_sample, 2, 1)[0]
+        cb = None if args.skip_cpu else cpu_reference_time(args, args.cpu_sample, 3, 1)[0]
         imgs = N * world * K
         line = {
-            "metric": METRIC, "value": imgs / (ms_dev * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "metric": metric_name(args), "value": imgs / (ms_dev * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp16x3": "f32 (fp16 hi/lo split tensor-core products)", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": f"{args.model} {args.variant} train step (fwd+loss+bwd+SGD), {N}x1x{HW}x{HW} per GPU, "
                                    f"loss on main_seg (SURVEY F7)", "global_batch": N * world, "parallelism": f"dp{world}",
-                       "cuda_graph": step.graph_enabled, "bn": "per-rank batch statistics (stock DDP semantics)",
+                       "precision": args.precision, "cuda_graph": bool(graph_on),
+                       "bn": "per-rank batch statistics (stock DDP semantics)",
                        "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush needed"},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel()), "d2h_bytes_per_step": 4},
-            "gpu_launches": (step.launches_per_step * K) if step.graph_enabled else launches_eager,
-            "gpu_launches_per_step": step.launches_per_step,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": table,
-            "loss_first": first_loss, "loss_last": float(lv),
+            "gpu_launches": (lps * K) if graph_on else launches_eager,
+            "gpu_launches_per_step": lps,
+            "clocks": clocks, "roofline": roof, "layers": layers, "cpu_baseline": cb, "gpu_baseline": gpu_base, "parity": parity, "modes": modes,
+            "kernels": table, "loss_first": first_loss, "loss_last": float(lv),
         }
         print(json.dumps(line))
     if dist is not None:

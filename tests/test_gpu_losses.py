@@ -73,11 +73,23 @@ def test_gatedcrf_border_and_ragged_tiles(kat):
     assert np.allclose(g.cpu().numpy(), kat["crf2:grad_y"], rtol=5e-4, atol=1e-7)
 
 
-def test_gatedcrf_rejects_unsupported():
-    y = torch.softmax(torch.randn(1, 4, 16, 16, device=DEV), 1)
+def test_gatedcrf_other_argument_patterns_take_the_general_path():
+    """radius 3 is not the scripts' pattern: the tensor-expression formulation runs (on the GPU tensors) and matches the oracle; the
+    shape contract of gate_crf_loss.py:51-57 still raises AssertionError."""
+    y = torch.softmax(torch.randn(1, 4, 16, 16, device=DEV), 1).requires_grad_(True)
     img = torch.rand(1, 1, 16, 16, device=DEV)
-    with pytest.raises(NotImplementedError):
-        ModelLossSemsegGatedCRF()(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 3, img, 16, 16)
+    out = ModelLossSemsegGatedCRF()(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 3, img, 16, 16)["loss"]
+    (g,) = torch.autograd.grad(out, y)
+    yc = y.detach().cpu().requires_grad_(True)
+    ref = O.gated_crf_loss(yc, img.cpu(), radius=3)
+    (gr,) = torch.autograd.grad(ref, yc)
+    assert abs(out.item() - ref.item()) < 3e-5 * abs(ref.item())
+    assert np.allclose(g.cpu().numpy(), gr.numpy(), rtol=5e-4, atol=1e-7)
+    # the scripts' pattern itself through the module equals the general formulation evaluated explicitly
+    from wsl4mis_b200.utils.gate_crf_loss import _general_forward
+    fast = ModelLossSemsegGatedCRF()(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 16, 16)["loss"]
+    gen = _general_forward(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 16, 16, None, None, None, None, False)["loss"]
+    assert abs(fast.item() - gen.item()) < 3e-5 * abs(gen.item())
     with pytest.raises(AssertionError):
         ModelLossSemsegGatedCRF()(y, [{"weight": 1, "xy": 6, "rgb": 0.1}], 5, img, 17, 16)
 

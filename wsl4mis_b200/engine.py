@@ -72,13 +72,24 @@ class TrainStep:
         self.n_heads_trained = 2 if (variant == "dmpls") else 1
         if variant == "dmpls":
             assert self.two_heads, "dmpls needs a two-head model (unet_cct)"
-        # parameter range that receives gradients (encoder + trained decoders are a prefix of parameters())
+        # Parameters that receive gradients in this step body: everything the executor runs except (a) the aux decoder when
+        # only main_seg enters the loss and (b) deep-supervision heads (UNet_DS: the variants use output 0 only;
+        # out_conv_dp4 never runs at all).  Like torch.optim.SGD with grad=None, the fused optimiser leaves those untouched:
+        # it walks the contiguous segments of trained parameters in the flat buffer.
+        skip = set()
         if self.two_heads and self.n_heads_trained == 1:
-            aux = self.model.aux_decoder1
-            first_aux = next(aux.parameters())
-            self.n_trained = self.offsets[id(first_aux)][0]
-        else:
-            self.n_trained = n
+            skip.update(id(q) for q in self.model.aux_decoder1.parameters())
+        skip.update(id(q) for nm, q in model.named_parameters() if "out_conv_dp" in nm)
+        self.segments = []
+        for p in params:
+            if id(p) in skip or id(p) not in self.ex.used_param_ids:
+                continue
+            off_p, n_p = self.offsets[id(p)]
+            if self.segments and self.segments[-1][0] + self.segments[-1][1] == off_p:
+                self.segments[-1][1] += n_p
+            else:
+                self.segments.append([off_p, n_p])
+        self.n_trained = self.segments[-1][0] + self.segments[-1][1]     # prefix that holds every trained parameter (the all-reduce payload)
         self.loss_parts = {}
         self.launches_per_step = 0
 
@@ -196,9 +207,9 @@ class TrainStep:
         return loss, gflat
 
     def _opt(self, gflat):
-        n = self.n_trained
-        call("wsl_sgd_step", self.flat, gflat, self.mom, n, self.lr_dev, self.base_lr, self.momentum, self.weight_decay,
-             1.0 / self.world_size)
+        for off, n in self.segments:
+            call("wsl_sgd_step", self.flat[off:], gflat[off:], self.mom[off:], n, self.lr_dev, self.base_lr, self.momentum,
+                 self.weight_decay, 1.0 / self.world_size)
 
     def _allreduce(self, gflat):
         if self.world_size > 1:
@@ -251,13 +262,15 @@ class TrainStep:
                         g2 = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g2):
                             self._opt(gg)
-                    self._graphs[idx] = (g1, g2, gloss, gg)
-                g1, g2, gloss, gg = self._graphs[idx]
+                    self._graphs[idx] = (g1, g2, gloss, gg, self._outs, dict(self.loss_parts))
+                g1, g2, gloss, gg, self._outs, self.loss_parts = self._graphs[idx]
                 g1.replay()
                 if self.world_size > 1:
                     self._allreduce(gg)
                     g2.replay()
-                loss = gloss
+                # the captured loss lives in graph-pool memory that the next replay overwrites: hand out a copy
+                # (step.outputs / step.loss_parts still alias the pool: read them before the next step)
+                loss = gloss.clone()
         # poly LR applied after the step with the pre-increment iteration (...pCE_2D.py:106-108)
         lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
         self.lr_dev.fill_(lr_)
@@ -290,8 +303,12 @@ class UAMTStep:
     Two-head models (unet_cct) use main_seg on both sides."""
 
     def __init__(self, model, ema_model, base_lr=0.01, max_iterations=30000, consistency=0.1, consistency_rampup=200.0,
-                 momentum=0.9, weight_decay=1e-4, T=8):
+                 momentum=0.9, weight_decay=1e-4, T=8, process_group=None, world_size=1):
+        """world_size > 1: batch-sharded data parallel -- every rank runs the step on its shard, the flat gradient bucket is
+        all-reduced (sum) over NCCL and the fused SGD applies the 1/world mean, as `TrainStep` does.  The student replicas are
+        broadcast from rank 0 at construction; the teacher is never updated by the reference and is broadcast once."""
         from .utils import ramps
+        self.world_size, self.pg = int(world_size), process_group
         self.ramps = ramps
         self.model, self.ema_model = model, ema_model
         self.ex, self.ex_t = model.executor, ema_model.executor
@@ -311,9 +328,14 @@ class UAMTStep:
             off += p.numel()
         first_aux = next(model.aux_decoder1.parameters()) if len(self.ex.dec) == 2 else None
         self.n_trained = n if first_aux is None else sum(p.numel() for p in params[: [id(q) for q in params].index(id(first_aux))])
+        if self.world_size > 1:
+            ddp.broadcast_flat(self.flat, 0, self.pg)
+            for q in list(ema_model.parameters()) + list(ema_model.buffers()):
+                ddp.broadcast_flat(q.data, 0, self.pg)
         self.mom = torch.zeros_like(self.flat)
         self.lr_dev = torch.full((1,), self.base_lr, dtype=torch.float32, device=dev)
-        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        from .networks._engine import initial_rng_counter
+        self.seed_dev = torch.full((1,), initial_rng_counter() ^ 0x5A5A5A5A, dtype=torch.int64, device=dev)
 
     def _noisy(self, x, reps, salt, given):
         if given is not None:
@@ -367,7 +389,10 @@ class UAMTStep:
         nd = len(ex.dec)
         ex.backward(slot_u, [dl_u] + [None] * (nd - 1), zero_grads=True)
         g = ex.backward(slot_l, [dl_l] + [None] * (nd - 1), zero_grads=False)
-        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay, 1.0)
+        if self.world_size > 1:
+            ddp.allreduce_flat(g[: self.n_trained], self.pg)
+        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay,
+             1.0 / self.world_size)
         lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
         self.lr_dev.fill_(lr_)
         self.iter_num += 1
@@ -433,7 +458,10 @@ class USTMStep(UAMTStep):
         loss = st[0] + cw * cst[2]
         self.parts = {"ce": st[0], "consistency": cst[2], "weight": cw, "threshold": thr, "mask": mask}
         g = ex.backward(slot, [d] + [None] * (len(ex.dec) - 1))
-        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay, 1.0)
+        if self.world_size > 1:
+            ddp.allreduce_flat(g[: self.n_trained], self.pg)
+        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay,
+             1.0 / self.world_size)
         alpha = min(1 - 1 / (self.iter_num + 1), self.ema_decay)         # :63, global_step = iter_num before the increment
         call("wsl_ema_update", self.tflat, self.flat, min(self.tflat.numel(), self.flat.numel()), float(alpha))
         lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9

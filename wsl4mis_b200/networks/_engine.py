@@ -44,6 +44,24 @@ def _ceil16(c):
     return (c + 15) // 16 * 16
 
 
+def initial_rng_counter():
+    """Start value of the device-side dropout / noise counter: a hash of torch's seed (the scripts call
+    torch.manual_seed(args.seed), train_weakly_supervised_pCE_2D.py:187-190) and of the data-parallel rank, so that different
+    --seed runs draw different masks and the ranks of one job draw different masks on their shards."""
+    rank = 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank()
+        else:
+            rank = int(os.environ.get("RANK", "0"))
+    except Exception:
+        rank = 0
+    z = (torch.initial_seed() * 0x9E3779B97F4A7C15 + (rank + 1) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 31
+    return int(z & 0x3FFFFFFFFFFF)           # 46 bits: room for ~10^13 increments inside int64
+
+
 class ConvLayer:
     """One nn.Conv2d (+ optional following BatchNorm2d/LeakyReLU/Dropout) and its packed operands."""
 
@@ -314,6 +332,7 @@ class UNetExecutor:
                 bn = L.bn
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0, N, H, W, L.CoutP, cout_store, L.ks, self.dt,
                      sb, ctypes.addressof(self._stat_rows))
+                self._untag()                      # the finalize launch is not a convolution: keep it out of the conv roofline rows
                 call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
                      bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
                 rows = True
@@ -346,6 +365,7 @@ class UNetExecutor:
         self._untag()
 
     def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False):
+        self.last_backward_param_ids.update((id(L.conv.weight), id(L.conv.bias)))
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
         c0 = L.srcC[0]
@@ -404,6 +424,7 @@ class UNetExecutor:
 
     def bn_bwd(self, L: ConvLayer, y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, dy, N, H, W, slot, tag):
         bn = L.bn
+        self.last_backward_param_ids.update((id(bn.weight), id(bn.bias)))
         C = L.Cout
         coef = self.buf(slot, tag + ".coef", (2 * C,), torch.float32)
         p = L.drop_p
@@ -475,7 +496,7 @@ class UNetExecutor:
         assert H % 16 == 0 and W % 16 == 0, "H, W must be multiples of 16 (4 pooling levels)"
         self.dev = x.device
         if not hasattr(self, "seed_dev") or self.seed_dev.device != self.dev:
-            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.seed_dev = torch.full((1,), initial_rng_counter(), dtype=torch.int64, device=self.dev)
         x = x.contiguous()
         slot = self._acquire_slot() if need_grad else "ng"
         self.pack_all()
@@ -604,6 +625,8 @@ class UNetExecutor:
         elif S != 1.0:
             gflat.mul_(S)                      # the bucket holds unscaled gradients of an earlier pass: bring them to this pass' scale
         self._accumulate = not zero_grads      # BN affine gradients are written (not added) unless accumulating
+        if zero_grads or not hasattr(self, "last_backward_param_ids"):
+            self.last_backward_param_ids = set()   # ids of the parameters this backward (chain) produced gradients for
         B = lambda name, shape, dt=None: self.buf(slot, "g." + name, shape, dt)
 
         def block_bwd(tag, blk, r, g0, g1=None, cs1=None, gpool=None, need_dsrc=True):

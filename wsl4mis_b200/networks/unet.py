@@ -112,15 +112,24 @@ class _NetFn(torch.autograd.Function):
         ex = holder.executor
         outs, slot = ex.forward(x, training, need, masks, chan_keep)
         ctx.ex, ctx.slot, ctx.nparams = ex, slot, len(params)
+        ctx.set_materialize_grads(False)       # an output the loss never touched arrives as None, not as a zero tensor
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gouts):
         ex = ctx.ex
-        ex.backward(ctx.slot, list(gouts))
-        views = ex.grads()[1]
-        return (None, None, None, None, None, None) + tuple(views[id(p)].clone() if id(p) in ex.used_param_ids else None
-                                                            for p in ex.params)
+        gflat = ex.backward(ctx.slot, list(gouts))
+        # ONE copy of the flat bucket (the executor reuses it next step); parameters whose sub-network received no gradient
+        # (an unused aux decoder / deep-supervision head, Decoder_DS.out_conv_dp4) get None, exactly like autograd on the
+        # reference modules -- torch.optim.SGD then skips them instead of applying weight decay and momentum
+        flat = gflat.clone()
+        live = ex.last_backward_param_ids
+        grads, off = [], 0
+        for p in ex.params:
+            n = p.numel()
+            grads.append(flat[off:off + n].view_as(p) if id(p) in live else None)
+            off += n
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 class _Holder:
