@@ -153,7 +153,7 @@ int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1, int src
 /* first layer (Cin = 1 -> 16, unet.py:81): x fp32 [N,H,W], w fp32 torch layout [16][1][3][3], y bf16 NHWC; and its
  * weight gradient (dw accumulated, zero-filled by the caller; the bias feeds BatchNorm -> zero gradient). */
 int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout,
-                   cudaStream_t stream);
+                   float* stat_partials, int* stat_rows_host, cudaStream_t stream);   /* stat_*: as for wsl_conv_tc2 (optional) */
 int wsl_wgrad_first(const float* x, const void* dy, int dtype, float* dw, int N, int H, int W, int Cout,
                     cudaStream_t stream);
 
@@ -226,6 +226,13 @@ int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, con
                const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws, int accumulate,
                cudaStream_t stream);
+
+/* first layer (1 -> 16 channels, unet.py:81 in_conv): BatchNorm backward + the convolution's weight gradient in one pass -- dY is
+ * formed in registers and never stored (the image needs no data gradient): dgamma / dbeta as wsl_bn_bwd, dw[16][1][3][3] += dY^T * x. */
+int wsl_bn_bwd_first(const void* y, int dtype, const float* ss, const float* save, const void* g0, const uint8_t* mask,
+                     unsigned long long seed, const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W,
+                     float* dgamma, float* dbeta, float* coef, const float* image, float* dw, float* ws, int accumulate,
+                     cudaStream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:56-57) and its transpose. */
 int wsl_upsample2x_fwd(const void* t, int dtype, int N, int h, int w, int C, void* u, cudaStream_t stream);

@@ -299,10 +299,16 @@ def test_first_layer_kernels(shape):
     w = torch.randn(16, 1, 3, 3, generator=g) * 0.5
     b = torch.randn(16, generator=g) * 0.1
     y = torch.zeros((N, H, W, 16), device=DEV, dtype=BF)
-    call("wsl_conv_first", x.to(DEV), w.to(DEV), b.to(DEV), y, 0, N, H, W, 16)
+    import ctypes
+    rows = ctypes.c_int(0)
+    parts = torch.zeros(592 * 2 * 16, device=DEV)
+    call("wsl_conv_first", x.to(DEV), w.to(DEV), b.to(DEV), y, 0, N, H, W, 16, parts, ctypes.addressof(rows))
     torch.cuda.synchronize()
     ref = F.conv2d(x, w, b, padding=1)
     assert (nchw(y.cpu()) - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    st = parts[: rows.value * 32].view(rows.value, 2, 16).double().sum(0).cpu()        # fused BatchNorm statistics of the stored values
+    o = nchw(y.cpu()).double()
+    assert torch.allclose(st[0], o.sum((0, 2, 3)), rtol=1e-5, atol=1e-3) and torch.allclose(st[1], (o * o).sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
     dy = bf16_round(torch.randn(N, 16, H, W, generator=g))
     dw = torch.zeros(16, 1, 3, 3, device=DEV)
     call("wsl_wgrad_first", x.to(DEV), nhwc(dy).to(DEV), 0, dw, N, H, W, 16)
@@ -402,6 +408,44 @@ def test_bn_backward_chain(shape):
     assert rel_l2(dgam.cpu(), dgr.float()) < 1e-4
     assert rel_l2(dbet.cpu(), dbr.float()) < 1e-4
     assert rel_l2(nchw(dy.cpu()), dyr.float()) < 2 ** -8
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16), (3, 24, 40), (2, 64, 128)])
+@pytest.mark.parametrize("dt", [0, 1])
+def test_first_layer_fused_backward(shape, dt):
+    """wsl_bn_bwd_first: conv(1->16) -> BN(train) -> LeakyReLU -> dropout; dgamma, dbeta and the convolution's weight gradient
+    against fp64 autograd (dY itself is never materialised)."""
+    N, H, W = shape
+    C = 16
+    g = torch.Generator().manual_seed(41)
+    x = torch.rand(N, 1, H, W, generator=g)
+    w = torch.randn(C, 1, 3, 3, generator=g) * 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    p = 0.05
+    mask = (torch.rand(N, C, H, W, generator=g) >= p)
+    g0 = torch.randn(N, C, H, W, generator=g)
+    tdt = torch.float32 if dt == 1 else BF
+    y = F.conv2d(x, w, b, padding=1).to(tdt).float()           # the stored convolution output
+    g0 = g0.to(tdt).float()
+    wr = w.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    yr = F.conv2d(x.double(), wr, b.double(), padding=1)
+    yr = yr + (y.double() - yr).detach()                        # evaluate at the stored values, differentiate through the conv
+    a = F.leaky_relu(F.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5), 0.01) * mask / (1 - p)
+    dwr, dgr, dbr = torch.autograd.grad(a, [wr, gr, br], g0.double())
+    yd = nhwc(y, tdt).to(DEV)
+    save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
+    call("wsl_bn_stats", yd, dt, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
+    mk = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
+    dgam, dbet, coef = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2 * C, device=DEV)
+    dw = torch.zeros(C, 1, 3, 3, device=DEV)
+    call("wsl_bn_bwd_first", yd, dt, ss, save, nhwc(g0, tdt).to(DEV), mk, 0, None, p, 0.01, N, H, W, dgam, dbet, coef, x.to(DEV), dw,
+         workspace("bn"), 0)
+    torch.cuda.synchronize()
+    tol = 1e-4 if dt == 1 else 2 ** -7
+    assert rel_l2(dgam.cpu(), dgr.float()) < tol and rel_l2(dbet.cpu(), dbr.float()) < tol
+    assert rel_l2(dw.cpu(), dwr.float()) < tol, rel_l2(dw.cpu(), dwr.float())
 
 
 def test_bn_backward_is_well_conditioned_at_the_baseline_shape():

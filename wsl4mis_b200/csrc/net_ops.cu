@@ -153,37 +153,93 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
 // ================================================================================================
 // first layer (Cin = 1, unet.py:81 in_conv): x fp32 [N,H,W] -> y bf16 [N,H,W,16]; HBM-bound (36 B/pixel)
 // ================================================================================================
+// Two horizontally adjacent pixels x eight channels per thread: the 3 x 4 input window is loaded once, every tap's weights are read
+// from shared memory as 16-byte vectors and used for both pixels (the one-pixel form issued 144 scalar shared-memory loads per pixel and
+// was bound by the LDS pipe: 85 us for 64 x 256 x 256 against the 23 us its 150 MB of traffic need).  Optional fused BatchNorm
+// statistics: per-CTA rows {sum, sum of squares} of the values as stored, finalised by bn_finalize_kernel like conv_tc2's.
+__device__ __forceinline__ float4 lds128_volatile(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TPB, 4) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w /*[16][9]*/,
                                                          const float* __restrict__ bias, T* __restrict__ y,
-                                                         int N, int H, int W) {
-  __shared__ float s_w[9][16];
-  __shared__ float s_b[16];
+                                                         int N, int H, int W, float* __restrict__ stat_partials) {
+  __shared__ __align__(16) float s_w[9][16];
+  __shared__ __align__(16) float s_b[16];
+  __shared__ float s_stat[TPB / 32][32];
   if (threadIdx.x < 144) s_w[threadIdx.x % 9][threadIdx.x / 9] = w[threadIdx.x];
   if (threadIdx.x < 16) s_b[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long long total = (long long)N * H * W;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-    const int xx = (int)(i % W), yy = (int)((i / W) % H);
-    const float* base = x + (i - (long long)yy * W - xx);
-    float v[9];
+  // thread = (pixel pair, channel half): lanes 2k / 2k+1 own channels 0-7 / 8-15 of the same two pixels, so a pair of lanes
+  // stores one full 32-byte pixel and the input window is a broadcast load
+  const int half = threadIdx.x & 1;
+  const int PW = (W + 1) >> 1;                                   // pixel pairs per row
+  const int total = N * H * PW;                                    // 32-bit indexing (64-bit div / mod dominated the loop)
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ssum[c] = ssq[c] = 0.f;
+  const float4 bl = reinterpret_cast<const float4*>(s_b)[half * 2], bh = reinterpret_cast<const float4*>(s_b)[half * 2 + 1];
+  for (int i = (blockIdx.x * TPB + threadIdx.x) >> 1; i < total; i += (gridDim.x * TPB) >> 1) {
+    const int xp = i % PW, q_ = i / PW, yy = q_ % H;
+    const long long n = q_ / H;
+    const int xx = xp * 2;
+    const bool two = xx + 1 < W;
+    const float* img = x + n * (long long)H * W;
+    float v[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int gy = yy + a - 1;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int gx = xx + b - 1;
+        v[a][b] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(long long)gy * W + gx] : 0.f;
+      }
+    }
+    float o0[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w}, o1[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
-      v[t] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? base[(long long)gy * W + gx] : 0.f;
+      const float a0 = v[t / 3][t % 3], a1 = v[t / 3][t % 3 + 1];
+      // volatile shared-memory loads: as plain loads the compiler hoists all 72 loop-invariant weights out of the pixel loop
+      // and spills them (272 bytes of stack per thread, 141 us)
+      const float4 wl = lds128_volatile(&s_w[t][half * 8]), wh = lds128_volatile(&s_w[t][half * 8 + 4]);
+      o0[0] = fmaf(a0, wl.x, o0[0]); o0[1] = fmaf(a0, wl.y, o0[1]); o0[2] = fmaf(a0, wl.z, o0[2]); o0[3] = fmaf(a0, wl.w, o0[3]);
+      o0[4] = fmaf(a0, wh.x, o0[4]); o0[5] = fmaf(a0, wh.y, o0[5]); o0[6] = fmaf(a0, wh.z, o0[6]); o0[7] = fmaf(a0, wh.w, o0[7]);
+      o1[0] = fmaf(a1, wl.x, o1[0]); o1[1] = fmaf(a1, wl.y, o1[1]); o1[2] = fmaf(a1, wl.z, o1[2]); o1[3] = fmaf(a1, wl.w, o1[3]);
+      o1[4] = fmaf(a1, wh.x, o1[4]); o1[5] = fmaf(a1, wh.y, o1[5]); o1[6] = fmaf(a1, wh.z, o1[6]); o1[7] = fmaf(a1, wh.w, o1[7]);
     }
-    float o[16];
+    const long long pix = (n * H + yy) * (long long)W + xx;
+    st8(y + pix * 16 + half * 8, o0);
+    if (two) st8(y + (pix + 1) * 16 + half * 8, o1);
+    if (stat_partials) {
+      round8<T>(o0);
+      round8<T>(o1);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = s_b[c];
+      for (int c = 0; c < 8; ++c) {
+        ssum[c] += o0[c];
+        ssq[c] = fmaf(o0[c], o0[c], ssq[c]);
+        if (two) { ssum[c] += o1[c]; ssq[c] = fmaf(o1[c], o1[c], ssq[c]); }
+      }
+    }
+  }
+  if (stat_partials) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < 8; ++c) {
+      float a = ssum[c], b = ssq[c];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) o[c] = fmaf(v[t], s_w[t][c], o[c]);
-    float lo[8], hi[8];
+      for (int o = 16; o > 1; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }   // lanes of equal parity
+      if (lane < 2) { s_stat[warp][lane * 8 + c] = a; s_stat[warp][16 + lane * 8 + c] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float a = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { lo[c] = o[c]; hi[c] = o[8 + c]; }
-    st8(y + i * 16, lo);
-    st8(y + i * 16 + 8, hi);
+      for (int wv = 0; wv < TPB / 32; ++wv) a += s_stat[wv][threadIdx.x];
+      stat_partials[(size_t)blockIdx.x * 32 + threadIdx.x] = a;      // row layout [2][16], like the conv_tc2 epilogue rows
+    }
   }
 }
 
@@ -837,117 +893,188 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
   }
 }
 
+// First layer (Cin = 1 -> 16, unet.py:81): the BatchNorm-backward apply pass and the weight gradient in ONE kernel.  dY of the first
+// layer has no other consumer (there is no data gradient towards the image), so it is formed in registers,
+//   dY = dz*scale + y*B + D,   dW[co][t] += sum_p dY[p][co] * x[p + tap_t],
+// and never written: replaces bn_bwd_apply (read 2, write 1 activation-sized tensors) + wgrad_first (read 1) by one pass that reads 2.
+// Thread = (pixel, channel half); two pixels in flight; 8 x 9 accumulators per thread, reduced over the warp / block, one atomicAdd per
+// value and block.
+template <typename T>
+__global__ void __launch_bounds__(TPB, 1) bn_bwd_apply_first_kernel(BnBwdArgs<T> a, const float* __restrict__ coef, const float* __restrict__ x,
+                                                                    float* __restrict__ dw /*[16][9]*/) {
+  // (a channel-QUARTER mapping with 36 accumulators and two blocks per SM was measured slower, 240 vs 177 us: the bytes in flight per
+  // SM are what bounds this kernel, and halving the bytes per thread cancels the doubled thread count)
+  const BnBwdThread t = bn_bwd_thread(a);          // C == 16: cg == 2, t.g = channel half
+  const int C = 16, rows = TPB / 2;
+  const int P = a.N * a.H * a.W;
+  const int r = threadIdx.x >> 1;
+  float kb_[8], kd_[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { kb_[j] = coef[t.c0 + j]; kd_[j] = coef[C + t.c0 + j]; }
+  float acc[8][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[j][k] = 0.f;
+  auto window = [&](int p, float (&v)[9]) {
+    const int xx = p % a.W, q = p / a.W, yy = q % a.H;
+    const float* base = x + (long long)(p - yy * a.W - xx);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int gy = yy + k / 3 - 1, gx = xx + k % 3 - 1;
+      v[k] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? base[(long long)gy * a.W + gx] : 0.f;
+    }
+  };
+  auto accumulate = [&](const float (&dz)[8], const float (&yv)[8], const float (&v)[9]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float o = fmaf(dz[j], t.sc[j], fmaf(yv[j], kb_[j], kd_[j]));
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[j][k] = fmaf(o, v[k], acc[j][k]);
+    }
+  };
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + stride < P; p += 2 * stride) {
+    float dz0[8], y0[8], dz1[8], y1[8], v0[9], v1[9];
+    bn_bwd_gather8<0>(a, t, p, dz0, y0);
+    bn_bwd_gather8<0>(a, t, p + stride, dz1, y1);
+    window(p, v0);
+    window(p + stride, v1);
+    bn_bwd_finish8(a, t, p, dz0, y0);
+    bn_bwd_finish8(a, t, p + stride, dz1, y1);
+    accumulate(dz0, y0, v0);
+    accumulate(dz1, y1, v1);
+  }
+  if (p < P) {
+    float dz[8], yv[8], v[9];
+    bn_bwd_gather8<0>(a, t, p, dz, yv);
+    window(p, v);
+    bn_bwd_finish8(a, t, p, dz, yv);
+    accumulate(dz, yv, v);
+  }
+  __shared__ float s_red[TPB / 32][2][72];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float v = acc[j][k];
+#pragma unroll
+      for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);       // lanes of equal parity = same channel half
+      if (lane < 2) s_red[warp][lane][j * 9 + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 144) {
+    const int half = threadIdx.x / 72, e = threadIdx.x % 72;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < TPB / 32; ++wv) v += s_red[wv][half][e];
+    atomicAdd(dw + half * 72 + e, v);                                               // dw[co][t], co = half*8 + j
+  }
+}
+
 // ================================================================================================
 // bilinear x2 upsample, align_corners=True (nn.Upsample(scale_factor=2, mode='bilinear'), unet.py:56-57)
 // index arithmetic follows ATen's area_pixel_compute_source_index for align_corners: src = dst*(in-1)/(out-1)
 // ================================================================================================
-__device__ __forceinline__ void up_src(int d, int in, int out, int& i0, int& i1, float& lam) {
-  const float r = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
-  const float s = r * (float)d;
-  i0 = (int)s;
-  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
-  lam = s - (float)i0;
+// With align_corners=True and out = 2*in, src(Y) = Y*(in-1)/(2*in-1): output rows 2i and 2i+1 interpolate between source rows
+// (i-1, i) and (i, i+1) respectively (src(2i) = i - i/(2in-1), src(2i+1) = i + (in-1-i)/(2in-1)), and likewise for columns.  So a
+// 2 x 2 block of output pixels needs exactly the 3 x 3 source neighbourhood of (i, j): nine 16-byte loads for four stores instead
+// of sixteen (the old one-pixel-per-thread form was bound by L2 read bandwidth: 4 loads per stored vector).
+// Weight of the upper / left source of output index Y = 2i + a: lam = clamp(src(Y) - (i - 1 + a), 0, 1) (clamped border rows coincide).
+__device__ __forceinline__ float up_lam(int Y, int i_base, float ratio) {
+  return fminf(fmaxf(ratio * (float)Y - (float)i_base, 0.f), 1.f);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(TPB) upsample2x_fwd_kernel(const T* __restrict__ t, int N, int h, int w, int C,
                                                              T* __restrict__ u) {
-  // thread t owns channel group g = t % (C/8); rows of the block walk output pixels (32-bit indexing)
-  const int cg = C >> 3, rows = TPB / cg, H = 2 * h, W = 2 * w;
-  const int g = threadIdx.x % cg, r = threadIdx.x / cg, c0 = g * 8;
-  const int P = N * H * W;
+  const int cg = C >> 3, H = 2 * h, W = 2 * w;
   const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  auto src = [&](int p, const T*& pa, const T*& pb, const T*& pc, const T*& pd, float& lx, float& ly) {
-    const int x = p % W, q = p / W, y = q % H, n = q / H;
-    const float sy = ry * (float)y, sx = rx * (float)x;
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
-    ly = sy - (float)y0;
-    lx = sx - (float)x0;
-    const T* base = t + (long long)n * h * w * C + c0;
-    pa = base + (y0 * w + x0) * C; pb = base + (y0 * w + x1) * C; pc = base + (y1 * w + x0) * C; pd = base + (y1 * w + x1) * C;
-  };
-  const int stride = gridDim.x * rows;
-  int p = blockIdx.x * rows + r;
-  for (; p + stride < P; p += 2 * stride) {      // two output pixels per iteration, all eight loads issued first
-    const T *a0, *b0, *c0p, *d0, *a1, *b1, *c1p, *d1;
-    float lx0, ly0, lx1, ly1;
-    src(p, a0, b0, c0p, d0, lx0, ly0);
-    src(p + stride, a1, b1, c1p, d1, lx1, ly1);
-    float a[8], b[8], c[8], d[8], e[8], f[8], gg[8], hh[8], o[8];
-    ld8(a0, a); ld8(b0, b); ld8(c0p, c); ld8(d0, d);
-    ld8(a1, e); ld8(b1, f); ld8(c1p, gg); ld8(d1, hh);
+  const int total = N * h * w * cg;                    // 32-bit index arithmetic (checked on the host)
+  for (int idx = blockIdx.x * TPB + threadIdx.x; idx < total; idx += gridDim.x * TPB) {
+    const int g = idx % cg;
+    const int p = idx / cg;
+    const int j = p % w, q_ = p / w, i = q_ % h;
+    const long long n = q_ / h;
+    const int c0 = g * 8;
+    const int ys[3] = {max(i - 1, 0), i, min(i + 1, h - 1)}, xs[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
+    const T* base = t + n * (long long)h * w * C + c0;
+    float v[3][3][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = (1.f - ly0) * ((1.f - lx0) * a[j] + lx0 * b[j]) + ly0 * ((1.f - lx0) * c[j] + lx0 * d[j]);
-    st8(u + (long long)p * C + c0, o);
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = (1.f - ly1) * ((1.f - lx1) * e[j] + lx1 * f[j]) + ly1 * ((1.f - lx1) * gg[j] + lx1 * hh[j]);
-    st8(u + (long long)(p + stride) * C + c0, o);
-  }
-  if (p < P) {
-    const T *a0, *b0, *c0p, *d0;
-    float lx, ly;
-    src(p, a0, b0, c0p, d0, lx, ly);
-    float a[8], b[8], c[8], d[8], o[8];
-    ld8(a0, a); ld8(b0, b); ld8(c0p, c); ld8(d0, d);
+      for (int b = 0; b < 3; ++b) ld8(base + ((long long)ys[a] * w + xs[b]) * C, v[a][b]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
-    st8(u + (long long)p * C + c0, o);
+    for (int a = 0; a < 2; ++a) {
+      const float ly = up_lam(2 * i + a, i - 1 + a, ry);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float lx = up_lam(2 * j + b, j - 1 + b, rx);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          o[k] = (1.f - ly) * ((1.f - lx) * v[a][b][k] + lx * v[a][b + 1][k]) + ly * ((1.f - lx) * v[a + 1][b][k] + lx * v[a + 1][b + 1][k]);
+        st8(u + ((n * H + 2 * i + a) * (long long)W + 2 * j + b) * C + c0, o);
+      }
+    }
   }
 }
 
-// gather form of the transpose (deterministic): a low-res pixel collects from the <= 5 x 5 high-res pixels whose bilinear
-// footprint touches it.  The first contributing row / column is searched with the forward index arithmetic itself, the five
-// column weights live in registers and the five loads of a row are issued together.
-__device__ __forceinline__ float up_weight(int Q, int in, int out, int i) {
-  if (Q < 0 || Q >= out) return 0.f;
-  int q0, q1;
-  float l;
-  up_src(Q, in, out, q0, q1, l);
-  float wgt = 0.f;
-  if (q0 == i) wgt += 1.f - l;
-  if (q1 == i) wgt += l;
-  return wgt;
-}
-
+// transpose of the above in gather form (deterministic): source row i receives from output rows 2i-1, 2i (as the LOWER source,
+// weight lam) and 2i+1, 2i+2 (as the UPPER source, weight 1 - lam); the same for columns -> a 4 x 4 window of du per low-res pixel
+// with closed-form weights.
 template <typename T>
 __global__ void __launch_bounds__(TPB) upsample2x_bwd_kernel(const T* __restrict__ du, int N, int h, int w, int C,
                                                              T* __restrict__ dt) {
   const int cg = C >> 3, H = 2 * h, W = 2 * w;
-  const long long total = (long long)N * h * w * cg;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-    const long long p = i / cg;
-    const int c0 = (int)(i - p * cg) * 8;
-    const int xi = (int)(p % w), yi = (int)((p / w) % h);
-    const long long n = p / ((long long)w * h);
-    int Xs = max(0, 2 * xi - 3), Ys = max(0, 2 * yi - 3);
-    for (int k = 0; k < 6 && up_weight(Xs, w, W, xi) == 0.f; ++k) ++Xs;
-    for (int k = 0; k < 6 && up_weight(Ys, h, H, yi) == 0.f; ++k) ++Ys;
-    float wx[5];
+  const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const int total = N * h * w * cg;                    // 32-bit index arithmetic (checked on the host)
+  for (int idx = blockIdx.x * TPB + threadIdx.x; idx < total; idx += gridDim.x * TPB) {
+    const int g = idx % cg;
+    const int p = idx / cg;
+    const int j = p % w, q_ = p / w, i = q_ % h;
+    const long long n = q_ / h;
+    const int c0 = g * 8;
+    // window rows Y = 2i-1+d, d = 0..3: d < 2 -> this pixel is the lower source (base row i-1 ... i), else the upper one
+    float wy[4], wx[4];
 #pragma unroll
-    for (int d = 0; d < 5; ++d) wx[d] = up_weight(Xs + d, w, W, xi);
+    for (int d = 0; d < 4; ++d) {
+      const int Y = 2 * i - 1 + d, X = 2 * j - 1 + d;
+      const int iy = (Y >> 1), ay = Y & 1, ix = (X >> 1), ax = X & 1;      // Y = 2*iy + ay (Y >= 0 where used)
+      const float ly = up_lam(Y, iy - 1 + ay, ry), lx = up_lam(X, ix - 1 + ax, rx);
+      // upper source of Y is clamp(iy - 1 + ay), lower is clamp(iy + ay): pixel i may be either or (at clamped borders) both
+      float a = 0.f, b = 0.f;
+      if (Y >= 0 && Y < H) {
+        if (max(iy - 1 + ay, 0) == i) a += 1.f - ly;
+        if (min(iy + ay, h - 1) == i) a += ly;
+      }
+      if (X >= 0 && X < W) {
+        if (max(ix - 1 + ax, 0) == j) b += 1.f - lx;
+        if (min(ix + ax, w - 1) == j) b += lx;
+      }
+      wy[d] = a;
+      wx[d] = b;
+    }
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll 1
-    for (int dy = 0; dy < 5; ++dy) {
-      const float wy = up_weight(Ys + dy, h, H, yi);
-      if (wy == 0.f) continue;
-      const T* row = du + ((n * H + (Ys + dy)) * (long long)W) * C + c0;
-      float g[5][8];
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const T* base = du + n * (long long)H * W * C + c0;
 #pragma unroll
-      for (int d = 0; d < 5; ++d) ld8(row + (long long)min(Xs + d, W - 1) * C, g[d]);   // weight 0 where clamped
+    for (int dy = 0; dy < 4; ++dy) {
+      const int Y = min(max(2 * i - 1 + dy, 0), H - 1);                  // weight is 0 where clamped
+      float gv[4][8];
 #pragma unroll
-      for (int d = 0; d < 5; ++d) {
-        const float ww = wy * wx[d];
+      for (int d = 0; d < 4; ++d) ld8(base + ((long long)Y * W + min(max(2 * j - 1 + d, 0), W - 1)) * C, gv[d]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, g[d][j], acc[j]);
+      for (int d = 0; d < 4; ++d) {
+        const float ww = wy[dy] * wx[d];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, gv[d][k], acc[k]);
       }
     }
-    st8(dt + p * C + c0, acc);
+    st8(dt + (long long)p * C + c0, acc);
   }
 }
 
@@ -963,16 +1090,16 @@ __global__ void chan_mask_gen_kernel(unsigned long long seed, const unsigned lon
 template <typename T>
 __global__ void __launch_bounds__(TPB) chan_scale_kernel(const T* __restrict__ a, const float* __restrict__ cs,
                                                          long long HW, int C, long long total_vec, T* __restrict__ d) {
-  const int cg = C >> 3;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total_vec; i += (long long)gridDim.x * TPB) {
-    const long long p = i / cg;
-    const int c0 = (int)(i - p * cg) * 8;
-    const long long n = p / HW;
+  const int cg = C >> 3, hw = (int)HW, tv = (int)total_vec;       // 32-bit index arithmetic (checked on the host)
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < tv; i += gridDim.x * TPB) {
+    const int p = i / cg;
+    const int c0 = (i - p * cg) * 8;
+    const long long n = p / hw;
     float v[8];
-    ld8(a + p * C + c0, v);
+    ld8(a + (long long)p * C + c0, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= cs[n * C + c0 + j];
-    st8(d + p * C + c0, v);
+    st8(d + (long long)p * C + c0, v);
   }
 }
 
@@ -1297,15 +1424,40 @@ WSL_API int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* s
   return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
 }
 
+WSL_API int wsl_bn_bwd_first(const void* y, int dtype, const float* ss, const float* save, const void* g0, const uint8_t* mask,
+                             unsigned long long seed, const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W,
+                             float* dgamma, float* dbeta, float* coef, const float* image, float* dw, float* ws, int accumulate,
+                             cudaStream_t stream) {
+  const int C = 16;
+  const long long P = (long long)N * H * W;
+  WSL_REQUIRE(g0 != nullptr && image != nullptr && dw != nullptr, "wsl_bn_bwd_first: g0, image and dw are required");
+  WSL_REQUIRE((long long)bn_grid(P, C) * 2 * C + 64 <= WSL_WS_FLOATS && P < (1LL << 31), "wsl_bn_bwd_first: workspace too small / too many pixels");
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws);
+  const int grid = bn_grid(P, C, 3);
+  int grid2 = (int)((P * 2 + TPB - 1) / TPB);
+  if (grid2 > 148) grid2 = 148;
+  if (grid2 < 1) grid2 = 1;
+  WSL_DISPATCH_T(dtype, {
+    BnBwdArgs<T> a;
+    a.y = (const T*)y; a.ss = ss; a.save = save; a.g0 = (const T*)g0; a.g1 = nullptr; a.cs1 = nullptr; a.gp = nullptr; a.pool_idx = nullptr;
+    a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p; a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
+    bn_bwd_reduce_kernel<0, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, ticket, accumulate);
+    bn_bwd_apply_first_kernel<T><<<grid2, TPB, 0, stream>>>(a, coef, image, dw);
+  });
+  return wsl_check_launch("bn_bwd_first");
+}
+
 WSL_API int wsl_upsample2x_fwd(const void* t, int dtype, int N, int h, int w, int C, void* u, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_fwd: C %% 8 != 0");
   WSL_REQUIRE(TPB % (C / 8) == 0, "wsl_upsample2x_fwd: unsupported C=%d", C);
-  WSL_DISPATCH_T(dtype, upsample2x_fwd_kernel<T><<<grid_for((long long)N * 4 * h * w * (C / 8) / 2), TPB, 0, stream>>>((const T*)t, N, h, w, C, (T*)u));
+  WSL_REQUIRE((long long)N * h * w * (C / 8) < (1LL << 31), "wsl_upsample2x_fwd: too many elements for 32-bit indexing");
+  WSL_DISPATCH_T(dtype, upsample2x_fwd_kernel<T><<<grid_for((long long)N * h * w * (C / 8)), TPB, 0, stream>>>((const T*)t, N, h, w, C, (T*)u));
   return wsl_check_launch("upsample2x_fwd");
 }
 
 WSL_API int wsl_upsample2x_bwd(const void* du, int dtype, int N, int h, int w, int C, void* dt, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_upsample2x_bwd: C %% 8 != 0");
+  WSL_REQUIRE((long long)N * h * w * (C / 8) < (1LL << 31), "wsl_upsample2x_bwd: too many elements for 32-bit indexing");
   WSL_DISPATCH_T(dtype, upsample2x_bwd_kernel<T><<<grid_for((long long)N * h * w * (C / 8)), TPB, 0, stream>>>((const T*)du, N, h, w, C, (T*)dt));
   return wsl_check_launch("upsample2x_bwd");
 }
@@ -1319,6 +1471,7 @@ WSL_API int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long*
 WSL_API int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0, "wsl_chan_scale: C %% 8 != 0");
   const long long tv = (long long)N * H * W * (C / 8);
+  WSL_REQUIRE(tv < (1LL << 31), "wsl_chan_scale: too many elements for 32-bit indexing");
   WSL_DISPATCH_T(dtype, chan_scale_kernel<T><<<grid_for(tv), TPB, 0, stream>>>((const T*)a, cs, (long long)H * W, C, tv, (T*)d));
   return wsl_check_launch("chan_scale");
 }
@@ -1374,9 +1527,14 @@ WSL_API int wsl_sgd_step(float* param, const float* grad, float* mom, long long 
 }
 
 WSL_API int wsl_conv_first(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout,
-                           cudaStream_t stream) {
+                           float* stat_partials, int* stat_rows_host, cudaStream_t stream) {
   WSL_REQUIRE(Cout == 16, "wsl_conv_first: compiled for 1 -> 16 channels (got Cout=%d)", Cout);
-  WSL_DISPATCH_T(dtype, conv_first_kernel<T><<<grid_for((long long)N * H * W), TPB, 0, stream>>>(x, w, bias, (T*)y, N, H, W));
+  WSL_REQUIRE((long long)N * H * W < (1LL << 30), "wsl_conv_first: too many pixels for 32-bit indexing");
+  long long b = ((long long)N * H * ((W + 1) / 2) * 2 + TPB - 1) / TPB;
+  if (b > 148 * 4) b = 148 * 4;                  // one wave: four resident blocks per SM
+  if (b < 1) b = 1;
+  WSL_DISPATCH_T(dtype, conv_first_kernel<T><<<(int)b, TPB, 0, stream>>>(x, w, bias, (T*)y, N, H, W, stat_partials));
+  if (stat_rows_host) *stat_rows_host = (int)b;
   return wsl_check_launch("conv_first");
 }
 

@@ -180,6 +180,7 @@ class UNetExecutor:
         self.wgrad_version = int(os.environ.get("WSL4MIS_WGRAD", "3"))
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
+        self.fuse_first_bwd = os.environ.get("WSL4MIS_NO_FUSED_FIRST_BWD", "0") != "1"
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._sides = {}                 # named side streams
         self._side_stack = []            # names of the side streams we are currently issuing on (innermost last)
@@ -321,8 +322,20 @@ class UNetExecutor:
         f32 = 1 if (src_f32 or self.dt == 1) else self.dt  # dtype code of the sources
         if out_mode == 0 and self.dt != 0:
             out_mode = 2 if self.dt == 1 else 3            # fp32 / fp16 NHWC activations
-        if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2, 3):
-            call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout)
+        first = src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and out_mode in (0, 2, 3)
+        if not first:
+            self.join_side("pack")        # packed operands are produced on a side stream at the start of forward()
+        if first:
+            if bn_out is not None and self.fuse_bn_stats:
+                sb = self._stat_scratch()
+                bn = L.bn
+                call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, sb, ctypes.addressof(self._stat_rows))
+                self._untag()
+                call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
+                     bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
+                rows = True
+            else:
+                call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, None, None)
         elif not src_f32 and self._split_ok(L.srcC, H, W):
             st, inv = self._staged("x", srcs, L.srcC, N * H * W)
             call("wsl_conv_tc_split", st, L.Cin, inv, pk["f3"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
@@ -499,7 +512,8 @@ class UNetExecutor:
             self.seed_dev = torch.full((1,), initial_rng_counter(), dtype=torch.int64, device=self.dev)
         x = x.contiguous()
         slot = self._acquire_slot() if need_grad else "ng"
-        self.pack_all()
+        with self.on_side("pack"):      # operand packing runs beside the first layer (which reads the raw fp32 weights)
+            self.pack_all()
         if training:
             self.seed_dev.add_(1)
         ft = self.ft
@@ -640,6 +654,18 @@ class UNetExecutor:
                 self.conv_wgrad(l2, [r["a1"]], dy2, N, h, w)
             da1 = B(tag + ".da1", (N, h, w, C))
             self.conv_dgrad(l2, 0, dy2, da1, N, h, w)
+            if r["src_f32"] and l1.Cin == 1 and l1.Cout == 16 and l1.ks == 3 and self.fuse_first_bwd:
+                # first layer: BatchNorm backward + weight gradient in one pass, dY never stored (no data gradient towards the image)
+                bn = l1.bn
+                self.last_backward_param_ids.update(id(q) for q in (bn.weight, bn.bias, l1.conv.weight, l1.conv.bias))
+                coef = self.buf(slot, tag + ".bn1.coef", (2 * C,), torch.float32)
+                p1 = l1.drop_p
+                self._tag_bytes("bn_bwd_first", l1, N * h * w * C * (4 if self.dt == 1 else 2) * 4)
+                call("wsl_bn_bwd_first", r["y1"], self.dt, r["ss1"], r["sv1"], da1, r["mask"], self._layer_seed(l1),
+                     self.seed_dev if r["mask"] is None and p1 > 0 else None, p1, LRELU_SLOPE, N, h, w, self.gview(bn.weight),
+                     self.gview(bn.bias), coef, r["srcs"][0], self.gview(l1.conv.weight), self._ws("bn"), 1 if self._accumulate else 0)
+                self._untag()
+                return []
             dy1 = B(tag + ".dy1", (N, h, w, C))
             self.bn_bwd(l1, r["y1"], r["ss1"], r["sv1"], da1, None, None, None, None, r["mask"], dy1, N, h, w, slot,
                         tag + ".bn1")
