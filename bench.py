@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 HW = 256
-VARIANT_LABEL = {"pce": "pCE", "pce_gatedcrf": "pCE+GatedCRF", "pce_ms": "pCE+MumfordShah", "pce_tv": "pCE+TV", "dmpls": "DMPLS (pCE + mixed pseudo-label Dice)",
+VARIANT_LABEL = {"uamt": "UAMT (uncertainty-aware mean teacher: Dice+CE + masked consistency, T=8 teacher passes)", "pce": "pCE", "pce_gatedcrf": "pCE+GatedCRF", "pce_ms": "pCE+MumfordShah", "pce_tv": "pCE+TV", "dmpls": "DMPLS (pCE + mixed pseudo-label Dice)",
                  "pce_entropy": "pCE+EntropyMin", "pce_variance": "pCE+ClassVariance"}
 CRF_DESC = [{"weight": 1, "xy": 6, "rgb": 0.1}]
 
@@ -395,10 +395,34 @@ def main():
     N = args.batch if args.scaling == "weak" else max(1, args.batch // world)
     torch.manual_seed(2022)
     model = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4).to(dev).set_precision(args.precision)
-    step = TrainStep(model, args.variant, base_lr=0.01, max_iterations=30000, graph=not args.no_graph, world_size=world)
+    uamt = args.variant == "uamt"
+    if uamt:
+        # BASELINE config 5 (train_uncertainty_aware_mean_teacher_2D.py:138-197): the per-GPU batch is half labelled (dense labels)
+        # and half unlabelled; the teacher is a second, never-updated network; main_seg on both sides for unet_cct (F7)
+        from wsl4mis_b200.engine import UAMTStep
+        torch.manual_seed(2023)
+        ema = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4).to(dev).set_precision(args.precision)
+        for q in ema.parameters():
+            q.detach_()
+        ustep = UAMTStep(model, ema, base_lr=0.01, max_iterations=30000, world_size=world)
+
+        class _U:                                    # the TrainStep surface bench.py drives
+            graph_enabled, launches_per_step, ex = False, 0, ustep.ex
+
+            def __call__(self, img, lab):
+                h = img.shape[0] // 2
+                c0 = _lib.COUNTERS["launch_calls"]
+                out = ustep(img[:h], lab[:h], img[h:])
+                self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0
+                return out
+        step = _U()
+    else:
+        step = TrainStep(model, args.variant, base_lr=0.01, max_iterations=30000, graph=not args.no_graph, world_size=world)
 
     # synthetic batch: image ~ U[0,1), ~3 % scribble pixels; different per rank
     img_h, lab_h = synth(N, 2022 + rank)
+    if uamt:                                        # --sup_type label: dense labels 0..3
+        lab_h = torch.randint(0, 4, lab_h.shape, generator=torch.Generator().manual_seed(99 + rank), dtype=torch.uint8)
     img_h, lab_h = img_h.pin_memory(), lab_h.pin_memory()
     img_d, lab_d = img_h.to(dev), lab_h.to(dev)
 
@@ -485,7 +509,7 @@ def main():
     # ---- per-kernel table (eager, CUDA events around every C-ABI launch), rank 0, outside the timed regions ----
     table, roof, layers, launches_per_step = None, None, None, None
     peaks = load_peaks()
-    if rank == 0 and not args.no_kernel_table:
+    if rank == 0 and not args.no_kernel_table and not uamt:
         prof = _lib.Profiler()
         eager = TrainStep(model, args.variant, graph=False, world_size=1)
         eager.ex.multi_stream = False        # serialise: per-kernel event times are only meaningful without overlap
@@ -554,16 +578,16 @@ def main():
 
     lps, graph_on = step.launches_per_step, step.graph_enabled     # C-ABI launches per step, counted by TrainStep at capture time
     parity = modes = gpu_base = None
-    if rank == 0 and world == 1 and not args.skip_extras:
+    if rank == 0 and world == 1 and not args.skip_extras and not uamt:
         parity = parity_report(args, dev)
         modes = time_other_modes(args, dev, img_d, lab_d, world)
-    if rank == 0 and world == 1 and not args.skip_gpu_baseline:
+    if rank == 0 and world == 1 and not args.skip_gpu_baseline and not uamt:
         del step
         torch.cuda.empty_cache()
         gpu_base = gpu_reference_baseline(args, dev, img_d, lab_d)
 
     if rank == 0:
-        cb = None if args.skip_cpu else cpu_reference_time(args, args.cpu_sample, 3, 1)[0]
+        cb = None if (args.skip_cpu or uamt) else cpu_reference_time(args, args.cpu_sample, 3, 1)[0]
         imgs = N * world * K
         line = {
             "metric": metric_name(args), "value": imgs / (ms_dev * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
@@ -573,6 +597,7 @@ def main():
             "config": {"workload": f"{args.model} {args.variant} train step (fwd+loss+bwd+SGD), {N}x1x{HW}x{HW} per GPU, "
                                    f"loss on main_seg (SURVEY F7)", "global_batch": N * world, "parallelism": f"dp{world}",
                        "precision": args.precision, "cuda_graph": bool(graph_on),
+                       "comm": getattr(step, "comm_mode", None) if world > 1 else None,
                        "bn": "per-rank batch statistics (stock DDP semantics)",
                        "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush needed"},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "ms_per_step": ms_e2e / K,

@@ -19,6 +19,7 @@ torch.optim.SGD with ``grad is None``, is skipped by the optimiser.
 """
 from __future__ import annotations
 
+import os
 import random
 
 import torch
@@ -90,6 +91,11 @@ class TrainStep:
             else:
                 self.segments.append([off_p, n_p])
         self.n_trained = self.segments[-1][0] + self.segments[-1][1]     # prefix that holds every trained parameter (the all-reduce payload)
+        # the encoder's parameters come first in parameters(): [0, enc_end) is final only at the very end of backward(), the
+        # decoder slice [enc_end, n_trained) ~2 ms earlier -- its all-reduce is issued from inside backward() on a side stream
+        self.enc_end = sum(q.numel() for q in model.encoder.parameters())
+        self.overlap_comm = self.world_size > 1 and os.environ.get("WSL4MIS_NO_COMM_OVERLAP", "0") != "1"
+        self.nccl_in_graph = os.environ.get("WSL4MIS_NCCL_IN_GRAPH", "0") == "1"     # opt-in: capture the collectives in the step graph
         self.loss_parts = {}
         self.launches_per_step = 0
 
@@ -201,7 +207,11 @@ class TrainStep:
         outs, slot = ex.forward(image, True, True, getattr(self.model, "dropout_masks", None),
                                 getattr(self.model, "channel_keep", None), defer_join=defer)
         loss, dl = self._head(outs, image, label, slot)
-        gflat = ex.backward(slot, dl)
+        ex.on_decoders_done = self._allreduce_decoders if self.overlap_comm else None
+        try:
+            gflat = ex.backward(slot, dl)
+        finally:
+            ex.on_decoders_done = None
         self._outs = outs
         self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0 + 1     # + the SGD kernel (also inside the graph)
         return loss, gflat
@@ -211,9 +221,24 @@ class TrainStep:
             call("wsl_sgd_step", self.flat[off:], gflat[off:], self.mom[off:], n, self.lr_dev, self.base_lr, self.momentum,
                  self.weight_decay, 1.0 / self.world_size)
 
+    def _allreduce_decoders(self, gflat):
+        """called by the executor between the decoder and encoder halves of backward(): sum the decoder slice of the bucket on the
+        'comm' side stream while the encoder's BatchNorm-backward / dgrad / wgrad chain keeps the SMs busy"""
+        if self.n_trained > self.enc_end:
+            with self.ex.on_side("comm"):
+                ddp.allreduce_flat(gflat[self.enc_end: self.n_trained], self.pg)
+
     def _allreduce(self, gflat):
+        """the rest of the bucket after backward(): the encoder slice (or everything when the overlap is off)"""
         if self.world_size > 1:
-            ddp.allreduce_flat(gflat[: self.n_trained], self.pg)
+            if self.overlap_comm:
+                # SAME stream as the decoder slice: two collectives of one communicator on different streams may be scheduled in
+                # different orders on different ranks (synchronous c10d collectives run on the caller's stream) and deadlock
+                with self.ex.on_side("comm"):
+                    ddp.allreduce_flat(gflat[: self.enc_end], self.pg)
+                self.ex.join_side("comm")
+            else:
+                ddp.allreduce_flat(gflat[: self.n_trained], self.pg)
 
     # ------------------------------------------------------------------
     def __call__(self, image, label):
@@ -251,21 +276,10 @@ class TrainStep:
                 self._warm += 1
             else:
                 if self._graphs[idx] is None:
-                    torch.cuda.synchronize()
-                    g1 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
-                        gloss, gg = self._fwd_bwd(simg, slab)
-                        if self.world_size == 1:
-                            self._opt(gg)
-                    g2 = None
-                    if self.world_size > 1:
-                        g2 = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g2):
-                            self._opt(gg)
-                    self._graphs[idx] = (g1, g2, gloss, gg, self._outs, dict(self.loss_parts))
+                    self._graphs[idx] = self._capture(simg, slab)
                 g1, g2, gloss, gg, self._outs, self.loss_parts = self._graphs[idx]
                 g1.replay()
-                if self.world_size > 1:
+                if g2 is not None:                  # two-graph fallback: NCCL issued from the host between the graphs
                     self._allreduce(gg)
                     g2.replay()
                 # the captured loss lives in graph-pool memory that the next replay overwrites: hand out a copy
@@ -276,6 +290,39 @@ class TrainStep:
         self.lr_dev.fill_(lr_)
         self.iter_num += 1
         return loss
+
+    def _capture(self, simg, slab):
+        """Capture the step.  world_size 1: one graph.  world_size > 1: ONE graph as well, with the NCCL all-reduces captured
+        inside it (decoder slice on a side branch under the encoder's backward, encoder slice + SGD at the end) -- no host round
+        trip and no second graph launch between backward and optimiser; if this NCCL / torch build refuses to capture the
+        collective, fall back to two graphs with the all-reduce issued from the host in between."""
+        torch.cuda.synchronize()
+        if self.world_size > 1 and self.nccl_in_graph:
+            try:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    gloss, gg = self._fwd_bwd(simg, slab)
+                    self._allreduce(gg)
+                    self._opt(gg)
+                self.comm_mode = "captured in the step graph (decoder slice overlapped with the encoder backward)" if self.overlap_comm else "captured in the step graph"
+                return (g1, None, gloss, gg, self._outs, dict(self.loss_parts))
+            except Exception as e:                   # pragma: no cover - depends on the NCCL build
+                self.comm_mode = f"two graphs, host-issued all-reduce (capture failed: {type(e).__name__})"
+                torch.cuda.synchronize()
+                self.overlap_comm = False            # a host-issued collective cannot sit inside backward()
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            gloss, gg = self._fwd_bwd(simg, slab)
+            if self.world_size == 1:
+                self._opt(gg)
+        g2 = None
+        if self.world_size > 1:
+            if not hasattr(self, "comm_mode"):
+                self.comm_mode = "two graphs, host-issued all-reduce"
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._opt(gg)
+        return (g1, g2, gloss, gg, self._outs, dict(self.loss_parts))
 
     def input_buffers(self, idx=0, like=None):
         """(image, label) device buffers read by captured graph `idx` (0 or 1)."""

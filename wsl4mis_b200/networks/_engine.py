@@ -181,6 +181,7 @@ class UNetExecutor:
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
         self.fuse_first_bwd = os.environ.get("WSL4MIS_NO_FUSED_FIRST_BWD", "0") != "1"
+        self.on_decoders_done = None     # optional callback(gflat) between the decoder and encoder halves of backward()
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._sides = {}                 # named side streams
         self._side_stack = []            # names of the side streams we are currently issuing on (innermost last)
@@ -749,6 +750,11 @@ class UNetExecutor:
                 decoder_bwd(di, ups, oc, g, rec["dec"][di])
         for nm in chains:
             self.join_side(nm)
+        if self.on_decoders_done is not None:
+            # data-parallel step: every decoder gradient is final once the decoders' weight-gradient launches (side stream) have
+            # joined -- the caller starts the all-reduce of that slice of the flat bucket here, underneath the encoder's backward
+            self.join_side("side")
+            self.on_decoders_done(gflat)
 
         # ---- encoder ----
         gpool = None
