@@ -96,6 +96,8 @@ class TrainStep:
         self.enc_end = sum(q.numel() for q in model.encoder.parameters())
         self.overlap_comm = self.world_size > 1 and os.environ.get("WSL4MIS_NO_COMM_OVERLAP", "0") != "1"
         self.nccl_in_graph = os.environ.get("WSL4MIS_NCCL_IN_GRAPH", "0") == "1"     # opt-in: capture the collectives in the step graph
+        if self.graph_enabled and not self.nccl_in_graph:
+            self.overlap_comm = False        # a host-issued collective cannot sit inside the captured backward
         self.loss_parts = {}
         self.launches_per_step = 0
 
