@@ -243,6 +243,13 @@ int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long* seed_pt
                       cudaStream_t stream);
 int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream);
 
+/* FeatureNoise of UNet_CCT_3H's third head (unet.py:270-283, :369): z = uniform(lo, hi) of the feature's [H][W][C] shape (one tensor
+ * for the whole batch), out = f * z + f; backward: acc += g * (1 + z) when acc != NULL, else out = g * (1 + z). */
+int wsl_uniform_fill(unsigned long long seed, const unsigned long long* seed_ptr, long long n, float lo, float hi, float* out,
+                     cudaStream_t stream);
+int wsl_feat_noise_fwd(const void* f, int dtype, const float* z, int N, long long hwc, void* out, cudaStream_t stream);
+int wsl_feat_noise_bwd(const void* g, int dtype, const float* z, int N, long long hwc, void* acc, void* out, cudaStream_t stream);
+
 /* layout helpers at the API boundary */
 int wsl_nchw_f32_to_nhwc(const float* src, int N, int Creal, int H, int W, int CP, void* dst, int dtype, float scale,
                          cudaStream_t stream);   /* dst = scale * src (the loss scale of the fp16 modes; 1 otherwise) */

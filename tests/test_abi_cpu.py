@@ -121,3 +121,14 @@ def test_unet_ds_state_dict_layout_matches_the_reference_order():
     p = O.synth_params(1, 4, ("decoder",), 3, ds=True)
     m.load_state_dict(p)
     assert torch.equal(m.state_dict()["decoder.out_conv_dp4.weight"], p["decoder.out_conv_dp4.weight"])
+
+
+def test_unet_cct_3h_and_urds_state_dict_layouts():
+    """UNet_CCT_3H registers encoder, main_decoder, aux_decoder1, aux_decoder2 (unet.py:358-361); Decoder_URDS is a constructible
+    parameter container with Decoder_DS's keys (unet.py:191-225)."""
+    import wsl_oracle as O
+    from wsl4mis_b200.networks.unet import UNet_CCT_3H, Decoder_URDS, Decoder_DS, _params
+    sd = UNet_CCT_3H(1, 4).state_dict()
+    want = O.unet_param_shapes(1, 4, ("main_decoder", "aux_decoder1", "aux_decoder2"))
+    assert list(sd.keys()) == list(want.keys()) and all(tuple(sd[k].shape) == tuple(v) for k, v in want.items())
+    assert list(Decoder_URDS(_params(1, 4)).state_dict().keys()) == list(Decoder_DS(_params(1, 4)).state_dict().keys())

@@ -410,3 +410,68 @@ def test_unet_ds_wide_input_runs_the_tensor_core_heads():
             continue
         if named[k].dim() == 4:
             assert cosine(named[k].grad.detach().cpu(), r) > GRAD_COS_Q, k
+
+
+def _3h_case(golden_dir, precision):
+    from torch.distributions.uniform import Uniform
+    from wsl4mis_b200.networks.unet import UNet_CCT_3H
+    g = np.load(os.path.join(golden_dir, "unet_heads.npz"))
+    n, hw = int(g["n"]), int(g["hw"])
+    p = O.synth_params(1, 4, ("main_decoder", "aux_decoder1", "aux_decoder2"), int(g["pseed"]))
+    m = UNet_CCT_3H(1, 4)
+    m.load_state_dict(p)
+    m = m.to(DEV).set_precision(precision)
+    em = elem_masks_nchw(int(g["mseed"]), n, hw, hw)
+    m.dropout_masks = {i: e.permute(0, 2, 3, 1).contiguous().to(DEV) for i, e in enumerate(em)}
+    m.channel_keep = [c.to(DEV) for c in chan_masks(int(g["cseed"]), n)]
+    torch.manual_seed(int(g["nseed"]))               # the reference's FeatureNoise draws, in feature order (unet.py:369)
+    m.feature_noise = [Uniform(-0.3, 0.3).sample((O.FT[i], hw >> i, hw >> i)) for i in range(5)]
+    return g, m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_unet_cct_3h_matches_the_reference_fixture(golden_dir, precision):
+    """UNet_CCT_3H: three outputs -- main, aux_decoder1 on channel-dropped features, aux_decoder1 AGAIN on
+    FeatureNoise'd features (unet.py:363-371) -- loss = sum of the heads' pCE, every parameter gradient (aux_decoder1 accumulates both
+    passes, aux_decoder2 gets none), against the fixture generated from the unmodified reference class."""
+    g, m = _3h_case(golden_dir, precision)
+    x, lab = torch.from_numpy(g["image"]).to(DEV), torch.from_numpy(g["label"]).to(DEV)
+    m.train()
+    outs = m(x)
+    assert len(outs) == 3
+    for i, o in enumerate(outs):
+        ref = torch.from_numpy(g[f"3h:out{i}"])
+        err = (o.detach().cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-3, (i, err)
+    loss = sum(Fn.softmax_pce(o, lab)[0] for o in outs)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["3h:loss"])) < 1e-3 * abs(float(g["3h:loss"]))
+    named = dict(m.named_parameters())
+    errs = {}
+    for k, (_, asum, l2) in zip([str(k) for k in g["3h:grad_keys"]], g["3h:grad_stats"]):
+        if k.endswith("bias") and (".0.bias" in k or ".4.bias" in k):
+            continue
+        assert named[k].grad is not None, k
+        errs[k] = abs(named[k].grad.double().norm().item() - l2) / (l2 + 1e-12)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print(f"[unet_cct_3h {precision}] worst gradient-norm errors:", [(k, f"{v:.2e}") for k, v in worst])
+    bad = {k: v for k, v in errs.items() if v > (2e-3 if named[k].dim() == 4 else 1e-2)}
+    assert not bad, bad
+    for k in (str(k) for k in g["3h:no_grad_keys"]):        # aux_decoder2 never runs: no gradient, exactly like autograd
+        assert named[k].grad is None, k
+
+
+def test_unet_cct_3h_bf16_runs_with_its_own_noise():
+    """default mode, no injected randomness: three finite outputs, a backward pass, fresh FeatureNoise every forward"""
+    from wsl4mis_b200.networks.net_factory import net_factory
+    torch.manual_seed(3)
+    m = net_factory("unet_cct_3h", in_chns=1, class_num=4)
+    x = torch.rand(2, 1, 64, 64, device=DEV)
+    m.train()
+    a = m(x)
+    b = m(x)
+    assert len(a) == 3 and all(torch.isfinite(o).all() for o in a)
+    assert not torch.equal(a[2], b[2])
+    sum(o.float().mean() for o in a).backward()
+    assert next(m.aux_decoder1.parameters()).grad is not None and next(m.aux_decoder2.parameters()).grad is None

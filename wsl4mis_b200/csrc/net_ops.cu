@@ -1087,6 +1087,34 @@ __global__ void chan_mask_gen_kernel(unsigned long long seed, const unsigned lon
   if (i < n) cs[i] = (wsl_uniform(seed, (unsigned long long)i) >= p) ? 1.f / (1.f - p) : 0.f;
 }
 
+// FeatureNoise of the third head of UNet_CCT_3H (unet.py:270-283, :369): out = f * z + f with one noise tensor z[H][W][C] shared by
+// the batch; backward d f = d out * (1 + z), optionally added onto another gradient of the same feature.
+__global__ void uniform_fill_kernel(unsigned long long seed, const unsigned long long* seed_ptr, long long n, float lo, float hi, float* out) {
+  if (seed_ptr) seed += *seed_ptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = lo + (hi - lo) * wsl_uniform(seed, (unsigned long long)i);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) feat_noise_kernel(const T* __restrict__ f, const float* __restrict__ z, long long total_vec,
+                                                         long long hwc_vec, const T* __restrict__ acc, T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total_vec; i += (long long)gridDim.x * TPB) {
+    const long long zi = (i % hwc_vec) * 8;
+    float v[8], a[8];
+    ld8(f + i * 8, v);
+    const float4 z0 = *reinterpret_cast<const float4*>(z + zi), z1 = *reinterpret_cast<const float4*>(z + zi + 4);
+    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], zz[j], v[j]);
+    if (acc) {
+      ld8(acc + i * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += a[j];
+    }
+    st8(out + i * 8, v);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TPB) chan_scale_kernel(const T* __restrict__ a, const float* __restrict__ cs,
                                                          long long HW, int C, long long total_vec, T* __restrict__ d) {
@@ -1466,6 +1494,26 @@ WSL_API int wsl_chan_mask_gen(unsigned long long seed, const unsigned long long*
                               cudaStream_t stream) {
   chan_mask_gen_kernel<<<(n + 255) / 256, 256, 0, stream>>>(seed, seed_ptr, n, p, cs);
   return wsl_check_launch("chan_mask_gen");
+}
+
+WSL_API int wsl_uniform_fill(unsigned long long seed, const unsigned long long* seed_ptr, long long n, float lo, float hi, float* out,
+                             cudaStream_t stream) {
+  uniform_fill_kernel<<<grid_for(n), 256, 0, stream>>>(seed, seed_ptr, n, lo, hi, out);
+  return wsl_check_launch("uniform_fill");
+}
+
+WSL_API int wsl_feat_noise_fwd(const void* f, int dtype, const float* z, int N, long long hwc, void* out, cudaStream_t stream) {
+  WSL_REQUIRE(hwc % 8 == 0, "wsl_feat_noise_fwd: H*W*C must be a multiple of 8");
+  WSL_DISPATCH_T(dtype, feat_noise_kernel<T><<<grid_for(N * hwc / 8), TPB, 0, stream>>>((const T*)f, z, N * hwc / 8, hwc / 8, nullptr, (T*)out));
+  return wsl_check_launch("feat_noise_fwd");
+}
+
+WSL_API int wsl_feat_noise_bwd(const void* g, int dtype, const float* z, int N, long long hwc, void* acc, void* out, cudaStream_t stream) {
+  WSL_REQUIRE(hwc % 8 == 0, "wsl_feat_noise_bwd: H*W*C must be a multiple of 8");
+  // acc != NULL: acc += g * (1 + z) (in place); else out = g * (1 + z) (out may alias g)
+  WSL_DISPATCH_T(dtype, feat_noise_kernel<T><<<grid_for(N * hwc / 8), TPB, 0, stream>>>((const T*)g, z, N * hwc / 8, hwc / 8, (const T*)acc,
+                                                                                    (T*)(acc ? acc : out)));
+  return wsl_check_launch("feat_noise_bwd");
 }
 
 WSL_API int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream) {

@@ -114,7 +114,10 @@ class UNetExecutor:
     MAX_SLOTS = 4
 
     def __init__(self, model: nn.Module, encoder: nn.Module, decoders: List[nn.Module], aux_dropout: Sequence[bool],
-                 precision: str = "bf16"):
+                 precision: str = "bf16", runs=None):
+        """decoders: the decoder modules that own parameters; aux_dropout[i]: decoder i sees channel-dropped features.
+        runs (optional): the decoder passes of one forward as (decoder index, feature transform) with transform in
+        {None, "chan_drop", "feat_noise"} -- UNet_CCT_3H runs aux_decoder1 twice (unet.py:367-370) and never runs aux_decoder2."""
         assert precision in PRECISIONS
         self.model = model
         self.precision = precision
@@ -123,7 +126,10 @@ class UNetExecutor:
         self.split_tc = precision == "fp16x3"
         # power-of-two factor carried by every activation gradient (set per backward from the batch shape; 1 = off)
         self.scaled_grads = precision == "fp16"        # fp16x3 scales every staged operand by its own power of two instead
-        self.aux = list(aux_dropout)
+        if runs is None:
+            runs = [(i, "chan_drop" if a else None) for i, a in enumerate(aux_dropout)]
+        self.runs = list(runs)
+        self.aux = [t for _, t in self.runs]           # feature transform of every decoder pass
         self.layers: List[ConvLayer] = []
         ft = encoder.ft_chns
         self.ft = ft
@@ -141,7 +147,13 @@ class UNetExecutor:
             self.enc_blocks.append(block(f"encoder.down{i}", cb.conv_conv, [ft[i - 1]]))
         self.dec = []
         self.ds_heads = []
-        for d in decoders:
+        built = {}
+        for didx, _ in self.runs:
+            if didx in built:                  # a second pass through the same decoder shares its layers (and their gradients)
+                self.dec.append(built[didx][0])
+                self.ds_heads.append(built[didx][1])
+                continue
+            d = decoders[didx]
             ups = []
             for j in range(1, 5):
                 ub = getattr(d, f"up{j}")
@@ -161,6 +173,7 @@ class UNetExecutor:
                     heads[j] = ConvLayer(f"out_conv_dp{lvl}", hc, None, 0.0, [hc.in_channels])
                     self.layers.append(heads[j])
             self.ds_heads.append(heads)
+            built[didx] = (self.dec[-1], heads)
         self.n_class = decoders[0].out_conv.out_channels
         self.params = [p for p in model.parameters()]
         used = set()
@@ -558,7 +571,24 @@ class UNetExecutor:
         def run_decoder(di, ups, oc):
             drec = {"ups": [], "cs": None}
             fe = feats
-            if self.aux[di]:
+            if self.aux[di] == "feat_noise":
+                # FeatureNoise (unet.py:270-283, :369): one uniform(-0.3, 0.3) tensor of the feature's [C, H, W] shape, shared by the
+                # batch: f * noise + f.  model.feature_noise (tests) injects the five tensors; otherwise the counter RNG draws them.
+                nz, fe = [], []
+                given = getattr(self.model, "feature_noise", None)
+                for i, f in enumerate(feats):
+                    hwc = f.shape[1] * f.shape[2] * f.shape[3]
+                    z = self.buf(slot, f"dec{di}.noise{i}", (f.shape[1], f.shape[2], f.shape[3]), torch.float32)
+                    if given is not None:
+                        z.copy_(given[i].to(device=self.dev, dtype=torch.float32).permute(1, 2, 0))      # [C,H,W] -> [H,W,C]
+                    else:
+                        call("wsl_uniform_fill", (di + 1) * 104729 + i, self.seed_dev, hwc, -0.3, 0.3, z)
+                    d = self.buf(slot, f"dec{di}.noisy{i}", tuple(f.shape))
+                    call("wsl_feat_noise_fwd", f, self.dt, z, N, hwc, d)
+                    nz.append(z)
+                    fe.append(d)
+                drec["noise"] = nz
+            elif self.aux[di]:
                 cs, fe = [], []
                 for i, f in enumerate(feats):
                     c = self.buf(slot, f"dec{di}.cs{i}", (N, ft[i]), torch.float32)
@@ -598,8 +628,8 @@ class UNetExecutor:
             return drec
 
         drecs = [None] * len(self.dec)
-        for di in range(len(self.dec) - 1, 0, -1):          # aux decoders first, on the side stream
-            with self.on_side():
+        for di in range(1, len(self.dec)):                  # aux passes first, on the side stream, in the reference's order
+            with self.on_side():                            # (a decoder that runs twice updates its running statistics twice)
                 drecs[di] = run_decoder(di, *self.dec[di])
         drecs[0] = run_decoder(0, *self.dec[0])
         if not (defer_join and need_grad and self.defer_aux):
@@ -691,6 +721,13 @@ class UNetExecutor:
                         ds_grads[(di, j)] = grad_logits[nxt]
                     nxt += 1
 
+        def tag_of(drec, lvl):
+            """how the encoder feature of level lvl entered this decoder pass: None (as is), a [N,C] channel scale (F.dropout2d)
+            or ("noise", z) for FeatureNoise (d feature = d noisy * (1 + z))"""
+            if drec.get("noise") is not None:
+                return ("noise", drec["noise"][lvl])
+            return drec["cs"][lvl] if drec["cs"] else None
+
         def decoder_bwd(di, ups, oc, g, drec):
             if isinstance(g, tuple):                      # ("nhwc16", tensor): already in the executor's layout
                 dl = g[1]
@@ -720,7 +757,7 @@ class UNetExecutor:
                     self.conv_dgrad(hl, 0, dl16, dh, N, hh_, ww_)
                 dskip, du = block_bwd(f"dec{di}.up{j}", blk, r, da, dh)
                 lvl = 3 - j
-                skip_grads[lvl].append((dskip, drec["cs"][lvl] if drec["cs"] else None))
+                skip_grads[lvl].append((dskip, tag_of(drec, lvl)))
                 hh, ww, C2 = r["h"] // 2, r["w"] // 2, c1.Cout
                 dt = B(f"dec{di}.up{j}.dt", (N, hh, ww, C2))
                 self._tag_bytes("up_bwd", c1, N * hh * ww * C2 * (4 if self.dt == 1 else 2) * 5)
@@ -730,24 +767,33 @@ class UNetExecutor:
                     self.conv_wgrad(c1, [r["xlow"]], dt, N, hh, ww)
                 da = B(f"dec{di}.up{j}.dxlow", (N, hh, ww, c1.Cin))
                 self.conv_dgrad(c1, 0, dt, da, N, hh, ww)
-            skip_grads[4].append((da, drec["cs"][4] if drec["cs"] else None))
+            skip_grads[4].append((da, tag_of(drec, 4)))
 
         # aux decoder chains run on their own streams beside the main decoder's (HBM-bound BatchNorm backward of one chain
         # overlaps the tensor-core data gradients of the other); the encoder needs all of them
         chains = []
+        seen_decoders = set()
+        base_accumulate = self._accumulate
         for di, (ups, oc) in enumerate(self.dec):
-            g = grad_logits[di]
+            g = grad_logits[di] if di < len(grad_logits) else None
             if g is None and any(k[0] == di for k in ds_grads):     # only deep-supervision heads were used in the loss
                 g = torch.zeros((N, self.n_class, H, W), dtype=torch.float32, device=self.dev)
             if g is None:
                 continue
+            didx = self.runs[di][0]
+            # a second pass through the same decoder ADDS its BatchNorm affine gradients (weight gradients always accumulate) and
+            # runs on the same stream as the first one, so the two never touch the shared gradient rows concurrently
+            self._accumulate = base_accumulate or (didx in seen_decoders)
+            seen_decoders.add(didx)
             if di > 0 and self.bwd_streams and self.multi_stream:
-                nm = f"dec{di}"
+                nm = f"dec{didx}"
                 with self.on_side(nm):
                     decoder_bwd(di, ups, oc, g, rec["dec"][di])
-                chains.append(nm)
+                if nm not in chains:
+                    chains.append(nm)
             else:
                 decoder_bwd(di, ups, oc, g, rec["dec"][di])
+        self._accumulate = base_accumulate
         for nm in chains:
             self.join_side(nm)
         if self.on_decoders_done is not None:
@@ -762,7 +808,13 @@ class UNetExecutor:
             r = rec["enc"][i]
             srcs = skip_grads[i]
             plain = [g for g, cs in srcs if cs is None]
-            scaled = [(g, cs) for g, cs in srcs if cs is not None]
+            noisy = [(g, cs[1]) for g, cs in srcs if isinstance(cs, tuple)]
+            scaled = [(g, cs) for g, cs in srcs if cs is not None and not isinstance(cs, tuple)]
+            for gn, z in noisy:            # FeatureNoise pass: fold d noisy * (1 + z) into the plain skip gradient (or make it the plain one)
+                hwc = gn.shape[1] * gn.shape[2] * gn.shape[3]
+                call("wsl_feat_noise_bwd", gn, self.dt, z, N, hwc, plain[0] if plain else None, gn)
+                if not plain:
+                    plain = [gn]
             assert len(plain) <= 1 and len(scaled) <= 1
             g0 = plain[0] if plain else None
             g1, cs1 = scaled[0] if scaled else (None, None)

@@ -166,10 +166,13 @@ class _PlannedNet(nn.Module):
         object.__setattr__(self, "_holder", None)
         return self
 
+    _runs = None           # decoder passes (decoder index, feature transform) when they differ from one pass per decoder
+
     @property
     def executor(self):
         if self._holder is None:
-            ex = UNetExecutor(self, self.encoder, [getattr(self, n) for n in self._decoders], list(self._aux), self.precision)
+            ex = UNetExecutor(self, self.encoder, [getattr(self, n) for n in self._decoders], list(self._aux), self.precision,
+                              runs=self._runs)
             object.__setattr__(self, "_holder", _Holder(ex))
         return self._holder.executor
 
@@ -252,8 +255,14 @@ class Decoder_DS(Decoder):
             setattr(self, f"out_conv_dp{lvl}", nn.Conv2d(f[lvl], self.n_class, kernel_size=3, padding=1))
 
 
-class Decoder_URDS(_OffPath):
-    pass
+class Decoder_URDS(Decoder_DS):
+    """reference unet.py:191-251: Decoder_DS's layers plus a FeatureNoise module; its forward perturbs the inputs of the three
+    deep-supervision heads in training mode.  No network class of the reference instantiates it (grep: only its definition), so it
+    is kept as a constructible parameter container with the reference's state_dict layout."""
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.feature_noise = FeatureNoise()
 
 
 class UNet_DS(_PlannedNet):
@@ -270,5 +279,20 @@ class UNet_DS(_PlannedNet):
         return self._run(x)
 
 
-class UNet_CCT_3H(_OffPath):
-    pass
+class UNet_CCT_3H(_PlannedNet):
+    """reference unet.py:349-371, as written: returns (main_seg, aux_seg1, aux_seg2) where aux_seg1 = aux_decoder1 on
+    F.dropout2d'ed features and aux_seg2 = aux_decoder1 AGAIN on FeatureNoise'd features (:369-370); ``aux_decoder2`` owns
+    parameters (state_dict parity) and never runs, so its parameters get no gradient.  ``feature_noise`` (tests) injects the five
+    [C, H, W] noise tensors the reference draws from torch's RNG."""
+    _decoders = ("main_decoder", "aux_decoder1", "aux_decoder2")
+    _aux = (False, True, True)
+    _runs = ((0, None), (1, "chan_drop"), (1, "feat_noise"))
+
+    def __init__(self, in_chns, class_num):
+        super().__init__()
+        self._build(in_chns, class_num)
+        self.feature_noise = None
+
+    def forward(self, x):
+        main_seg, aux_seg1, aux_seg2 = self._run(x)
+        return main_seg, aux_seg1, aux_seg2
