@@ -178,13 +178,15 @@ int wsl_bn_finalize(const float* partials, int nrows, long long P, int C, const 
 /* tcgen05 weight gradient (conv_tc.cu): dw (fp32, torch layout [CoutReal][C0+C1][k][k]) += dY^T * X over all pixels.
  * Bias gradients are NOT produced here (see wsl_channel_sum). */
 int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                 int W, int CoutReal, int ksize, int dtype, cudaStream_t stream);
+                 int W, int CoutReal, int ksize, int dtype, float* partial_ws, long long partial_floats, cudaStream_t stream);
 /* v2 of the 3x3 weight gradient: one halo load of X per 16x8 pixel chunk, nine row-shifted descriptor views. */
 int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                   int W, int CoutReal, int ksize, int dtype, cudaStream_t stream);
 /* v3: filter columns ride in the MMA's M dimension (A = X halo with one-pixel group stride, B = dY, N = Cout tile). */
 int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                  int W, int CoutReal, int ksize, int dtype, cudaStream_t stream);
+                  int W, int CoutReal, int ksize, int dtype, float* partial_ws, long long partial_floats, cudaStream_t stream);
+/* partial_ws (optional, partial_floats floats): split-K partial tiles go there and a fixed-order finalize adds them into dw -> the
+ * weight gradient is bit-stable run to run; NULL (or too small): fp32 red.global.add, order-dependent in the last bits. */
 
 /* fp16 hi/lo split ("fp16x3") tensor-core parity mode: the reference computes in fp32 (unet.py:18-26); here an fp32 value
  * travels as hi = fp16(v), lo = fp16(v - hi) and a product is a_hi*b_hi + a_lo*b_hi + a_hi*b_lo on kind::f16 with fp32
@@ -203,7 +205,8 @@ int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scale, const
 int wsl_wgrad_tc_split(const void* x_staged, int Cin, const float* x_inv_scale, const void* dy_staged, int CoutP,
                        const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
 /* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
-int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, cudaStream_t stream);
+int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, float* ws, cudaStream_t stream);
+/* ws (optional zero-initialised workspace): per-block rows + fixed-order sum by the last block -> bit-stable; NULL: atomicAdd */
 
 /* nn.BatchNorm2d training statistics (unet.py:20,24): save = {mean[C], invstd[C]}, ss = {scale[C], shift[C]};
  * running stats / num_batches_tracked updated in place when non-NULL. */

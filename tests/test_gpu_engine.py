@@ -260,3 +260,24 @@ def test_ustm_step_matches_oracle(rot):
         assert cosine(named[k].detach().cpu() - ps[k], new_s[k] - ps[k]) > 0.999, k
         ref_t = pt[k] * alpha + (1 - alpha) * named[k].detach().cpu()
         assert torch.allclose(tnamed[k].detach().cpu(), ref_t, atol=1e-6), k
+
+
+def test_training_is_bit_reproducible_run_to_run():
+    """Two runs of three fused steps from the same weights / batch / seeds end with bit-identical parameters and losses: every
+    reduction on the path has a fixed order (BatchNorm statistics, loss sums, split-K weight gradients via per-CTA partial tiles
+    and a fixed-order finalize, bias gradients, the first layer's fused weight gradient)."""
+    import random
+    outs = []
+    for rep in range(2):
+        torch.manual_seed(3)
+        random.seed(3)
+        m = UNet_CCT(1, 4).to(DEV)
+        # 256 x 256: every layer runs on the tensor-core kernels (maps smaller than one 16 x 8 tile fall back to the CUDA-core
+        # weight gradient, which still accumulates with atomics)
+        image, label = O.synth_batch(2, 256, 256, seed=11, frac=0.05)
+        step = TrainStep(m, "dmpls", graph=False)
+        losses = [float(step(image.to(DEV), label.to(DEV))) for _ in range(3)]
+        torch.cuda.synchronize()
+        outs.append((step.flat.detach().clone(), losses))
+    assert outs[0][1] == outs[1][1], (outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])

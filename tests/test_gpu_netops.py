@@ -209,9 +209,13 @@ def test_wgrad_tc(case, ver):
     s0 = nhwc(x[:, :C0], T16[dt]).to(DEV)
     s1 = nhwc(x[:, C0:], T16[dt]).to(DEV) if C1 else None
     dyd = nhwc(dy, T16[dt]).to(DEV)
-    call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks, dt)
+    extra = ()
+    if ver in ("wsl_wgrad_tc3", "wsl_wgrad_tc"):   # deterministic split-K: partial tiles + fixed-order finalize (None -> atomics)
+        pw = torch.empty(8 * 1024 * 1024, device=DEV) if (hash(case) % 3) else None
+        extra = (pw, pw.numel() if pw is not None else 0)
+    call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks, dt, *extra)
     db = torch.zeros(Cout, device=DEV)
-    call("wsl_channel_sum", dyd, dt, N * H * W, CoutP, Cout, db)
+    call("wsl_channel_sum", dyd, dt, N * H * W, CoutP, Cout, db, workspace("csum") if (hash(case) % 2) else None)
     torch.cuda.synchronize()
     wz = torch.zeros(Cout, Cin, ks, ks, dtype=torch.double, requires_grad=True)
     bz = torch.zeros(Cout, dtype=torch.double, requires_grad=True)
@@ -220,9 +224,15 @@ def test_wgrad_tc(case, ver):
     assert rel_l2(dw.cpu(), gw.float()) < 1e-4, (case, rel_l2(dw.cpu(), gw.float()))
     assert rel_l2(db.cpu(), gb.float()) < 1e-5
     # accumulation semantics: a second call doubles the result
-    call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks, dt)
+    call(ver, s0, C0, s1, C1, dyd, CoutP, dw, N, H, W, Cout, ks, dt, *extra)
     torch.cuda.synchronize()
     assert rel_l2(dw.cpu(), 2 * gw.float()) < 1e-4
+    if extra and extra[0] is not None:   # bit-stable: two fresh runs give identical bits
+        d1, d2 = torch.zeros_like(dw), torch.zeros_like(dw)
+        call(ver, s0, C0, s1, C1, dyd, CoutP, d1, N, H, W, Cout, ks, dt, *extra)
+        call(ver, s0, C0, s1, C1, dyd, CoutP, d2, N, H, W, Cout, ks, dt, *extra)
+        torch.cuda.synchronize()
+        assert torch.equal(d1, d2)
 
 
 SPLIT_CASES = [(2, 16, 16, 16, 0, 16, 3), (1, 16, 32, 32, 32, 32, 3), (1, 8, 16, 256, 0, 128, 1), (1, 16, 16, 128, 128, 128, 3),

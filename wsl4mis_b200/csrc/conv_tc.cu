@@ -740,6 +740,7 @@ struct WgradTcParams {
   const float* scale_a;  // optional device scalars multiplied into the result (split mode: 2^-k of the staged dY / X)
   const float* scale_b;
   float* dw;
+  float* partials;       // optional [gridDim.y][gridDim.x][TG*CWB][128]: per-CTA partial tiles for the fixed-order finalize
 };
 
 template <int CWA, int NA, int CWB, int TG, int STAGES>
@@ -849,6 +850,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     tc_fence_after();
     const int CinTot = p.C0 + p.C1;
     const float osc = (p.scale_a ? *p.scale_a : 1.f) * (p.scale_b ? *p.scale_b : 1.f);
+    if (p.partials != nullptr) {          // deterministic split-K (see wgrad1_finalize_kernel)
+      float* slot = p.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(TG * CWB * 128) + (q * 32 + lane);
+#pragma unroll 1
+      for (int c = 0; c < TG * CWB; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) slot[(size_t)(c + j) * 128] = v[j] * osc;
+      }
+    } else
 #pragma unroll 1
     for (int tl = 0; tl < TG; ++tl) {
       const int t = tg * TG + tl;
@@ -1060,6 +1071,7 @@ struct Wgrad3Params {
   int k_tiles0, k_tiles1;     // Cin blocks (of CWB channels) in source 0 / 1
   int dt;                     // 16-bit operand type: 0 bf16, 2 fp16
   float* dw;
+  float* partials;            // optional [gridDim.y][gridDim.x][3*NTILE][128]: per-CTA partial tiles for the fixed-order finalize
 };
 
 template <int CWB, int CWN, int NBOX, int STAGES, bool DYN>
@@ -1162,6 +1174,18 @@ __global__ void __launch_bounds__(NUM_THREADS, (DYN && CWN <= 32) ? 2 : 1) wgrad
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int CinTot = p.C0 + p.C1;
+    if (p.partials != nullptr) {
+      // deterministic split-K: this CTA's partial tile goes to its own slot (coalesced: lane = TMEM lane is the fastest index);
+      // wgrad3_finalize_kernel sums the slots of an output tile in split order and adds the result into dw
+      float* slot = p.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(3 * NTILE * 128) + m;
+#pragma unroll 1
+      for (int c = 0; c < 3 * NTILE; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) slot[(size_t)(c + j) * 128] = v[j];
+      }
+    } else
 #pragma unroll 1
     for (int grp = 0; grp < 3; ++grp) {
       const int dy = DYN ? 2 - grp : grp;       // column group -> filter row
@@ -1184,9 +1208,40 @@ __global__ void __launch_bounds__(NUM_THREADS, (DYN && CWN <= 32) ? 2 : 1) wgrad
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// Fixed-order reduction of the per-CTA partial tiles of one wgrad_tc3 launch: element e = (grp * NTILE + col) * 128 + m of output tile
+// blockIdx.y is summed over the `splits` slots in index order (independent of which CTA finished when) and ADDED to the torch-layout
+// gradient (accumulation semantics are kept: a second backward through shared weights adds on top).
+__global__ void __launch_bounds__(256) wgrad3_finalize_kernel(const float* __restrict__ partials, int splits, int ntile, int cwb, int dyn,
+                                                              int k_tiles0, int k_tiles, int C0, int CinTot, int CoutReal,
+                                                              float* __restrict__ dw) {
+  const int E = 3 * ntile * 128;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= E) return;
+  const int m = e & 127, col = (e >> 7) % ntile, grp = (e >> 7) / ntile;
+  const int g = m / cwb, ci = m % cwb;
+  const int kt = blockIdx.y % k_tiles, nt = blockIdx.y / k_tiles;
+  const int co = nt * ntile + col;
+  if (g >= 3 || co >= CoutReal) return;
+  const bool src1 = kt >= k_tiles0;
+  const int ci_global = (src1 ? C0 : 0) + (src1 ? kt - k_tiles0 : kt) * cwb;
+  const float* src = partials + (size_t)blockIdx.y * splits * E + e;
+  float acc = 0.f;
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(s + u) * E);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; s < splits; ++s) acc += __ldcg(src + (size_t)s * E);
+  const int dy = dyn ? 2 - grp : grp;
+  dw[((size_t)co * CinTot + ci_global + ci) * 9 + dy * 3 + g] += acc;
+}
+
 template <int CWB, int CWN, int NBOX>
-int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const Wgrad3Params& p, int n_tiles,
-                  cudaStream_t stream) {
+int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, Wgrad3Params p, int n_tiles,
+                  float* partial_ws, long long partial_floats, cudaStream_t stream) {
   constexpr bool DYN = (NBOX == 1);
   constexpr int per_stage = NBOX * TILE_M * CWN * 2 + 12 * 1024;
   constexpr int STAGES = per_stage >= 40 * 1024 ? 3 : 4;
@@ -1204,12 +1259,43 @@ int launch_wgrad3(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensor
   if (splits > p.nchunks) splits = p.nchunks;
   if (splits < 1) splits = 1;
   dim3 grid(splits, gy);
+  constexpr int NTILE = CWN * NBOX;
+  const long long need = (long long)splits * gy * 3 * NTILE * 128;
+  p.partials = (partial_ws != nullptr && need <= partial_floats) ? partial_ws : nullptr;     // too small a workspace: atomics
   wgrad_tc3_kernel<CWB, CWN, NBOX, STAGES, DYN><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
-  return wsl_check_launch("wgrad_tc3");
+  int rc = wsl_check_launch("wgrad_tc3");
+  if (rc || p.partials == nullptr) return rc;
+  wgrad3_finalize_kernel<<<dim3((3 * NTILE * 128 + 255) / 256, gy), 256, 0, stream>>>(p.partials, splits, NTILE, CWB, DYN ? 1 : 0, p.k_tiles0,
+                                                                                     p.k_tiles0 + p.k_tiles1, p.C0, p.C0 + p.C1, p.CoutReal, p.dw);
+  return wsl_check_launch("wgrad3_finalize");
 }
 
+// fixed-order reduction of wgrad_tc_kernel's per-CTA partial tiles: element e = (tl * CWB + c) * 128 + lane of output tile blockIdx.y
+__global__ void __launch_bounds__(256) wgrad1_finalize_kernel(const float* __restrict__ partials, int splits, int tg_size, int cwb,
+                                                              int tap_groups, int n_tiles0, int n_tiles, int C0, int CinTot,
+                                                              int CoutReal, int taps, float* __restrict__ dw) {
+  const int E = tg_size * cwb * 128;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= E) return;
+  const int lane = e & 127, c = (e >> 7) % cwb, tl = (e >> 7) / cwb;
+  int by = blockIdx.y;
+  const int tg = by % tap_groups; by /= tap_groups;
+  const int nt = by % n_tiles, mt = by / n_tiles;
+  const int row = mt * 128 + lane;
+  if (row >= CoutReal) return;
+  const bool src1 = nt >= n_tiles0;
+  const int ci = (src1 ? C0 : 0) + (src1 ? nt - n_tiles0 : nt) * cwb + c;
+  const float* src = partials + (size_t)blockIdx.y * splits * E + e;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += __ldcg(src + (size_t)s * E);
+  dw[((size_t)row * CinTot + ci) * taps + tg * tg_size + tl] += acc;
+}
+
+static thread_local float* g_wgrad1_ws = nullptr;        // set by the entry point for the launch helpers below
+static thread_local long long g_wgrad1_ws_floats = 0;
+
 template <int CWA, int NA, int CWB, int TG>
-int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, const WgradTcParams& p, int m_tiles,
+int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorMap& mx1, WgradTcParams p, int m_tiles,
                  cudaStream_t stream) {
   constexpr int per_stage = NA * TILE_M * CWA * 2 + TG * TILE_M * CWB * 2;
   constexpr int STAGES = per_stage >= 80 * 1024 ? 2 : per_stage >= 48 * 1024 ? 3 : 4;
@@ -1225,8 +1311,15 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx0, const CUtensorM
   if (splits > p.nchunks) splits = p.nchunks;
   if (splits < 1) splits = 1;
   dim3 grid(splits, gy);
+  const long long need = (long long)splits * gy * TG * CWB * 128;
+  p.partials = (g_wgrad1_ws != nullptr && need <= g_wgrad1_ws_floats) ? g_wgrad1_ws : nullptr;
   wgrad_tc_kernel<CWA, NA, CWB, TG, STAGES><<<grid, NUM_THREADS, S::TOTAL, stream>>>(mdy, mx0, mx1, p);
-  return wsl_check_launch("wgrad_tc");
+  int rc = wsl_check_launch("wgrad_tc");
+  if (rc || p.partials == nullptr) return rc;
+  wgrad1_finalize_kernel<<<dim3((TG * CWB * 128 + 255) / 256, gy), 256, 0, stream>>>(p.partials, splits, TG, CWB, p.tap_groups, p.n_tiles0,
+                                                                                   p.n_tiles0 + p.n_tiles1, p.C0, p.C0 + p.C1, p.CoutReal,
+                                                                                   p.taps, p.dw);
+  return wsl_check_launch("wgrad1_finalize");
 }
 
 template <int CWA, int NA, int CWB>
@@ -1246,7 +1339,7 @@ int wgrad_dispatch_b(int cwb, const CUtensorMap& a, const CUtensorMap& b0, const
 // per-channel sum of a channels-last bf16 tensor, added into out[C] (bias gradients of conv1x1 / out_conv)
 template <typename T, bool HALF = false>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ x, long long P, int C, int Creal,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, float* __restrict__ ws) {
   extern __shared__ float s_red[];
   const int cg = C >> 3, rows = 256 / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -1267,11 +1360,33 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_red[threadIdx.x * 8 + j] = sum[j];
   __syncthreads();
+  if (ws == nullptr) {
+    for (int c = threadIdx.x; c < Creal; c += 256) {
+      float a = 0.f;
+      for (int rr = 0; rr < rows; ++rr) a += s_red[(rr * cg + (c >> 3)) * 8 + (c & 7)];
+      atomicAdd(out + c, a);
+    }
+    return;
+  }
+  // deterministic: per-block rows, the last block to finish (ticket in ws[0]) adds them up in block order
   for (int c = threadIdx.x; c < Creal; c += 256) {
     float a = 0.f;
     for (int rr = 0; rr < rows; ++rr) a += s_red[(rr * cg + (c >> 3)) * 8 + (c & 7)];
-    atomicAdd(out + c, a);
+    ws[64 + (size_t)blockIdx.x * Creal + c] = a;
   }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<unsigned*>(ws), 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < Creal; c += 256) {
+    float a = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&ws[64 + (size_t)b * Creal + c]);
+    out[c] += a;
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws) = 0u;
 }
 
 
@@ -1650,7 +1765,9 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
 // pitch_x / pitch_dy > 0: the operands are channel-range views of wider channels-last tensors (fp16 hi/lo split planes)
 static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                          int W, int CoutReal, int ksize, int dtype, int pitch_x, int pitch_dy, const float* scale_a,
-                         const float* scale_b, cudaStream_t stream) {
+                         const float* scale_b, cudaStream_t stream, float* partial_ws = nullptr, long long partial_floats = 0) {
+  g_wgrad1_ws = partial_ws;
+  g_wgrad1_ws_floats = partial_floats;
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_wgrad_tc: ksize must be 1 or 3");
   WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_wgrad_tc: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc: source channels must be multiples of 16 (got %d,%d)", C0, C1);
@@ -1687,7 +1804,7 @@ static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, con
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = ksize * ksize; p.ks = ksize;
   p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dt = dtype; p.scale_a = scale_a; p.scale_b = scale_b; p.dw = dw;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dt = dtype; p.scale_a = scale_a; p.scale_b = scale_b; p.dw = dw; p.partials = nullptr;
   if (cwa == 64 && na == 2) return wgrad_dispatch_b<64, 2>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 64) return wgrad_dispatch_b<64, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 32) return wgrad_dispatch_b<32, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
@@ -1695,8 +1812,9 @@ static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, con
 }
 
 WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                         int W, int CoutReal, int ksize, int dtype, cudaStream_t stream) {
-  return wgrad_tc_impl(src0, C0, src1, C1, dy, CoutP, dw, N, H, W, CoutReal, ksize, dtype, 0, 0, nullptr, nullptr, stream);
+                         int W, int CoutReal, int ksize, int dtype, float* partial_ws, long long partial_floats, cudaStream_t stream) {
+  return wgrad_tc_impl(src0, C0, src1, C1, dy, CoutP, dw, N, H, W, CoutReal, ksize, dtype, 0, 0, nullptr, nullptr, stream, partial_ws,
+                       partial_floats);
 }
 
 // ---- fp16 hi/lo split ("fp16x3") tensor-core parity mode ------------------------------------------------------------
@@ -1759,15 +1877,15 @@ WSL_API int wsl_wgrad_tc_split(const void* x_staged, int Cin, const float* x_inv
   return wgrad_tc_impl(x, Cin, nullptr, 0, g + CoutP, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
 }
 
-WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, cudaStream_t stream) {
+WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, float* ws, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && Creal <= C, "wsl_channel_sum: unsupported channel count %d", C);
   const int rows = 256 / (C / 8);
   long long b = (P + rows * 16 - 1) / (rows * 16);
   if (b > 148 * 2) b = 148 * 2;
   if (b < 1) b = 1;
-  if (dtype == 1) channel_sum_kernel<float><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const float*)x, P, C, Creal, out);
-  else if (dtype == 2) channel_sum_kernel<__nv_bfloat16, true><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
-  else channel_sum_kernel<__nv_bfloat16><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out);
+  if (dtype == 1) channel_sum_kernel<float><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const float*)x, P, C, Creal, out, ws);
+  else if (dtype == 2) channel_sum_kernel<__nv_bfloat16, true><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out, ws);
+  else channel_sum_kernel<__nv_bfloat16><<<(int)b, 256, 256 * 8 * sizeof(float), stream>>>((const __nv_bfloat16*)x, P, C, Creal, out, ws);
   return wsl_check_launch("channel_sum");
 }
 
@@ -1918,7 +2036,7 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = 9; p.ks = 3;
   p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dt = dtype; p.scale_a = nullptr; p.scale_b = nullptr; p.dw = dw;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dt = dtype; p.scale_a = nullptr; p.scale_b = nullptr; p.dw = dw; p.partials = nullptr;
   if (cwb == 32) {
     if (cwa == 64 && na == 2) return launch_wgrad2<64, 2, 32>(mdy, mx0, mx1, p, m_tiles, stream);
     if (cwa == 64) return launch_wgrad2<64, 1, 32>(mdy, mx0, mx1, p, m_tiles, stream);
@@ -1933,7 +2051,7 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
 
 // 3x3 weight gradient, v3 (filter columns in the MMA's M dimension).  Same contract as wsl_wgrad_tc2.
 WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
-                          int W, int CoutReal, int ksize, int dtype, cudaStream_t stream) {
+                          int W, int CoutReal, int ksize, int dtype, float* partial_ws, long long partial_floats, cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3, "wsl_wgrad_tc3: 3x3 only");
   WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_wgrad_tc3: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_wgrad_tc3: source channels must be multiples of 16 (got %d,%d)", C0, C1);
@@ -1969,12 +2087,12 @@ WSL_API int wsl_wgrad_tc3(const void* src0, int C0, const void* src1, int C1, co
   Wgrad3Params p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutReal = CoutReal;
   p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.k_tiles0 = C0 / cwb; p.k_tiles1 = C1 / cwb; p.dt = dtype; p.dw = dw;
+  p.k_tiles0 = C0 / cwb; p.k_tiles1 = C1 / cwb; p.dt = dtype; p.dw = dw; p.partials = nullptr;
 #define WSL_W3(CWB_) \
-  if (ntile == 128) return launch_wgrad3<CWB_, 64, 2>(mdy, mx0, mx1, p, n_tiles, stream); \
-  if (ntile == 64) return launch_wgrad3<CWB_, 64, 1>(mdy, mx0, mx1, p, n_tiles, stream);  \
-  if (ntile == 32) return launch_wgrad3<CWB_, 32, 1>(mdy, mx0, mx1, p, n_tiles, stream);  \
-  return launch_wgrad3<CWB_, 16, 1>(mdy, mx0, mx1, p, n_tiles, stream);
+  if (ntile == 128) return launch_wgrad3<CWB_, 64, 2>(mdy, mx0, mx1, p, n_tiles, partial_ws, partial_floats, stream); \
+  if (ntile == 64) return launch_wgrad3<CWB_, 64, 1>(mdy, mx0, mx1, p, n_tiles, partial_ws, partial_floats, stream);  \
+  if (ntile == 32) return launch_wgrad3<CWB_, 32, 1>(mdy, mx0, mx1, p, n_tiles, partial_ws, partial_floats, stream);  \
+  return launch_wgrad3<CWB_, 16, 1>(mdy, mx0, mx1, p, n_tiles, partial_ws, partial_floats, stream);
   if (cwb == 32) { WSL_W3(32) }
   WSL_W3(16)
 #undef WSL_W3

@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
 // value and block.
 template <typename T>
 __global__ void __launch_bounds__(TPB, 1) bn_bwd_apply_first_kernel(BnBwdArgs<T> a, const float* __restrict__ coef, const float* __restrict__ x,
-                                                                    float* __restrict__ dw /*[16][9]*/) {
+                                                                    float* __restrict__ dw /*[16][9]*/, float* __restrict__ ws) {
   // (a channel-QUARTER mapping with 36 accumulators and two blocks per SM was measured slower, 240 vs 177 us: the bytes in flight per
   // SM are what bounds this kernel, and halving the bytes per thread cancels the doubled thread count)
   const BnBwdThread t = bn_bwd_thread(a);          // C == 16: cg == 2, t.g = channel half
@@ -965,13 +965,27 @@ __global__ void __launch_bounds__(TPB, 1) bn_bwd_apply_first_kernel(BnBwdArgs<T>
       if (lane < 2) s_red[warp][lane][j * 9 + k] = v;
     }
   __syncthreads();
+  // deterministic: one row of 144 values per block in the workspace, the last block (ticket) adds the rows in block order into dw
   if (threadIdx.x < 144) {
     const int half = threadIdx.x / 72, e = threadIdx.x % 72;
     float v = 0.f;
 #pragma unroll
     for (int wv = 0; wv < TPB / 32; ++wv) v += s_red[wv][half][e];
-    atomicAdd(dw + half * 72 + e, v);                                               // dw[co][t], co = half*8 + j
+    ws[64 + (size_t)blockIdx.x * 144 + threadIdx.x] = v;                            // index = co*9 + t with co = half*8 + j
   }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<unsigned*>(ws) + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 144) {
+    float v = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) v += __ldcg(&ws[64 + (size_t)b * 144 + threadIdx.x]);
+    dw[threadIdx.x] += v;
+  }
+  if (threadIdx.x == 0) reinterpret_cast<unsigned*>(ws)[1] = 0u;
 }
 
 // ================================================================================================
@@ -1470,7 +1484,7 @@ WSL_API int wsl_bn_bwd_first(const void* y, int dtype, const float* ss, const fl
     a.y = (const T*)y; a.ss = ss; a.save = save; a.g0 = (const T*)g0; a.g1 = nullptr; a.cs1 = nullptr; a.gp = nullptr; a.pool_idx = nullptr;
     a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p; a.slope = slope; a.N = N; a.H = H; a.W = W; a.C = C;
     bn_bwd_reduce_kernel<0, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, ticket, accumulate);
-    bn_bwd_apply_first_kernel<T><<<grid2, TPB, 0, stream>>>(a, coef, image, dw);
+    bn_bwd_apply_first_kernel<T><<<grid2, TPB, 0, stream>>>(a, coef, image, dw, ws);   // reuses ws after the reduce kernel (same stream)
   });
   return wsl_check_launch("bn_bwd_first");
 }

@@ -194,6 +194,7 @@ class UNetExecutor:
         self.fuse_bn_stats = os.environ.get("WSL4MIS_NO_FUSED_STATS", "0") != "1"
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
         self.fuse_first_bwd = os.environ.get("WSL4MIS_NO_FUSED_FIRST_BWD", "0") != "1"
+        self.deterministic_wgrad = os.environ.get("WSL4MIS_ATOMIC_WGRAD", "0") != "1"     # split-K partials + fixed-order finalize
         self.on_decoders_done = None     # optional callback(gflat) between the decoder and encoder halves of backward()
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._sides = {}                 # named side streams
@@ -231,6 +232,14 @@ class UNetExecutor:
 
     def _ws(self, tag):
         return workspace(tag + ("" if not self._side_stack else "." + self._side_stack[-1]), self.dev)
+
+    def _wgrad_partials(self):
+        """per-stream workspace for the split-K partial tiles of the deterministic weight gradient (largest layer: 144 CTAs x 196 KB)"""
+        key = ("wgp", self._side_stack[-1] if self._side_stack else "main")
+        t = self._bufs.get(key)
+        if t is None or t.device != self.dev:
+            t = self._bufs[key] = torch.empty(8 * 1024 * 1024, dtype=torch.float32, device=self.dev)
+        return t
 
     def _stat_scratch(self):
         """per-stream scratch for the conv-epilogue BatchNorm partial rows"""
@@ -409,11 +418,15 @@ class UNetExecutor:
             call("wsl_wgrad_tc_split", sx, L.Cin, ix, sg, L.CoutP, ig, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
             tc = True
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W) and self.wgrad_version == 3 and (L.CoutP <= 64 or L.CoutP % 128 == 0):
-            call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
+            pw = self._wgrad_partials() if self.deterministic_wgrad else None
+            call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt, pw,
+                 pw.numel() if pw is not None else 0)
         elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W):
             call("wsl_wgrad_tc2", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
         elif tc:
-            call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
+            pw = self._wgrad_partials() if self.deterministic_wgrad else None
+            call("wsl_wgrad_tc", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt, pw,
+                 pw.numel() if pw is not None else 0)
         else:
             call("wsl_wgrad_direct", s0, c0, s1, c1, 1 if (src_f32 or self.dt == 1) else self.dt, dy, self.dt, L.CoutP,
                  self.gview(L.conv.weight), self.gview(L.conv.bias) if L.bn is None else None, N, H, W, L.Cout, L.ks)
@@ -421,7 +434,8 @@ class UNetExecutor:
         # Bias gradient.  A conv bias that feeds training-mode BatchNorm has an exactly-zero gradient (BN removes the
         # per-channel mean); the reference holds ~1e-8 rounding noise there.  We leave the zero-filled bucket as is.
         if tc and L.bn is None:
-            call("wsl_channel_sum", dy, self.dt, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias))
+            call("wsl_channel_sum", dy, self.dt, N * H * W, L.CoutP, L.Cout, self.gview(L.conv.bias),
+                 self._ws("csum") if self.deterministic_wgrad else None)
 
     def bn_bufs(self, L, slot, tag):
         C = L.Cout
