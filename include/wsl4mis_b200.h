@@ -223,6 +223,14 @@ int wsl_bn_act_fwd(const void* y, int dtype, const float* ss, int N, int H, int 
                    const uint8_t* mask, unsigned long long seed, const unsigned long long* seed_ptr, void* act,
                    void* pooled, uint8_t* pool_idx, cudaStream_t stream);
 
+/* the same with wsl_bn_finalize folded in (C <= 32): every block derives {scale, shift} from the convolution epilogue's partial rows,
+ * block 0 publishes save / ss / running statistics; one launch less on the forward critical path of the full-resolution layers. */
+int wsl_bn_finalize_act_fwd(const void* y, int dtype, const float* partials, int nrows, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                            float* save, float* ss, int N, int H, int W, int C, float slope, float drop_p, const uint8_t* mask,
+                            unsigned long long seed, const unsigned long long* seed_ptr, void* act, void* pooled,
+                            uint8_t* pool_idx, cudaStream_t stream);
+
 /* backward of the same chain: dA = g0 + cs1*g1 + maxpool-routed gpool (each optional) -> dY, dgamma, dbeta (added to the
  * existing values when accumulate != 0: a second backward through shared weights, e.g. the mean-teacher student). */
 int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,

@@ -1287,7 +1287,15 @@ __global__ void __launch_bounds__(256) wgrad1_finalize_kernel(const float* __res
   const int ci = (src1 ? C0 : 0) + (src1 ? nt - n_tiles0 : nt) * cwb + c;
   const float* src = partials + (size_t)blockIdx.y * splits * E + e;
   float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += __ldcg(src + (size_t)s * E);
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {            // eight loads in flight, fixed summation order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(s + u) * E);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; s < splits; ++s) acc += __ldcg(src + (size_t)s * E);
   dw[((size_t)row * CinTot + ci) * taps + tg * tg_size + tl] += acc;
 }
 
@@ -1381,10 +1389,28 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < Creal; c += 256) {
-    float a = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&ws[64 + (size_t)b * Creal + c]);
-    out[c] += a;
+  // all 256 threads: `parts` threads per channel walk interleaved block subsets (8 loads in flight), then a fixed-order combine
+  __shared__ float s_fin[256];
+  const int parts = 256 / Creal > 0 ? 256 / Creal : 1;
+  const int c = threadIdx.x % Creal, part = threadIdx.x / Creal;
+  float a = 0.f;
+  if (part < parts) {
+    int b = part;
+    for (; b + 7 * parts < (int)gridDim.x; b += 8 * parts) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(&ws[64 + (size_t)(b + u * parts) * Creal + c]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; b < (int)gridDim.x; b += parts) a += __ldcg(&ws[64 + (size_t)b * Creal + c]);
+  }
+  s_fin[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < Creal) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += s_fin[q * Creal + threadIdx.x];
+    out[threadIdx.x] += t;
   }
   if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws) = 0u;
 }

@@ -195,6 +195,9 @@ class UNetExecutor:
         self.defer_aux = os.environ.get("WSL4MIS_DEFER_AUX", "1") == "1"
         self.fuse_first_bwd = os.environ.get("WSL4MIS_NO_FUSED_FIRST_BWD", "0") != "1"
         self.deterministic_wgrad = os.environ.get("WSL4MIS_ATOMIC_WGRAD", "0") != "1"     # split-K partials + fixed-order finalize
+        # bn_finalize folded into bn_act_fwd for C <= 32 (every block re-derives scale / shift from the partial rows): measured SLOWER
+        # (12 launches 0.50 + 0.11 ms -> 0.91 ms: 1184 blocks each pay the fp64 prologue), so it stays off; kept for the A/B record
+        self.fold_finalize = os.environ.get("WSL4MIS_FOLDED_FINALIZE", "0") == "1"
         self.on_decoders_done = None     # optional callback(gflat) between the decoder and encoder halves of backward()
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._sides = {}                 # named side streams
@@ -354,9 +357,12 @@ class UNetExecutor:
                 bn = L.bn
                 call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, sb, ctypes.addressof(self._stat_rows))
                 self._untag()
-                call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
-                     bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
-                rows = True
+                if self.fold_finalize and L.Cout <= 32:
+                    rows = (sb, self._stat_rows.value)          # finalised inside the consumer (bn_fwd)
+                else:
+                    call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
+                         bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
+                    rows = True
             else:
                 call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, None, None)
         elif not src_f32 and self._split_ok(L.srcC, H, W):
@@ -369,9 +375,12 @@ class UNetExecutor:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0, N, H, W, L.CoutP, cout_store, L.ks, self.dt,
                      sb, ctypes.addressof(self._stat_rows))
                 self._untag()                      # the finalize launch is not a convolution: keep it out of the conv roofline rows
-                call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
-                     bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
-                rows = True
+                if self.fold_finalize and L.Cout <= 32:
+                    rows = (sb, self._stat_rows.value)          # finalised inside the consumer (bn_fwd)
+                else:
+                    call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
+                         bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
+                    rows = True
             else:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
                      cout_store, L.ks, self.dt, None, None)
@@ -447,8 +456,9 @@ class UNetExecutor:
         pk = L.packs(self.dev)
         save = self.buf(slot, tag + ".save", (2 * C,), torch.float32)
         ss = self.buf(slot, tag + ".ss", (2 * C,), torch.float32)
+        deferred = stats_done if isinstance(stats_done, tuple) else None
         if training and stats_done:
-            pass                       # save / ss were written by the convolution kernel
+            pass                       # save / ss come from the convolution epilogue's partial rows (bn_finalize, or folded in below)
         elif training:
             call("wsl_bn_stats", y, self.dt, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                  bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"))
@@ -458,8 +468,13 @@ class UNetExecutor:
         seed = self._layer_seed(L)
         esz = 4 if self.dt == 1 else 2
         self._tag_bytes("bn_act", L, N * H * W * C * esz * (2.25 if pooled is not None else 2.0))
-        call("wsl_bn_act_fwd", y, self.dt, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
-             act, pooled, pool_idx)
+        if training and deferred is not None:
+            call("wsl_bn_finalize_act_fwd", y, self.dt, deferred[0], deferred[1], bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed,
+                 self.seed_dev if mask is None and p > 0 else None, act, pooled, pool_idx)
+        else:
+            call("wsl_bn_act_fwd", y, self.dt, ss, N, H, W, C, LRELU_SLOPE, p, mask, seed, self.seed_dev if mask is None and p > 0 else None,
+                 act, pooled, pool_idx)
         self._untag()
         return save, ss
 
