@@ -212,7 +212,9 @@ int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, flo
  * running stats / num_batches_tracked updated in place when non-NULL. */
 int wsl_bn_stats(const void* y, int dtype, long long P, int C, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
-                 float* ss, float* ws, cudaStream_t stream);
+                 float* ss, float* ws, float* raw_sums, cudaStream_t stream);
+/* raw_sums (optional, 2C floats): write {sum, sum of squares} there and stop (no save / ss / running update): synchronised BatchNorm
+ * all-reduces them over the data-parallel ranks and finalises with wsl_bn_finalize(raw_sums, 1, P_global, ...). */
 int wsl_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float eps, int C, float* ss, cudaStream_t stream);
 
@@ -237,6 +239,15 @@ int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* save, con
                const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma, float* dbeta, float* coef, void* dy, float* ws, int accumulate,
                cudaStream_t stream);
+
+/* synchronised BatchNorm backward: phase 1 = reduction only (local dgamma / dbeta + raw_sums {sum dz, sum dz*xhat}); the caller
+ * all-reduces raw_sums; wsl_bn_bwd_coef forms the apply constants from the GLOBAL sums and pixel count; phase 2 = apply only. */
+int wsl_bn_bwd_phase(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+                     const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
+                     const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma,
+                     float* dbeta, float* coef, void* dy, float* ws, int accumulate, int phase, float* raw_sums, cudaStream_t stream);
+int wsl_bn_bwd_coef(const float* raw_sums, long long P_global, const float* ss, const float* save, int C, float* coef,
+                    cudaStream_t stream);
 
 /* first layer (1 -> 16 channels, unet.py:81 in_conv): BatchNorm backward + the convolution's weight gradient in one pass -- dY is
  * formed in registers and never stored (the image needs no data gradient): dgamma / dbeta as wsl_bn_bwd, dw[16][1][3][3] += dY^T * x. */

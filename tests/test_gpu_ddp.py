@@ -128,3 +128,61 @@ def test_graph_mode_equals_eager():
     print(f"parameters after 5 steps, eager vs graph mode: rel-L2 {err:.2e}")
     assert err < 2e-3, err
     assert all(abs(x - y) < 2e-2 * abs(x) for x, y in zip(a[0]["losses"], b[0]["losses"])), (a[0]["losses"], b[0]["losses"])
+
+
+def _worker_global(rank, world, port, variant, out):
+    """two ranks with global_batch=True (synchronised BatchNorm, global loss normalisers), fp32-accurate executor"""
+    import datetime
+    import random
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
+    try:
+        from wsl4mis_b200.engine import TrainStep
+        N, HW = 8, 64
+        image, label = _batch(N, HW, 3)
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        m, cct = _model(dev, variant)
+        m.set_precision("fp16x3")
+        _fix_masks(m, hi - lo, HW, dev, cct)
+        step = TrainStep(m, variant, graph=False, world_size=world, global_batch=True)
+        random.seed(5)
+        loss = float(step(image[lo:hi].to(dev), label[lo:hi].to(dev)))
+        torch.cuda.synchronize()
+        out[rank] = {"flat": step.flat.detach().cpu(), "loss": loss}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("variant", ["pce_gatedcrf", "dmpls"])
+def test_global_batch_mode_equals_the_single_process_step(variant):
+    """with synchronised BatchNorm statistics and batch-wide loss normalisers, 2 ranks x 4 images take the SAME
+    optimiser step as one process on the 8 images (the reference's own arithmetic at the global batch), in the fp32-accurate mode."""
+    import random
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_global, args=(2, _free_port(), variant, out), nprocs=2, join=True)
+    res = dict(out)
+    assert torch.equal(res[0]["flat"], res[1]["flat"])
+    from wsl4mis_b200.engine import TrainStep
+    dev = torch.device("cuda", 0)
+    N, HW = 8, 64
+    image, label = _batch(N, HW, 3)
+    m, cct = _model(dev, variant)
+    m.set_precision("fp16x3")
+    before = torch.cat([q.detach().flatten() for q in m.parameters()]).cpu()
+    _fix_masks(m, N, HW, dev, cct)
+    st = TrainStep(m, variant, graph=False, world_size=1)
+    random.seed(5)
+    st(image.to(dev), label.to(dev))
+    torch.cuda.synchronize()
+    single = st.flat.detach().cpu()
+    upd_ref, upd = single - before, res[0]["flat"] - before
+    err = ((upd - upd_ref).norm() / upd_ref.norm()).item()
+    print(f"[{variant}] optimiser step of 2 x 4 (global-batch mode) vs 1 x 8: rel-L2 of the update {err:.2e}")
+    assert err < 2e-3, err

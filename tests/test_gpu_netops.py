@@ -339,7 +339,7 @@ def test_bn_stats_and_act(shape):
     save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
     rmd, rvd = rm.to(DEV), rv.to(DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
-    call("wsl_bn_stats", yd, 0, N * H * W, C, gamma.to(DEV), beta.to(DEV), rmd, rvd, nbt, 0.1, 1e-5, save, ss, workspace("bn"))
+    call("wsl_bn_stats", yd, 0, N * H * W, C, gamma.to(DEV), beta.to(DEV), rmd, rvd, nbt, 0.1, 1e-5, save, ss, workspace("bn"), None)
     rm2, rv2 = rm.clone(), rv.clone()
     ref = F.batch_norm(y, rm2, rv2, gamma, beta, True, 0.1, 1e-5)
     torch.cuda.synchronize()
@@ -404,7 +404,7 @@ def test_bn_backward_chain(shape):
     # kernels
     yd = nhwc(y).to(DEV)
     save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
-    call("wsl_bn_stats", yd, 0, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
+    call("wsl_bn_stats", yd, 0, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"), None)
     act = torch.zeros((N, H, W, C), device=DEV, dtype=BF)
     pooled = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=BF)
     pidx = torch.zeros((N, H // 2, W // 2, C), device=DEV, dtype=torch.uint8)
@@ -446,7 +446,7 @@ def test_first_layer_fused_backward(shape, dt):
     dwr, dgr, dbr = torch.autograd.grad(a, [wr, gr, br], g0.double())
     yd = nhwc(y, tdt).to(DEV)
     save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
-    call("wsl_bn_stats", yd, dt, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
+    call("wsl_bn_stats", yd, dt, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"), None)
     mk = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
     dgam, dbet, coef = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2 * C, device=DEV)
     dw = torch.zeros(C, 1, 3, 3, device=DEV)
@@ -473,7 +473,7 @@ def test_bn_backward_is_well_conditioned_at_the_baseline_shape():
     dyr, dgr, dbr = torch.autograd.grad(a, [yr, gr, br], g0.double())
     yd = nhwc(y, torch.float32).to(DEV)
     save, ss = torch.zeros(2 * C, device=DEV), torch.zeros(2 * C, device=DEV)
-    call("wsl_bn_stats", yd, 1, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"))
+    call("wsl_bn_stats", yd, 1, N * H * W, C, gamma.to(DEV), beta.to(DEV), None, None, None, 0.1, 1e-5, save, ss, workspace("bn"), None)
     dgam, dbet, coef = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2 * C, device=DEV)
     dy = torch.zeros((N, H, W, C), device=DEV)
     call("wsl_bn_bwd", yd, 1, ss, save, nhwc(g0, torch.float32).to(DEV), None, None, None, None, None, 0, None, 0.0, 0.01, N, H, W, C,

@@ -422,7 +422,7 @@ template <typename T>
 __global__ void __launch_bounds__(TPB) bn_stats_kernel(
     const T* __restrict__ y, long long P, int C, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt, float momentum,
-    float eps, float* __restrict__ save, float* __restrict__ ss, float* partials, unsigned* ticket) {
+    float eps, float* __restrict__ save, float* __restrict__ ss, float* partials, unsigned* ticket, float* raw_sums) {
   extern __shared__ float s_red[];  // [TPB][16]
   const int cg = C >> 3, rows = TPB / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -457,6 +457,11 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(
   __shared__ double s_fin[2 * 256];
   __shared__ double s_part[TPB * 2];
   bn_finalize_partials(partials, gridDim.x, C, s_fin, s_part);
+  if (raw_sums != nullptr) {       // synchronised BatchNorm: hand out {sum, sum of squares}; the caller all-reduces and finalises
+    for (int c = threadIdx.x; c < 2 * C; c += TPB) raw_sums[c] = (float)s_fin[c];
+    if (threadIdx.x == 0) *ticket = 0u;
+    return;
+  }
   for (int c = threadIdx.x; c < C; c += TPB) {
     const double a = s_fin[c], b = s_fin[C + c];
     const double mean = a / (double)P;
@@ -851,7 +856,7 @@ __device__ __forceinline__ void bn_bwd_finish8(const BnBwdArgs<T>& a, const BnBw
 template <int MODE, typename T>
 __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_reduce_kernel(BnBwdArgs<T> a, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ coef /*[2C]*/,
-                                                               float* partials, unsigned* ticket, int accumulate) {
+                                                               float* partials, unsigned* ticket, int accumulate, float* raw_sums = nullptr) {
   extern __shared__ float s_red[];
   const BnBwdThread t = bn_bwd_thread(a);
   const int C = a.C, cg = t.cg, rows = TPB / cg;
@@ -909,6 +914,7 @@ __global__ void __launch_bounds__(TPB, (MODE == 0 || MODE == 4) ? 3 : 2) bn_bwd_
     const double x = s_fin[c], y = s_fin[C + c];
     dbeta[c] = accumulate ? dbeta[c] + (float)x : (float)x;      // accumulate: second backward through shared weights
     dgamma[c] = accumulate ? dgamma[c] + (float)y : (float)y;
+    if (raw_sums != nullptr) { raw_sums[c] = (float)x; raw_sums[C + c] = (float)y; }   // synchronised BatchNorm: all-reduced by the caller
     // apply-pass constants: dY = dz*A + y*B + D with A = scale, B = -scale*c2*invstd, D = -scale*c1 + scale*c2*mean*invstd
     const double c1 = x / (double)P, c2 = y / (double)P;
     const double sc = (double)a.ss[c], istd = (double)a.save[C + c], mean = (double)a.save[c];
@@ -1457,13 +1463,13 @@ WSL_API int wsl_wgrad_direct(const void* src0, int C0, const void* src1, int C1,
 
 WSL_API int wsl_bn_stats(const void* y, int dtype, long long P, int C, const float* gamma, const float* beta, float* running_mean,
                          float* running_var, long long* num_batches_tracked, float momentum, float eps, float* save,
-                         float* ss, float* ws, cudaStream_t stream) {
+                         float* ss, float* ws, float* raw_sums, cudaStream_t stream) {
   WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_stats: unsupported channel count %d", C);
   const int grid = bn_grid(P, C);
   WSL_REQUIRE((long long)grid * 2 * C + 64 <= WSL_WS_FLOATS, "wsl_bn_stats: workspace too small");
   WSL_DISPATCH_T(dtype, bn_stats_kernel<T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(
                             (const T*)y, P, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, save, ss,
-                            ws + 64, reinterpret_cast<unsigned*>(ws)));
+                            ws + 64, reinterpret_cast<unsigned*>(ws), raw_sums));
   return wsl_check_launch("bn_stats");
 }
 
@@ -1511,7 +1517,8 @@ template <typename T>
 static int bn_bwd_launch(const void* y, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
                          const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
                          const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma,
-                         float* dbeta, float* coef, void* dy, float* ws, int accumulate, cudaStream_t stream) {
+                         float* dbeta, float* coef, void* dy, float* ws, int accumulate, cudaStream_t stream, int phase = 0,
+                         float* raw_sums = nullptr) {
   BnBwdArgs<T> a;
   a.y = (const T*)y; a.ss = ss; a.save = save; a.g0 = (const T*)g0; a.g1 = (const T*)g1;
   a.cs1 = cs1; a.gp = (const T*)gpool; a.pool_idx = pool_idx; a.mask = mask; a.seed = seed; a.seed_ptr = seed_ptr; a.drop_p = drop_p;
@@ -1520,17 +1527,20 @@ static int bn_bwd_launch(const void* y, const float* ss, const float* save, cons
   const int mode = (g0 == nullptr) ? 4 : ((g1 ? 1 : 0) | (gpool ? 2 : 0));
   const int grid = bn_grid(P, C, (mode == 0 || mode == 4) ? 3 : 2);
   unsigned* ticket = reinterpret_cast<unsigned*>(ws);
-#define WSL_BN_RED(M) bn_bwd_reduce_kernel<M, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, ticket, accumulate)
+#define WSL_BN_RED(M) bn_bwd_reduce_kernel<M, T><<<grid, TPB, TPB * 16 * sizeof(float), stream>>>(a, dgamma, dbeta, coef, ws + 64, ticket, accumulate, raw_sums)
 #define WSL_BN_APP(M) bn_bwd_apply_kernel<M, T><<<grid, TPB, 0, stream>>>(a, coef, (T*)dy)
-  switch (mode) {
-    case 0: WSL_BN_RED(0); break;
-    case 1: WSL_BN_RED(1); break;
-    case 2: WSL_BN_RED(2); break;
-    case 3: WSL_BN_RED(3); break;
-    default: WSL_BN_RED(4); break;
+  int rc = 0;
+  if (phase != 2) {
+    switch (mode) {
+      case 0: WSL_BN_RED(0); break;
+      case 1: WSL_BN_RED(1); break;
+      case 2: WSL_BN_RED(2); break;
+      case 3: WSL_BN_RED(3); break;
+      default: WSL_BN_RED(4); break;
+    }
+    rc = wsl_check_launch("bn_bwd_reduce");
+    if (rc || phase == 1) return rc;
   }
-  int rc = wsl_check_launch("bn_bwd_reduce");
-  if (rc) return rc;
   switch (mode) {
     case 0: WSL_BN_APP(0); break;
     case 1: WSL_BN_APP(1); break;
@@ -1555,6 +1565,38 @@ WSL_API int wsl_bn_bwd(const void* y, int dtype, const float* ss, const float* s
   if (dtype == 2)
     return bn_bwd_launch<__half>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
   return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream);
+}
+
+// Synchronised BatchNorm (global-batch statistics across data-parallel ranks): phase 1 = reduction only (local dgamma / dbeta and the raw
+// sums {sum dz, sum dz*xhat}), the caller all-reduces raw_sums, wsl_bn_bwd_coef turns the GLOBAL sums into the apply constants, phase 2 =
+// apply only.
+WSL_API int wsl_bn_bwd_phase(const void* y, int dtype, const float* ss, const float* save, const void* g0, const void* g1, const float* cs1,
+                             const void* gpool, const uint8_t* pool_idx, const uint8_t* mask, unsigned long long seed,
+                             const unsigned long long* seed_ptr, float drop_p, float slope, int N, int H, int W, int C, float* dgamma,
+                             float* dbeta, float* coef, void* dy, float* ws, int accumulate, int phase, float* raw_sums, cudaStream_t stream) {
+  WSL_REQUIRE(C % 8 == 0 && C <= 256 && TPB % (C / 8) == 0, "wsl_bn_bwd_phase: unsupported channel count %d", C);
+  WSL_REQUIRE(phase == 1 || phase == 2, "wsl_bn_bwd_phase: phase must be 1 (reduce) or 2 (apply)");
+  if (dtype == 1)
+    return bn_bwd_launch<float>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream, phase, raw_sums);
+  if (dtype == 2)
+    return bn_bwd_launch<__half>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream, phase, raw_sums);
+  return bn_bwd_launch<bf16>(y, ss, save, g0, g1, cs1, gpool, pool_idx, mask, seed, seed_ptr, drop_p, slope, N, H, W, C, dgamma, dbeta, coef, dy, ws, accumulate, stream, phase, raw_sums);
+}
+
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ raw_sums, double P, const float* __restrict__ ss, const float* __restrict__ save,
+                                   int C, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double c1 = (double)raw_sums[c] / P, c2 = (double)raw_sums[C + c] / P;
+  const double sc = (double)ss[c], istd = (double)save[C + c], mean = (double)save[c];
+  coef[c] = (float)(-sc * c2 * istd);
+  coef[C + c] = (float)(-sc * c1 + sc * c2 * mean * istd);
+}
+
+WSL_API int wsl_bn_bwd_coef(const float* raw_sums, long long P_global, const float* ss, const float* save, int C, float* coef,
+                            cudaStream_t stream) {
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(raw_sums, (double)P_global, ss, save, C, coef);
+  return wsl_check_launch("bn_bwd_coef");
 }
 
 WSL_API int wsl_bn_bwd_first(const void* y, int dtype, const float* ss, const float* save, const void* g0, const uint8_t* mask,

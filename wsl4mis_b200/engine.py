@@ -33,7 +33,12 @@ VARIANTS = ("pce", "pce_gatedcrf", "pce_ms", "pce_tv", "dmpls", "pce_entropy", "
 
 class TrainStep:
     def __init__(self, model, variant="pce_gatedcrf", base_lr=0.01, max_iterations=30000, momentum=0.9,
-                 weight_decay=1e-4, graph=True, process_group=None, world_size=1):
+                 weight_decay=1e-4, graph=True, process_group=None, world_size=1, global_batch=False):
+        """global_batch (world_size > 1): reproduce the SINGLE-PROCESS arithmetic of the reference at the global batch:
+        BatchNorm statistics over all ranks' pixels (forward and backward all-reduce 2C floats per layer), the pCE mean over the
+        labelled pixels of the whole batch, Dice ratios of batch-wide sums.  Default off = stock DDP semantics (per-rank BatchNorm
+        and loss normalisers), which is what the weak-scaling benchmark runs.  The collectives are issued from the host inside the
+        step, so this mode runs eagerly (no CUDA graph)."""
         assert variant in VARIANTS
         self.model, self.variant = model, variant
         self.ex = model.executor
@@ -42,6 +47,10 @@ class TrainStep:
         self.graph_enabled = bool(graph)
         self.world_size = int(world_size)
         self.pg = process_group
+        self.global_batch = bool(global_batch) and self.world_size > 1
+        if self.global_batch:
+            self.graph_enabled = False
+            self.ex.sync_bn = (self.world_size, self.pg)
         self.iter_num = 0
         self._graphs = [None, None]
         self._warm = 0
@@ -122,13 +131,23 @@ class TrainStep:
         # the 16-bit layouts receive the logit gradient already multiplied by the executor's loss scale (1 unless fp16);
         # plain fp32 NCHW gradients are scaled by the executor itself
         S = ex.grad_scale_for(N, H, W) if ex.dt != 1 else 1.0
+        if self.global_batch:
+            S = S * self.world_size      # the pCE term is normalised by the global count: its rank contributions ADD, while the
+            #                              optimiser averages the bucket (1/world) -- every per-rank-mean term is divided back below
+        G = 1.0 / self.world_size if self.global_batch else 1.0       # factor for regularisers that are per-rank MEANS (CRF, entropy)
         v = self.variant
+        if self.global_batch and v in ("pce_tv", "pce_variance"):
+            raise NotImplementedError(f"global_batch semantics are not defined here for '{v}' (batch-slice TV / per-sample variance ramps)")
         heads = range(self.n_heads_trained)
         probs, stats = [], []
         for h in heads:
             p = B(f"probs{h}", (N, C, H, W))
             st = B(f"stats{h}", (2,))
             call("wsl_softmax_pce_fwd", logits_list[h], label, p, N, C, H, W, 4, st, workspace("pce", dev))
+            if self.global_batch:        # mean over the labelled pixels of the GLOBAL batch: all-reduce {sum of NLL, count}
+                tot = torch.stack((st[0] * st[1], st[1]))
+                ddp.allreduce_flat(tot, self.pg)
+                st.copy_(torch.stack((tot[0] / tot[1], tot[1])))
             probs.append(p)
             stats.append(st)
         ce = stats[0][0]
@@ -142,7 +161,7 @@ class TrainStep:
             call("wsl_gatedcrf_fwd", probs[0], image, gp, N, C, H, W, 5, 6.0, 0.1, 1.0, out, workspace("crf", dev))
             loss = ce + 0.1 * out[0]
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 0.1 * S, N, C, H, W, 4, d, d16, self.ex.dt)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 0.1 * S * G, N, C, H, W, 4, d, d16, self.ex.dt)
             self.loss_parts = {"ce": ce, "crf": out[0]}
         elif v == "pce_ms":
             gp = B("gprobs0", (N, C, H, W))
@@ -172,7 +191,7 @@ class TrainStep:
             call("wsl_entropy_bwd", probs[0], N, C, H, W, 0.1, 0, gp)
             loss = ce + 0.1 * out[0]
             d, d16, dl[0] = self._dlogits(ex, slot, "dl0", N, C, H, W)
-            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 1.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)
+            call("wsl_head_bwd", probs[0], label, stats[0], None, 1.0 * S, gp, 1.0 * S * G, N, C, H, W, 4, d, d16, self.ex.dt)
         elif v == "pce_variance":
             from .utils import ramps
             w = self.consistency * ramps.sigmoid_rampup(self.iter_num // 150, self.consistency_rampup)
@@ -190,11 +209,18 @@ class TrainStep:
             pseudo = B("pseudo", (N, H, W), torch.uint8)
             call("wsl_mix_argmax", probs[0], probs[1], 0.0, 0.0, self.beta_dev, N, C, H, W, pseudo)   # beta from device memory
             loss = 0.5 * (stats[0][0] + stats[1][0])
+            # pDLoss weighs every pixel by the batch-summed ignore mask (F14); with pseudo labels nothing is ignored, so the weight
+            # is the batch size -- the GLOBAL one when the ranks reproduce the single-process arithmetic
+            nb = float(N * self.world_size) if self.global_batch else float(N)
             for h in heads:
                 sums = B(f"pd{h}", (13,))
-                call("wsl_pdice_fwd", probs[h], pseudo, None, float(N), N, C, H, W, sums, workspace("pdice", dev))
+                call("wsl_pdice_fwd", probs[h], pseudo, None, nb, N, C, H, W, sums, workspace("pdice", dev))
+                if self.global_batch:    # Dice is a ratio of batch-wide sums (losses.py:209-217): all-reduce {I, Y, Z} per class first
+                    ddp.allreduce_flat(sums[1:], self.pg)
+                    i_, y_, z_ = sums[1:5].double(), sums[5:9].double(), sums[9:13].double()
+                    sums[0:1].copy_((1.0 - (2.0 * i_ + 1e-5) / (z_ + y_ + 1e-5)).mean().float().reshape(1))
                 gp = B(f"gprobs{h}", (N, C, H, W))
-                call("wsl_pdice_bwd", probs[h], pseudo, None, float(N), sums, N, C, H, W, 0.25, 0, gp)
+                call("wsl_pdice_bwd", probs[h], pseudo, None, nb, sums, N, C, H, W, 0.25, 0, gp)
                 loss = loss + 0.25 * sums[0]
                 d, d16, dl[h] = self._dlogits(ex, slot, f"dl{h}", N, C, H, W)
                 call("wsl_head_bwd", probs[h], label, stats[h], None, 0.5 * S, gp, 1.0 * S, N, C, H, W, 4, d, d16, self.ex.dt)

@@ -199,6 +199,9 @@ class UNetExecutor:
         # (12 launches 0.50 + 0.11 ms -> 0.91 ms: 1184 blocks each pay the fp64 prologue), so it stays off; kept for the A/B record
         self.fold_finalize = os.environ.get("WSL4MIS_FOLDED_FINALIZE", "0") == "1"
         self.on_decoders_done = None     # optional callback(gflat) between the decoder and encoder halves of backward()
+        # Synchronised BatchNorm over data-parallel ranks: (world_size, process_group) or None.  Statistics of the
+        # GLOBAL batch: forward all-reduces {sum, sum of squares} per layer, backward {sum dz, sum dz*xhat}; 2C floats each.
+        self.sync_bn = None
         self.multi_stream = os.environ.get("WSL4MIS_SINGLE_STREAM", "0") != "1"
         self._sides = {}                 # named side streams
         self._side_stack = []            # names of the side streams we are currently issuing on (innermost last)
@@ -357,11 +360,10 @@ class UNetExecutor:
                 bn = L.bn
                 call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, sb, ctypes.addressof(self._stat_rows))
                 self._untag()
-                if self.fold_finalize and L.Cout <= 32:
+                if self.fold_finalize and L.Cout <= 32 and self.sync_bn is None:
                     rows = (sb, self._stat_rows.value)          # finalised inside the consumer (bn_fwd)
                 else:
-                    call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
-                         bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
+                    self._finalize_stats(L, sb, self._stat_rows.value, N * H * W, bn_out[0], bn_out[1])
                     rows = True
             else:
                 call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, None, None)
@@ -375,11 +377,10 @@ class UNetExecutor:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0, N, H, W, L.CoutP, cout_store, L.ks, self.dt,
                      sb, ctypes.addressof(self._stat_rows))
                 self._untag()                      # the finalize launch is not a convolution: keep it out of the conv roofline rows
-                if self.fold_finalize and L.Cout <= 32:
+                if self.fold_finalize and L.Cout <= 32 and self.sync_bn is None:
                     rows = (sb, self._stat_rows.value)          # finalised inside the consumer (bn_fwd)
                 else:
-                    call("wsl_bn_finalize", sb, self._stat_rows.value, N * H * W, L.Cout, bn.weight, bn.bias, bn.running_mean,
-                         bn.running_var, bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bn_out[0], bn_out[1])
+                    self._finalize_stats(L, sb, self._stat_rows.value, N * H * W, bn_out[0], bn_out[1])
                     rows = True
             else:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
@@ -459,9 +460,17 @@ class UNetExecutor:
         deferred = stats_done if isinstance(stats_done, tuple) else None
         if training and stats_done:
             pass                       # save / ss come from the convolution epilogue's partial rows (bn_finalize, or folded in below)
+        elif training and self.sync_bn is not None:
+            raw = self.buf(slot, tag + ".raw", (2 * C,), torch.float32)
+            call("wsl_bn_stats", y, self.dt, N * H * W, C, bn.weight, bn.bias, None, None, None, float(bn.momentum), float(bn.eps),
+                 save, ss, self._ws("bn"), raw)
+            from .. import ddp
+            ddp.allreduce_flat(raw, self.sync_bn[1])
+            call("wsl_bn_finalize", raw, 1, N * H * W * self.sync_bn[0], C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss)
         elif training:
             call("wsl_bn_stats", y, self.dt, N * H * W, C, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"))
+                 bn.num_batches_tracked, float(bn.momentum), float(bn.eps), save, ss, self._ws("bn"), None)
         else:
             call("wsl_bn_eval_prepare", bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), C, ss)
         p = L.drop_p if training else 0.0
@@ -487,9 +496,19 @@ class UNetExecutor:
         esz = 4 if self.dt == 1 else 2
         nsrc = (g0 is not None) + (g1 is not None) + 0.25 * (gpool is not None)
         self._tag_bytes("bn_bwd", L, N * H * W * C * esz * (2 * (1 + nsrc) + 1))      # reduce: y + sources; apply: again + dY
-        call("wsl_bn_bwd", y, self.dt, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
-             self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
-             self.gview(bn.bias), coef, dy, self._ws("bn"), 1 if self._accumulate else 0)
+        args = (y, self.dt, ss, save, g0, g1, cs1, gpool, pool_idx, mask, self._layer_seed(L),
+                self.seed_dev if mask is None and p > 0 else None, p, LRELU_SLOPE, N, H, W, C, self.gview(bn.weight),
+                self.gview(bn.bias), coef, dy, self._ws("bn"), 1 if self._accumulate else 0)
+        if self.sync_bn is not None:
+            # global-batch BatchNorm backward: local reduction -> all-reduce {sum dz, sum dz*xhat} -> constants from the global sums
+            from .. import ddp
+            raw = self.buf(slot, tag + ".rawb", (2 * C,), torch.float32)
+            call("wsl_bn_bwd_phase", *args, 1, raw)
+            ddp.allreduce_flat(raw, self.sync_bn[1])
+            call("wsl_bn_bwd_coef", raw, N * H * W * self.sync_bn[0], ss, save, C, coef)
+            call("wsl_bn_bwd_phase", *args, 2, None)
+        else:
+            call("wsl_bn_bwd", *args)
         self._untag()
 
     def grad_scale_for(self, N, H, W):
@@ -501,6 +520,20 @@ class UNetExecutor:
             return 1.0
         import math
         return float(2 ** (round(math.log2(N * H * W)) - 1))
+
+    def _finalize_stats(self, L, sb, nrows, P, save, ss):
+        """partial rows of a convolution epilogue -> {mean, invstd, scale, shift} (+ running statistics); with sync_bn the rows are
+        summed locally, all-reduced over the ranks and finalised against the global pixel count"""
+        bn = L.bn
+        if self.sync_bn is not None:
+            world, pg = self.sync_bn
+            C = L.Cout                        # BatchNorm layers have Cout == CoutP (multiples of 16): rows are [2][C]
+            raw = sb[: nrows * 2 * C].view(nrows, 2 * C).double().sum(0).float().contiguous()
+            from .. import ddp
+            ddp.allreduce_flat(raw, pg)
+            sb, nrows, P = raw, 1, P * world
+        call("wsl_bn_finalize", sb, nrows, P, L.Cout, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+             float(bn.momentum), float(bn.eps), save, ss)
 
     def _layer_seed(self, L):
         return (self.layers.index(L) + 1) * 0x9E3779B1
@@ -714,7 +747,7 @@ class UNetExecutor:
                 self.conv_wgrad(l2, [r["a1"]], dy2, N, h, w)
             da1 = B(tag + ".da1", (N, h, w, C))
             self.conv_dgrad(l2, 0, dy2, da1, N, h, w)
-            if r["src_f32"] and l1.Cin == 1 and l1.Cout == 16 and l1.ks == 3 and self.fuse_first_bwd:
+            if r["src_f32"] and l1.Cin == 1 and l1.Cout == 16 and l1.ks == 3 and self.fuse_first_bwd and self.sync_bn is None:
                 # first layer: BatchNorm backward + weight gradient in one pass, dY never stored (no data gradient towards the image)
                 bn = l1.bn
                 self.last_backward_param_ids.update(id(q) for q in (bn.weight, bn.bias, l1.conv.weight, l1.conv.bias))
