@@ -201,9 +201,25 @@ int wsl_split_f32(const float* src0, int C0, const float* src1, int C1, long lon
 int wsl_pack_split_weights(const float* w, int Cout, int Cin, int ksize, int CoutP, int CinP, int ci_begin, int ci_count,
                            void* f3, void* d3, cudaStream_t stream);
 int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scale, const void* wpk3, const float* bias, float* out,
-                      int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream);
+                      int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dilation, cudaStream_t stream);
 int wsl_wgrad_tc_split(const void* x_staged, int Cin, const float* x_inv_scale, const void* dy_staged, int CoutP,
-                       const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream);
+                       const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, int dilation,
+                       cudaStream_t stream);
+
+/* dilated 3x3 convolution of PNet2D's blocks (networks/pnet.py:25-28, dilation = padding = 1, 2, 4, 8, 16) on the per-tap tcgen05
+ * kernel: tap (dy, dx) is the TMA box at (y0 + dilation*dy, x0 + dilation*dx), out-of-bounds zero fill = the padding; with the flipped /
+ * transposed pack it is the data gradient; wsl_wgrad_tc_dil is the matching weight gradient.  LeakyReLU backward without BatchNorm for the
+ * 1x1 heads (pnet.py:54-59,75-81). */
+int wsl_conv_tc_dil(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+                    int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, int dilation,
+                    cudaStream_t stream);
+int wsl_wgrad_tc_dil(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                     int W, int CoutReal, int ksize, int dtype, int dilation, float* partial_ws, long long partial_floats,
+                     cudaStream_t stream);
+/* nn.LeakyReLU without a BatchNorm in front (pnet.py:60-61,94-95): out = y > 0 ? y : slope*y over n elements of any layout;
+ * wsl_lrelu_bwd: out = g * (y > 0 ? 1 : slope) with y the PRE-activation */
+int wsl_lrelu_fwd(const void* y, int dtype, float slope, long long n, void* out, cudaStream_t stream);
+int wsl_lrelu_bwd(const void* y, int dtype, const void* g, float slope, long long n, void* out, cudaStream_t stream);
 /* out[c] += sum over the P pixels of a channels-last bf16 tensor (bias gradient of convs not followed by BN). */
 int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, float* ws, cudaStream_t stream);
 /* ws (optional zero-initialised workspace): per-block rows + fixed-order sum by the last block -> bit-stable; NULL: atomicAdd */

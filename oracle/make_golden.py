@@ -341,6 +341,48 @@ def heads_golden(n=2, hw=32, pseed=31, mseed=6, cseed=8, nseed=77):
     print("unet_heads.npz:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if ":out" in k})
 
 
+def pnet_golden(n=2, hw=32, pseed=43, cseed=12):
+    """PNet2D(1, 4, 64, [1, 2, 4, 8, 16]) as net_factory builds it (net_factory.py:18-19): train-mode forward with fixed Dropout2d
+    masks, pCE loss, every parameter gradient; eval-mode forward."""
+    from networks.pnet import PNet2D
+    rs = np.random.RandomState(cseed)
+    keeps = [torch.from_numpy((rs.uniform(size=(n, c)) >= 0.3).astype(np.uint8)) for c in (128, 64)]
+    p = O.pnet_synth_params(1, 4, pseed)
+    m = PNet2D(1, 4, 64, [1, 2, 4, 8, 16])
+    assert list(m.state_dict().keys()) == list(p.keys())
+    m.load_state_dict(p)
+    image, label = O.synth_batch(n, hw, hw, seed=pseed + 1, frac=0.1)
+    out = {"n": n, "hw": hw, "pseed": pseed, "cseed": cseed, "image": image.numpy(), "label": label.numpy()}
+    m.eval()
+    with torch.no_grad():
+        out["eval"] = m(image).numpy()
+    m.train()
+
+    class _P(PatchedDropout):          # Dropout2d(0.3): keep / 0.7
+        def __enter__(self):
+            super().__enter__()
+            cq = list(self.chan)
+
+            def dropout2d(x, p=0.5, training=True, inplace=False):
+                if not training:
+                    return x
+                k = cq.pop(0)
+                return x * (k.to(x.dtype) * (1.0 / (1.0 - p)))[:, :, None, None]
+            F.dropout2d = dropout2d
+            torch.nn.functional.dropout2d = dropout2d
+            return self
+
+    with _P(None, keeps):
+        o = m(image)
+    loss = torch.nn.CrossEntropyLoss(ignore_index=4)(o, label.long())
+    loss.backward()
+    out["train"], out["loss"] = o.detach().numpy(), np.float64(loss.item())
+    keys, stats, small = grad_summary({k: v.grad for k, v in m.named_parameters()})
+    out["grad_keys"], out["grad_stats"] = np.array(keys), stats
+    np.savez_compressed(os.path.join(OUT, "pnet.npz"), **out)
+    print("pnet.npz: loss", float(out["loss"]), "train logits max", float(np.abs(out["train"]).max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -357,3 +399,4 @@ if __name__ == "__main__":
     net_golden(True)
     augment_golden()
     heads_golden()
+    pnet_golden()

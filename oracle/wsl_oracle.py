@@ -258,6 +258,93 @@ def unet_cct_3h_forward(p, x, training=True, masks=None, chan_keep=None, noises=
 
 
 # ----------------------------------------------------------------------------------------------
+# PNet2D (networks/pnet.py:87-122; net_factory builds PNet2D(in_chns, class_num, 64, [1, 2, 4, 8, 16]))
+# ----------------------------------------------------------------------------------------------
+PNET_RATIOS = (1, 2, 4, 8, 16)
+
+
+def pnet_param_shapes(in_chns: int, out_chns: int, nf: int = 64):
+    """Ordered {state_dict key: shape} of PNet2D: per PNetBlock conv1, conv2, in1, in2 (pnet.py:25-32), then catblock.conv1/2
+    (:49-52), out.conv1/2 (:68-71)."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(prefix, cin, cout, k):
+        shapes[f"{prefix}.weight"] = (cout, cin, k, k)
+        shapes[f"{prefix}.bias"] = (cout,)
+
+    def bn(prefix, c):
+        for nm, shp in (("weight", (c,)), ("bias", (c,)), ("running_mean", (c,)), ("running_var", (c,)), ("num_batches_tracked", ())):
+            shapes[f"{prefix}.{nm}"] = shp
+
+    for b in range(1, 6):
+        conv(f"block{b}.conv1", in_chns if b == 1 else nf, nf, 3)
+        conv(f"block{b}.conv2", nf, nf, 3)
+        bn(f"block{b}.in1", nf)
+        bn(f"block{b}.in2", nf)
+    conv("catblock.conv1", 5 * nf, 5 * nf, 1)
+    conv("catblock.conv2", 5 * nf, 2 * nf, 1)
+    conv("out.conv1", 2 * nf, nf, 1)
+    conv("out.conv2", nf, out_chns, 1)
+    return shapes
+
+
+def pnet_synth_params(in_chns: int, out_chns: int, seed: int, nf: int = 64) -> Dict[str, torch.Tensor]:
+    """numpy-stream parameters for PNet2D (same recipe as synth_params)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for k, shp in pnet_param_shapes(in_chns, out_chns, nf).items():
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros((), dtype=torch.long)
+            continue
+        if k.endswith("running_var"):
+            a = rs.uniform(0.5, 1.5, size=shp)
+        elif k.endswith("running_mean"):
+            a = rs.uniform(-0.2, 0.2, size=shp)
+        elif len(shp) == 4:
+            b = math.sqrt(3.0 / (shp[1] * shp[2] * shp[3])) * 1.4
+            a = rs.uniform(-b, b, size=shp)
+        elif ".in1." in k or ".in2." in k:
+            a = rs.uniform(0.6, 1.4, size=shp) if k.endswith("weight") else rs.uniform(-0.3, 0.3, size=shp)
+        else:
+            a = rs.uniform(-0.1, 0.1, size=shp)
+        out[k] = torch.from_numpy(np.ascontiguousarray(a)).float()
+    return out
+
+
+def pnet2d_forward(p, x, training=True, chan_keep=None, new_stats=None):
+    """PNet2D.forward (pnet.py:112-122): five PNetBlocks (:34-41: dilated conv3x3 -> BN -> LeakyReLU, twice; dilation = padding =
+    ratio), concat of the five block outputs, ConcatBlock (:54-59: conv1x1 -> LeakyReLU -> conv1x1 -> LeakyReLU), OutPutBlock
+    (:75-81: Dropout2d(0.3) -> conv1x1 -> LeakyReLU -> Dropout2d(0.3) -> conv1x1).  chan_keep: the two [N, C] keep masks of the
+    Dropout2d layers (None -> torch RNG, like the reference)."""
+    feats = []
+    for b, r in enumerate(PNET_RATIOS, 1):
+        for cv, bnn in (("conv1", "in1"), ("conv2", "in2")):
+            x = _q(F.conv2d(x, _qw(p[f"block{b}.{cv}.weight"], x), p[f"block{b}.{cv}.bias"], padding=r, dilation=r))
+            rm, rv = p[f"block{b}.{bnn}.running_mean"].clone(), p[f"block{b}.{bnn}.running_var"].clone()
+            x = F.batch_norm(x, rm, rv, p[f"block{b}.{bnn}.weight"], p[f"block{b}.{bnn}.bias"], training, BN_MOM, BN_EPS)
+            if new_stats is not None and training:
+                new_stats[f"block{b}.{bnn}.running_mean"], new_stats[f"block{b}.{bnn}.running_var"] = rm, rv
+            x = _q(F.leaky_relu(x, LRELU))
+        feats.append(x)
+    x = torch.cat(feats, 1)
+    x = _q(F.leaky_relu(_q(F.conv2d(x, _qw(p["catblock.conv1.weight"], x), p["catblock.conv1.bias"])), LRELU))
+    x = _q(F.leaky_relu(_q(F.conv2d(x, _qw(p["catblock.conv2.weight"], x), p["catblock.conv2.bias"])), LRELU))
+
+    def drop2d(t, keep):
+        if not training:
+            return t
+        if keep is None:
+            return F.dropout2d(t, 0.3, True)
+        return _q(t * (keep.to(t.dtype) * (1.0 / 0.7))[:, :, None, None])
+
+    x = drop2d(x, None if chan_keep is None else chan_keep[0])
+    x = _q(F.leaky_relu(_q(F.conv2d(x, _qw(p["out.conv1.weight"], x), p["out.conv1.bias"])), LRELU))
+    x = drop2d(x, None if chan_keep is None else chan_keep[1])
+    return F.conv2d(x, _qw(p["out.conv2.weight"], x), p["out.conv2.bias"])
+
+
+# ----------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------
 def pce_loss(logits, label, ignore_index=4):

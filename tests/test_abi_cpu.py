@@ -132,3 +132,12 @@ def test_unet_cct_3h_and_urds_state_dict_layouts():
     want = O.unet_param_shapes(1, 4, ("main_decoder", "aux_decoder1", "aux_decoder2"))
     assert list(sd.keys()) == list(want.keys()) and all(tuple(sd[k].shape) == tuple(v) for k, v in want.items())
     assert list(Decoder_URDS(_params(1, 4)).state_dict().keys()) == list(Decoder_DS(_params(1, 4)).state_dict().keys())
+
+
+def test_pnet_state_dict_layout():
+    """PNet2D registers block{1..5}.{conv1,conv2,in1,in2}, catblock.conv{1,2}, out.conv{1,2} like networks/pnet.py:16-110"""
+    import wsl_oracle as O
+    from wsl4mis_b200.networks.pnet import PNet2D
+    sd = PNet2D(1, 4, 64, [1, 2, 4, 8, 16]).state_dict()
+    want = O.pnet_param_shapes(1, 4)
+    assert list(sd.keys()) == list(want.keys()) and all(tuple(sd[k].shape) == tuple(v) for k, v in want.items())

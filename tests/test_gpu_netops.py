@@ -273,7 +273,7 @@ def test_split_convolutions(case):
     # forward
     fp32_nchw = Cout == 4
     out = torch.zeros((N, Cout, H, W) if fp32_nchw else (N, H, W, Cout), device=DEV)
-    call("wsl_conv_tc_split", sx, Cin, kx[1:], f3, bias, out, 1 if fp32_nchw else 2, N, H, W, CoutP, Cout, ks)
+    call("wsl_conv_tc_split", sx, Cin, kx[1:], f3, bias, out, 1 if fp32_nchw else 2, N, H, W, CoutP, Cout, ks, 1)
     torch.cuda.synchronize()
     ref = F.conv2d(x.double(), w.double(), b.double(), padding=ks // 2).float()
     got = out.cpu() if fp32_nchw else nchw(out.cpu())
@@ -287,14 +287,14 @@ def test_split_convolutions(case):
     beg = 0
     for i, c in enumerate([C0, C1] if C1 else [C0]):
         o = torch.zeros((N, H, W, c), device=DEV)
-        call("wsl_conv_tc_split", sg, CoutP, kg[1:], d3[i], None, o, 2, N, H, W, c, c, ks)
+        call("wsl_conv_tc_split", sg, CoutP, kg[1:], d3[i], None, o, 2, N, H, W, c, c, ks, 1)
         torch.cuda.synchronize()
         r = refd[:, beg:beg + c]
         assert (nchw(o.cpu()) - r).abs().max().item() < 2e-5 * r.abs().max().item()
         beg += c
     # weight gradient
     dw = torch.zeros(Cout, Cin, ks, ks, device=DEV)
-    call("wsl_wgrad_tc_split", sx, Cin, kx[1:], sg, CoutP, kg[1:], dw, N, H, W, Cout, ks)
+    call("wsl_wgrad_tc_split", sx, Cin, kx[1:], sg, CoutP, kg[1:], dw, N, H, W, Cout, ks, 1)
     torch.cuda.synchronize()
     wz = torch.zeros(Cout, Cin, ks, ks, dtype=torch.double, requires_grad=True)
     (gw,) = torch.autograd.grad(F.conv2d(x.double(), wz, None, padding=ks // 2), wz, dy[:, :Cout].double())
@@ -531,3 +531,33 @@ def test_chan_dropout():
     call("wsl_chan_scale", nhwc(a).to(DEV), 0, cs, N, H, W, C, d)
     torch.cuda.synchronize()
     assert torch.equal(nchw(d.cpu()), a * cs.cpu().view(N, C, 1, 1))
+
+
+@pytest.mark.parametrize("dil", [2, 4, 16])
+@pytest.mark.parametrize("dt", [0, 2])
+def test_dilated_convolution(dil, dt):
+    """PNet2D's dilated 3x3 blocks (networks/pnet.py:25-28) on the per-tap tcgen05 kernel: forward, data gradient and weight gradient
+    against fp64 F.conv2d(dilation=d, padding=d) on the same 16-bit inputs."""
+    N, H, W, C, Cout, ks = 2, 32, 32, 64, 64, 3
+    g = torch.Generator().manual_seed(100 + dil)
+    x = r16(torch.randn(N, C, H, W, generator=g), dt)
+    w = torch.randn(Cout, C, ks, ks, generator=g) / np.sqrt(C * 9)
+    b = torch.randn(Cout, generator=g) * 0.1
+    dy = r16(torch.randn(N, Cout, H, W, generator=g), dt)
+    pk = _pack(w.to(DEV), [C], dt)
+    xd, dyd = nhwc(x, T16[dt]).to(DEV), nhwc(dy, T16[dt]).to(DEV)
+    out = torch.zeros((N, H, W, Cout), device=DEV, dtype=T16[dt])
+    call("wsl_conv_tc_dil", xd, C, None, 0, pk["bf"], b.to(DEV), out, 0, N, H, W, Cout, Cout, ks, dt, dil)
+    dx = torch.zeros((N, H, W, C), device=DEV, dtype=T16[dt])
+    call("wsl_conv_tc_dil", dyd, Cout, None, 0, pk["bd"][0], None, dx, 0, N, H, W, C, C, ks, dt, dil)
+    dw = torch.zeros(Cout, C, ks, ks, device=DEV)
+    pw = torch.empty(8 * 1024 * 1024, device=DEV)
+    call("wsl_wgrad_tc_dil", xd, C, None, 0, dyd, Cout, dw, N, H, W, Cout, ks, dt, dil, pw, pw.numel())
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(True)
+    wr = r16(w, dt).double().requires_grad_(True)
+    ref = F.conv2d(xr, wr, b.double(), padding=dil, dilation=dil)
+    gx, gw = torch.autograd.grad(ref, [xr, wr], dy.double())
+    assert (nchw(out.float().cpu()) - ref.detach().float()).abs().max().item() < 2 * ULP[dt] * ref.abs().max().item()
+    assert (nchw(dx.float().cpu()) - gx.float()).abs().max().item() < 2 * ULP[dt] * gx.abs().max().item()
+    assert rel_l2(dw.cpu(), gw.float()) < 1e-4

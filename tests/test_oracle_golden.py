@@ -168,3 +168,26 @@ def test_other_heads_match_reference(golden_dir, which):
         assert abs(gr.double().abs().sum().item() - asum) < 2e-3 * asum + 1e-6, k
     unused = {str(k).split(".")[0] for k in g[f"{which}:no_grad_keys"]}
     assert unused == ({"decoder"} if which == "ds" else {"aux_decoder2"})      # out_conv_dp4 / the never-run third decoder
+
+
+def test_pnet2d_matches_reference(golden_dir):
+    """PNet2D restatement (dilated 3x3 blocks, concat, 1x1 heads, Dropout2d) against the fixture generated from the unmodified
+    networks/pnet.py: eval and train logits, pCE loss, every parameter gradient."""
+    g = _load(golden_dir, "pnet.npz")
+    n = int(g["n"])
+    p = O.pnet_synth_params(1, 4, int(g["pseed"]))
+    image, label = torch.from_numpy(g["image"]), torch.from_numpy(g["label"])
+    rs = np.random.RandomState(int(g["cseed"]))
+    keeps = [torch.from_numpy((rs.uniform(size=(n, c)) >= 0.3).astype(np.uint8)) for c in (128, 64)]
+    with torch.no_grad():
+        ev = O.pnet2d_forward(p, image, False)
+    assert (ev - torch.from_numpy(g["eval"])).abs().max().item() < 5e-5 * max(1.0, np.abs(g["eval"]).max())
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+    o = O.pnet2d_forward(leaves, image, True, keeps)
+    assert (o.detach() - torch.from_numpy(g["train"])).abs().max().item() < 5e-5 * max(1.0, np.abs(g["train"]).max())
+    loss = O.pce_loss(o, label)
+    assert abs(loss.item() - float(g["loss"])) < 2e-5 * abs(float(g["loss"]))
+    keys = [str(k) for k in g["grad_keys"]]
+    grads = torch.autograd.grad(loss, [leaves[k] for k in keys])
+    for k, gr, (_, asum, l2) in zip(keys, grads, g["grad_stats"]):
+        assert abs(gr.double().norm().item() - l2) < 2e-3 * l2 + 1e-7, k

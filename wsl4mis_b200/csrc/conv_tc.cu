@@ -179,6 +179,7 @@ struct ConvTcParams {
   int tiles_x, tiles_y;
   int out_mode;       // 0: 16-bit NHWC, 1: fp32 NCHW, 2: fp32 NHWC
   int dt;             // 16-bit operand / storage type: 0 bf16, 2 fp16
+  int dil;            // dilation (PNet2D's blocks, networks/pnet.py:25-28): tap (dy, dx) reads pixel (y + dil*dy, x + dil*dx)
   const float* bias;
   const float* out_scale;   // optional device scalar multiplied into the accumulator before the bias (split mode: 2^-k of the staged operand)
   void* out;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (lane == 0) {
       int it = 0;
       for (int t = 0; t < p.taps; ++t) {
-        const int dy = t / p.ks - pad, dx = t % p.ks - pad;
+        const int dy = (t / p.ks - pad) * p.dil, dx = (t % p.ks - pad) * p.dil;
         for (int kb = 0; kb < kb0 + kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -741,6 +742,7 @@ struct WgradTcParams {
   const float* scale_b;
   float* dw;
   float* partials;       // optional [gridDim.y][gridDim.x][TG*CWB][128]: per-CTA partial tiles for the fixed-order finalize
+  int dil;               // dilation of the convolution
 };
 
 template <int CWA, int NA, int CWB, int TG, int STAGES>
@@ -812,7 +814,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
 #pragma unroll
         for (int tl = 0; tl < TG; ++tl) {
           const int t = tg * TG + tl;
-          const int dy = t / p.ks - pad, dx = t % p.ks - pad;
+          const int dy = (t / p.ks - pad) * p.dil, dx = (t % p.ks - pad) * p.dil;
           tma_load_4d(mx, &full_bar[s], b_dst + tl * S::B_BOX, cb0, x0 + dx, y0 + dy, n);
         }
       }
@@ -1354,7 +1356,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   float sum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = 0.f;
-  for (long long q = (long long)blockIdx.x * rows + r; q < P; q += (long long)gridDim.x * rows) {
+  for (long long q = (long long)blockIdx.x * rows + r; r < rows && q < P; q += (long long)gridDim.x * rows) {   // threads beyond rows*cg idle
     float v[8];
     if constexpr (sizeof(T) == 2) {
       unpack8_dt(*reinterpret_cast<const uint4*>(x + q * C + g * 8), v, HALF ? 2 : 0);
@@ -1744,9 +1746,11 @@ int launch_conv_row(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
 
 WSL_API int wsl_tc_available(void) { return get_encode() != nullptr ? 1 : 0; }
 
-WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
-                        int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, cudaStream_t stream) {
+static int conv_tc_impl(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+                        int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, int dilation,
+                        cudaStream_t stream) {
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc: ksize must be 1 or 3");
+  WSL_REQUIRE(dilation >= 1 && dilation <= 64, "wsl_conv_tc: dilation must be in 1..64 (got %d)", dilation);
   WSL_REQUIRE(dtype == 0 || dtype == 2, "wsl_conv_tc: dtype must be 0 (bf16) or 2 (fp16)");
   WSL_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "wsl_conv_tc: source channels must be multiples of 16 (got %d,%d)", C0, C1);
   WSL_REQUIRE(CoutP % 16 == 0, "wsl_conv_tc: CoutP must be a multiple of 16");
@@ -1755,6 +1759,7 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
   int kblk = 64;
   while (kblk > 16 && (C0 % kblk != 0 || (C1 > 0 && C1 % kblk != 0))) kblk >>= 1;
   int nt = CoutP >= 128 ? 128 : CoutP;
+  while (nt > 16 && CoutP % nt != 0) nt >>= 1;          // e.g. CoutP = 320 (PNet2D's concat block): five tiles of 64
   WSL_REQUIRE(CoutP % nt == 0 && (nt == 16 || nt == 32 || nt == 64 || nt == 128), "wsl_conv_tc: unsupported CoutP %d", CoutP);
   const int CinP = C0 + C1, T = ksize * ksize;
   CUtensorMap a0, a1, b;
@@ -1780,7 +1785,7 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
   }
   ConvTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutStore = CoutStore; p.taps = T; p.ks = ksize;
-  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.dt = dtype; p.bias = bias; p.out_scale = nullptr; p.out = out;
+  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.dt = dtype; p.dil = dilation; p.bias = bias; p.out_scale = nullptr; p.out = out;
   switch (kblk) {
     case 64: return dispatch_nt<64>(a0, a1, b, p, nt, stream);
     case 32: return dispatch_nt<32>(a0, a1, b, p, nt, stream);
@@ -1788,10 +1793,23 @@ WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, cons
   }
 }
 
+WSL_API int wsl_conv_tc(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+                        int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, cudaStream_t stream) {
+  return conv_tc_impl(src0, C0, src1, C1, wpk_bf16, bias, out, out_mode, N, H, W, CoutP, CoutStore, ksize, dtype, 1, stream);
+}
+
+// dilated 3x3 convolution (PNet2D, networks/pnet.py:25-28): same kernel, tap coordinates scaled by the dilation (TMA zero fill = padding)
+WSL_API int wsl_conv_tc_dil(const void* src0, int C0, const void* src1, int C1, const void* wpk_bf16, const float* bias, void* out,
+                            int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dtype, int dilation,
+                            cudaStream_t stream) {
+  return conv_tc_impl(src0, C0, src1, C1, wpk_bf16, bias, out, out_mode, N, H, W, CoutP, CoutStore, ksize, dtype, dilation, stream);
+}
+
 // pitch_x / pitch_dy > 0: the operands are channel-range views of wider channels-last tensors (fp16 hi/lo split planes)
 static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
                          int W, int CoutReal, int ksize, int dtype, int pitch_x, int pitch_dy, const float* scale_a,
-                         const float* scale_b, cudaStream_t stream, float* partial_ws = nullptr, long long partial_floats = 0) {
+                         const float* scale_b, cudaStream_t stream, float* partial_ws = nullptr, long long partial_floats = 0,
+                         int dilation = 1) {
   g_wgrad1_ws = partial_ws;
   g_wgrad1_ws_floats = partial_floats;
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_wgrad_tc: ksize must be 1 or 3");
@@ -1801,11 +1819,11 @@ static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, con
   WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_wgrad_tc: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
   const int cwa = CoutP >= 64 ? 64 : CoutP;       // 16 / 32 / 64
   WSL_REQUIRE(cwa == 16 || cwa == 32 || cwa == 64, "wsl_wgrad_tc: unsupported CoutP %d", CoutP);
-  WSL_REQUIRE(CoutP < 128 || CoutP % 128 == 0, "wsl_wgrad_tc: CoutP >= 128 must be a multiple of 128");
+  WSL_REQUIRE(CoutP < 128 || CoutP % 64 == 0, "wsl_wgrad_tc: CoutP >= 128 must be a multiple of 64");   // a half-filled last tile reads zeros (TMA)
   int cwb = 64;
   while (cwb > 16 && (C0 % cwb != 0 || (C1 > 0 && C1 % cwb != 0))) cwb >>= 1;
   const int na = CoutP >= 128 ? 2 : 1;
-  const int m_tiles = CoutP >= 128 ? CoutP / 128 : 1;
+  const int m_tiles = CoutP >= 128 ? (CoutP + 127) / 128 : 1;
   CUtensorMap mdy, mx0, mx1;
   {
     long long d[4] = {CoutP, W, H, N};
@@ -1830,7 +1848,7 @@ static int wgrad_tc_impl(const void* src0, int C0, const void* src1, int C1, con
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = ksize * ksize; p.ks = ksize;
   p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dt = dtype; p.scale_a = scale_a; p.scale_b = scale_b; p.dw = dw; p.partials = nullptr;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = ksize == 3 ? 3 : 1; p.dt = dtype; p.scale_a = scale_a; p.scale_b = scale_b; p.dw = dw; p.partials = nullptr; p.dil = dilation;
   if (cwa == 64 && na == 2) return wgrad_dispatch_b<64, 2>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 64) return wgrad_dispatch_b<64, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
   if (cwa == 32) return wgrad_dispatch_b<32, 1>(cwb, mdy, mx0, mx1, p, m_tiles, stream);
@@ -1843,6 +1861,14 @@ WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, con
                        partial_floats);
 }
 
+WSL_API int wsl_wgrad_tc_dil(const void* src0, int C0, const void* src1, int C1, const void* dy, int CoutP, float* dw, int N, int H,
+                             int W, int CoutReal, int ksize, int dtype, int dilation, float* partial_ws, long long partial_floats,
+                             cudaStream_t stream) {
+  WSL_REQUIRE(dilation >= 1 && dilation <= 64, "wsl_wgrad_tc_dil: dilation must be in 1..64 (got %d)", dilation);
+  return wgrad_tc_impl(src0, C0, src1, C1, dy, CoutP, dw, N, H, W, CoutReal, ksize, dtype, 0, 0, nullptr, nullptr, stream, partial_ws,
+                       partial_floats, dilation);
+}
+
 // ---- fp16 hi/lo split ("fp16x3") tensor-core parity mode ------------------------------------------------------------
 // An fp32 value v is carried as hi = fp16(v), lo = fp16(v - hi) (22 significant bits); a product a*b is evaluated as
 // a_hi*b_hi + a_lo*b_hi + a_hi*b_lo on kind::f16 with fp32 accumulation (the dropped lo*lo term is ~2^-22 relative).
@@ -1852,7 +1878,8 @@ WSL_API int wsl_wgrad_tc(const void* src0, int C0, const void* src1, int C1, con
 //   weight gradient: three accumulating launches (dy_hi,x_hi), (dy_hi,x_lo), (dy_lo,x_hi).
 // out_mode 2: fp32 NHWC [P][CoutStore]; 1: fp32 NCHW.
 WSL_API int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scale, const void* wpk3, const float* bias, float* out,
-                              int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, cudaStream_t stream) {
+                              int out_mode, int N, int H, int W, int CoutP, int CoutStore, int ksize, int dilation, cudaStream_t stream) {
+  WSL_REQUIRE(dilation >= 1 && dilation <= 64, "wsl_conv_tc_split: dilation must be in 1..64 (got %d)", dilation);
   WSL_REQUIRE(ksize == 3 || ksize == 1, "wsl_conv_tc_split: ksize must be 1 or 3");
   WSL_REQUIRE(Cin % 16 == 0 && Cin > 0 && CoutP % 16 == 0, "wsl_conv_tc_split: channel counts must be multiples of 16 (got %d,%d)", Cin, CoutP);
   WSL_REQUIRE(W % TILE_W == 0 && H % TILE_H == 0, "wsl_conv_tc_split: H,W must be multiples of the 8x16 pixel tile (got %dx%d)", H, W);
@@ -1860,6 +1887,7 @@ WSL_API int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scal
   int kblk = 64;
   while (kblk > 16 && Cin % kblk != 0) kblk >>= 1;
   int nt = CoutP >= 128 ? 128 : CoutP;
+  while (nt > 16 && CoutP % nt != 0) nt >>= 1;
   WSL_REQUIRE(CoutP % nt == 0 && (nt == 16 || nt == 32 || nt == 64 || nt == 128), "wsl_conv_tc_split: unsupported CoutP %d", CoutP);
   const int T = ksize * ksize;
   CUtensorMap a0, a1, b;
@@ -1883,7 +1911,7 @@ WSL_API int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scal
   }
   ConvTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = 2 * Cin; p.C1 = Cin; p.CoutP = CoutP; p.CoutStore = CoutStore; p.taps = T; p.ks = ksize;
-  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.dt = 2; p.bias = bias; p.out_scale = inv_scale; p.out = out;
+  p.tiles_x = W / TILE_W; p.tiles_y = H / TILE_H; p.out_mode = out_mode; p.dt = 2; p.dil = dilation; p.bias = bias; p.out_scale = inv_scale; p.out = out;
   switch (kblk) {
     case 64: return dispatch_nt<64>(a0, a1, b, p, nt, stream);
     case 32: return dispatch_nt<32>(a0, a1, b, p, nt, stream);
@@ -1892,19 +1920,20 @@ WSL_API int wsl_conv_tc_split(const void* staged, int Cin, const float* inv_scal
 }
 
 WSL_API int wsl_wgrad_tc_split(const void* x_staged, int Cin, const float* x_inv_scale, const void* dy_staged, int CoutP,
-                               const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, cudaStream_t stream) {
+                               const float* dy_inv_scale, float* dw, int N, int H, int W, int CoutReal, int ksize, int dilation,
+                               cudaStream_t stream) {
   WSL_REQUIRE(Cin % 16 == 0 && Cin > 0, "wsl_wgrad_tc_split: Cin must be a multiple of 16 (got %d)", Cin);
   const __half* x = reinterpret_cast<const __half*>(x_staged);
   const __half* g = reinterpret_cast<const __half*>(dy_staged);
-  int rc = wgrad_tc_impl(x, Cin, nullptr, 0, g, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
+  int rc = wgrad_tc_impl(x, Cin, nullptr, 0, g, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream, nullptr, 0, dilation);
   if (rc) return rc;
-  rc = wgrad_tc_impl(x + Cin, Cin, nullptr, 0, g, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
+  rc = wgrad_tc_impl(x + Cin, Cin, nullptr, 0, g, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream, nullptr, 0, dilation);
   if (rc) return rc;
-  return wgrad_tc_impl(x, Cin, nullptr, 0, g + CoutP, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream);
+  return wgrad_tc_impl(x, Cin, nullptr, 0, g + CoutP, CoutP, dw, N, H, W, CoutReal, ksize, 2, 2 * Cin, 2 * CoutP, dy_inv_scale, x_inv_scale, stream, nullptr, 0, dilation);
 }
 
 WSL_API int wsl_channel_sum(const void* x, int dtype, long long P, int C, int Creal, float* out, float* ws, cudaStream_t stream) {
-  WSL_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && Creal <= C, "wsl_channel_sum: unsupported channel count %d", C);
+  WSL_REQUIRE(C % 8 == 0 && C / 8 <= 256 && Creal <= C, "wsl_channel_sum: unsupported channel count %d", C);
   const int rows = 256 / (C / 8);
   long long b = (P + rows * 16 - 1) / (rows * 16);
   if (b > 148 * 2) b = 148 * 2;
@@ -2062,7 +2091,7 @@ WSL_API int wsl_wgrad_tc2(const void* src0, int C0, const void* src1, int C1, co
   WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.CoutP = CoutP; p.CoutReal = CoutReal; p.taps = 9; p.ks = 3;
   p.tiles_x = W / 8; p.tiles_y = H / 16; p.nchunks = N * p.tiles_x * p.tiles_y;
-  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dt = dtype; p.scale_a = nullptr; p.scale_b = nullptr; p.dw = dw; p.partials = nullptr;
+  p.n_tiles0 = C0 / cwb; p.n_tiles1 = C1 / cwb; p.tap_groups = 1; p.dt = dtype; p.scale_a = nullptr; p.scale_b = nullptr; p.dw = dw; p.partials = nullptr; p.dil = 1;
   if (cwb == 32) {
     if (cwa == 64 && na == 2) return launch_wgrad2<64, 2, 32>(mdy, mx0, mx1, p, m_tiles, stream);
     if (cwa == 64) return launch_wgrad2<64, 1, 32>(mdy, mx0, mx1, p, m_tiles, stream);

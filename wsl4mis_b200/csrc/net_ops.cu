@@ -1204,6 +1204,32 @@ __global__ void __launch_bounds__(TPB) feat_noise_kernel(const T* __restrict__ f
   }
 }
 
+// LeakyReLU backward without BatchNorm (PNet2D's 1x1 heads, networks/pnet.py:54-59,75-81): out = g * (y > 0 ? 1 : slope), y = the stored
+// pre-activation
+template <typename T>
+__global__ void __launch_bounds__(TPB) lrelu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ g, float slope, long long total_vec,
+                                                        T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total_vec; i += (long long)gridDim.x * TPB) {
+    float yv[8], gv[8];
+    ld8(y + i * 8, yv);
+    ld8(g + i * 8, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] *= (yv[j] > 0.f ? 1.f : slope);
+    st8(out + i * 8, gv);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) lrelu_fwd_kernel(const T* __restrict__ y, float slope, long long total_vec, T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < total_vec; i += (long long)gridDim.x * TPB) {
+    float v[8];
+    ld8(y + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+    st8(out + i * 8, v);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TPB) chan_scale_kernel(const T* __restrict__ a, const float* __restrict__ cs,
                                                          long long HW, int C, long long total_vec, T* __restrict__ d) {
@@ -1661,6 +1687,18 @@ WSL_API int wsl_feat_noise_bwd(const void* g, int dtype, const float* z, int N, 
   WSL_DISPATCH_T(dtype, feat_noise_kernel<T><<<grid_for(N * hwc / 8), TPB, 0, stream>>>((const T*)g, z, N * hwc / 8, hwc / 8, (const T*)acc,
                                                                                     (T*)(acc ? acc : out)));
   return wsl_check_launch("feat_noise_bwd");
+}
+
+WSL_API int wsl_lrelu_fwd(const void* y, int dtype, float slope, long long n, void* out, cudaStream_t stream) {
+  WSL_REQUIRE(n % 8 == 0, "wsl_lrelu_fwd: element count must be a multiple of 8");
+  WSL_DISPATCH_T(dtype, lrelu_fwd_kernel<T><<<grid_for(n / 8), TPB, 0, stream>>>((const T*)y, slope, n / 8, (T*)out));
+  return wsl_check_launch("lrelu_fwd");
+}
+
+WSL_API int wsl_lrelu_bwd(const void* y, int dtype, const void* g, float slope, long long n, void* out, cudaStream_t stream) {
+  WSL_REQUIRE(n % 8 == 0, "wsl_lrelu_bwd: element count must be a multiple of 8");
+  WSL_DISPATCH_T(dtype, lrelu_bwd_kernel<T><<<grid_for(n / 8), TPB, 0, stream>>>((const T*)y, (const T*)g, slope, n / 8, (T*)out));
+  return wsl_check_launch("lrelu_bwd");
 }
 
 WSL_API int wsl_chan_scale(const void* a, int dtype, const float* cs, int N, int H, int W, int C, void* d, cudaStream_t stream) {

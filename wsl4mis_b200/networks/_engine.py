@@ -68,6 +68,7 @@ class ConvLayer:
     def __init__(self, name, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], drop_p: float, src_channels: Sequence[int]):
         self.name, self.conv, self.bn, self.drop_p = name, conv, bn, float(drop_p)
         self.ks = conv.kernel_size[0]
+        self.dil = conv.dilation[0]          # PNet2D's blocks: 1, 2, 4, 8, 16 (networks/pnet.py:25-28); 1 everywhere in the U-Nets
         self.srcC = list(src_channels)
         self.Cin, self.Cout = conv.in_channels, conv.out_channels
         assert sum(self.srcC) == self.Cin
@@ -175,6 +176,11 @@ class UNetExecutor:
             self.ds_heads.append(heads)
             built[didx] = (self.dec[-1], heads)
         self.n_class = decoders[0].out_conv.out_channels
+        self._init_runtime(model)
+
+    def _init_runtime(self, model):
+        """state shared by every planned network (the U-Net family here, PNet2D in _pnet_engine.py): parameter bookkeeping, buffers,
+        side streams, A/B switches"""
         self.params = [p for p in model.parameters()]
         used = set()
         for L in self.layers:
@@ -337,16 +343,17 @@ class UNetExecutor:
         call("wsl_split_f32", srcs[0], chans[0], srcs[1] if len(srcs) > 1 else None, chans[1] if len(chans) > 1 else 0, P, t[0], t[1])
         return t[0], t[1][1:]
 
-    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, bn_out=None):
+    def conv_fwd(self, L: ConvLayer, srcs, out, out_mode, N, H, W, cout_store, src_f32=False, bn_out=None, srcC_override=None):
         """bn_out = (save, ss) buffers: when the convolution runs on the persistent tcgen05 kernel the complete
         training-mode BatchNorm statistics of its output are produced by the kernel itself (partial rows in the epilogue,
         finalised by the last CTA).  Returns True when that happened."""
         pk = L.packs(self.dev)
+        srcC = list(srcC_override) if srcC_override is not None else L.srcC     # (a materialised concat enters as ONE source)
         rows = False
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
-        c0 = L.srcC[0]
-        c1 = L.srcC[1] if len(L.srcC) > 1 else 0
+        c0 = srcC[0]
+        c1 = srcC[1] if len(srcC) > 1 else 0
         self._tag("fwd", L, N, H, W, L.Cin, L.Cout)
         f32 = 1 if (src_f32 or self.dt == 1) else self.dt  # dtype code of the sources
         if out_mode == 0 and self.dt != 0:
@@ -367,10 +374,14 @@ class UNetExecutor:
                     rows = True
             else:
                 call("wsl_conv_first", s0, L.conv.weight, L.conv.bias, out, self.dt, N, H, W, L.Cout, None, None)
-        elif not src_f32 and self._split_ok(L.srcC, H, W):
-            st, inv = self._staged("x", srcs, L.srcC, N * H * W)
-            call("wsl_conv_tc_split", st, L.Cin, inv, pk["f3"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks)
-        elif not src_f32 and self._tc2_ok(L.srcC, H, W):
+        elif not src_f32 and self._split_ok(srcC, H, W):
+            st, inv = self._staged("x", srcs, srcC, N * H * W)
+            call("wsl_conv_tc_split", st, L.Cin, inv, pk["f3"], pk["bias"], out, out_mode, N, H, W, L.CoutP, cout_store, L.ks, L.dil)
+        elif not src_f32 and L.dil != 1:
+            assert self._tc_ok(srcC, H, W), "dilated convolutions run on the per-tap tcgen05 kernel (W % 16 == 0, H % 8 == 0, 16-bit or fp16x3 mode)"
+            call("wsl_conv_tc_dil", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
+                 cout_store, L.ks, self.dt, L.dil)
+        elif not src_f32 and self._tc2_ok(srcC, H, W):
             if bn_out is not None and self.fuse_bn_stats and out_mode in (0, 3):
                 sb = self._stat_scratch()
                 bn = L.bn
@@ -385,7 +396,7 @@ class UNetExecutor:
             else:
                 call("wsl_conv_tc2", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
                      cout_store, L.ks, self.dt, None, None)
-        elif not src_f32 and self._tc_ok(L.srcC, H, W):
+        elif not src_f32 and self._tc_ok(srcC, H, W):
             call("wsl_conv_tc", s0, c0, s1, c1, pk["bf"], pk["bias"], out, 0 if out_mode == 3 else out_mode, N, H, W, L.CoutP,
                  cout_store, L.ks, self.dt)
         else:
@@ -401,7 +412,10 @@ class UNetExecutor:
         self._tag("dgrad", L, N, H, W, ci, L.Cout)
         if self._split_ok([L.CoutP], H, W):
             st, inv = self._staged("dy", [dy], [L.CoutP], N * H * W)
-            call("wsl_conv_tc_split", st, L.CoutP, inv, pk["d3"][i], None, out, 2, N, H, W, sp, ci, L.ks)
+            call("wsl_conv_tc_split", st, L.CoutP, inv, pk["d3"][i], None, out, 2, N, H, W, sp, ci, L.ks, L.dil)
+        elif L.dil != 1:
+            assert self._tc_ok([L.CoutP], H, W), "dilated data gradient: per-tap tcgen05 kernel only"
+            call("wsl_conv_tc_dil", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks, self.dt, L.dil)
         elif self._tc2_ok([L.CoutP], H, W):
             call("wsl_conv_tc2", dy, L.CoutP, None, 0, pk["bd"][i], None, out, 0, N, H, W, sp, ci, L.ks, self.dt, None, None)
         elif self._tc_ok([L.CoutP], H, W):
@@ -410,28 +424,34 @@ class UNetExecutor:
             call("wsl_conv_direct", dy, L.CoutP, None, 0, self.dt, pk["wd"][i], None, out, {0: 0, 1: 2, 2: 3}[self.dt], N, H, W, L.CoutP, sp, ci, L.ks)
         self._untag()
 
-    def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False):
+    def conv_wgrad(self, L: ConvLayer, srcs, dy, N, H, W, src_f32=False, srcC_override=None):
         self.last_backward_param_ids.update((id(L.conv.weight), id(L.conv.bias)))
+        srcC = list(srcC_override) if srcC_override is not None else L.srcC
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
-        c0 = L.srcC[0]
-        c1 = L.srcC[1] if len(L.srcC) > 1 else 0
+        c0 = srcC[0]
+        c1 = srcC[1] if len(srcC) > 1 else 0
         self._tag("wgrad", L, N, H, W, L.Cin, L.Cout)
-        tc = (not src_f32 and self.use_tc_wgrad and self._tc_ok(L.srcC, H, W)
-              and (L.CoutP < 128 or L.CoutP % 128 == 0))
-        split = (not src_f32 and self.use_tc_wgrad and self._split_ok(L.srcC, H, W) and (L.CoutP < 128 or L.CoutP % 128 == 0))
+        tc = (not src_f32 and self.use_tc_wgrad and self._tc_ok(srcC, H, W)
+              and (L.CoutP < 128 or L.CoutP % 64 == 0))
+        split = (not src_f32 and self.use_tc_wgrad and self._split_ok(srcC, H, W) and (L.CoutP < 128 or L.CoutP % 64 == 0))
         if src_f32 and L.Cin == 1 and L.Cout == 16 and L.ks == 3 and L.bn is not None:
             call("wsl_wgrad_first", s0, dy, self.dt, self.gview(L.conv.weight), N, H, W, L.Cout)
         elif split:
-            sx, ix = self._staged("x", srcs, L.srcC, N * H * W)
+            sx, ix = self._staged("x", srcs, srcC, N * H * W)
             sg, ig = self._staged("dy", [dy], [L.CoutP], N * H * W)
-            call("wsl_wgrad_tc_split", sx, L.Cin, ix, sg, L.CoutP, ig, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks)
+            call("wsl_wgrad_tc_split", sx, L.Cin, ix, sg, L.CoutP, ig, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, L.dil)
             tc = True
-        elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W) and self.wgrad_version == 3 and (L.CoutP <= 64 or L.CoutP % 128 == 0):
+        elif L.dil != 1 and not src_f32:
+            assert tc, "dilated weight gradient: per-tap tcgen05 kernel only"
+            pw = self._wgrad_partials() if self.deterministic_wgrad else None
+            call("wsl_wgrad_tc_dil", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt, L.dil, pw,
+                 pw.numel() if pw is not None else 0)
+        elif tc and L.ks == 3 and self._tc2_ok(srcC, H, W) and self.wgrad_version == 3 and (L.CoutP <= 64 or L.CoutP % 128 == 0):
             pw = self._wgrad_partials() if self.deterministic_wgrad else None
             call("wsl_wgrad_tc3", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt, pw,
                  pw.numel() if pw is not None else 0)
-        elif tc and L.ks == 3 and self._tc2_ok(L.srcC, H, W):
+        elif tc and L.ks == 3 and self._tc2_ok(srcC, H, W):
             call("wsl_wgrad_tc2", s0, c0, s1, c1, dy, L.CoutP, self.gview(L.conv.weight), N, H, W, L.Cout, L.ks, self.dt)
         elif tc:
             pw = self._wgrad_partials() if self.deterministic_wgrad else None
