@@ -1,4 +1,4 @@
-"""Shared by the shim packages: make `import utils.metrics` / `networks.pnet` / ... keep resolving to the reference's own
+"""Shared by the shim packages: make `import utils.metrics` / `networks.efficientunet` / ... keep resolving to the reference's own
 files for everything this repo does not replace.
 
 Each shim directory (`utils/`, `networks/`, `dataloaders/`) is a REGULAR package (it has an `__init__.py`), so it wins over

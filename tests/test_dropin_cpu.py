@@ -49,9 +49,10 @@ def test_shim_wins_from_the_script_directory(tmp_path):
     r = subprocess.run([sys.executable, probe], cwd=code, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     where = json.loads(r.stdout.strip().splitlines()[-1])
-    for m in ("utils.losses", "utils.gate_crf_loss", "utils.ramps", "networks.net_factory", "networks.unet", "dataloaders.dataset", "val_2D"):
+    for m in ("utils.losses", "utils.gate_crf_loss", "utils.ramps", "networks.net_factory", "networks.unet", "networks.pnet",
+              "dataloaders.dataset", "val_2D"):
         assert where[m].startswith(os.path.join(ROOT, "dropin")), (m, where[m])
-    for m in ("utils.metrics", "networks.pnet"):          # not replaced: still the files next to the script
+    for m in ("utils.metrics",):                          # not replaced: still the file next to the script
         assert where[m].startswith(code), (m, where[m])
 
 
