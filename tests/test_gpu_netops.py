@@ -533,6 +533,24 @@ def test_chan_dropout():
     assert torch.equal(nchw(d.cpu()), a * cs.cpu().view(N, C, 1, 1))
 
 
+@pytest.mark.parametrize("dt", [0, 1, 2])
+@pytest.mark.parametrize("C,Creal", [(320, 320), (128, 128), (16, 4), (48, 40)])
+@pytest.mark.parametrize("det", [False, True])
+def test_channel_sum_any_width(dt, C, Creal, det):
+    """bias gradient of the 1x1 heads: channel counts that do not divide the 256-thread block (PNet2D's 320-channel concat head, 40
+    pixel groups) and more than 256 real channels in the deterministic last-block combine"""
+    P = 2 * 40 * 24
+    g = torch.Generator().manual_seed(C + dt)
+    x = torch.randn(P, C, generator=g)
+    xd = x.to({0: torch.bfloat16, 1: torch.float32, 2: torch.float16}[dt]).to(DEV)
+    out = torch.ones(Creal, device=DEV)
+    for _ in range(2):                    # accumulates, and the workspace ticket resets
+        call("wsl_channel_sum", xd, dt, P, C, Creal, out, workspace("csum") if det else None)
+    torch.cuda.synchronize()
+    want = 1 + 2 * xd.double().sum(0)[:Creal].cpu()
+    assert (out.cpu().double() - want).abs().max().item() < 1e-3, (out.cpu().double() - want).abs().max().item()
+
+
 @pytest.mark.parametrize("dil", [2, 4, 16])
 @pytest.mark.parametrize("dt", [0, 2])
 def test_dilated_convolution(dil, dt):

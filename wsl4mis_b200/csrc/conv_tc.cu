@@ -1391,28 +1391,33 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // all 256 threads: `parts` threads per channel walk interleaved block subsets (8 loads in flight), then a fixed-order combine
+  // all 256 threads: `parts` threads per channel walk interleaved block subsets (8 loads in flight), then a fixed-order combine;
+  // more than 256 channels (PNet2D's 320-channel concat head) go in slabs of 256
   __shared__ float s_fin[256];
-  const int parts = 256 / Creal > 0 ? 256 / Creal : 1;
-  const int c = threadIdx.x % Creal, part = threadIdx.x / Creal;
-  float a = 0.f;
-  if (part < parts) {
-    int b = part;
-    for (; b + 7 * parts < (int)gridDim.x; b += 8 * parts) {
-      float v[8];
+  for (int cb = 0; cb < Creal; cb += 256) {
+    const int cn = Creal - cb < 256 ? Creal - cb : 256;
+    const int parts = 256 / cn;
+    const int c = cb + threadIdx.x % cn, part = threadIdx.x / cn;
+    float a = 0.f;
+    if (part < parts) {
+      int b = part;
+      for (; b + 7 * parts < (int)gridDim.x; b += 8 * parts) {
+        float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcg(&ws[64 + (size_t)(b + u * parts) * Creal + c]);
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(&ws[64 + (size_t)(b + u * parts) * Creal + c]);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a += v[u];
+        for (int u = 0; u < 8; ++u) a += v[u];
+      }
+      for (; b < (int)gridDim.x; b += parts) a += __ldcg(&ws[64 + (size_t)b * Creal + c]);
     }
-    for (; b < (int)gridDim.x; b += parts) a += __ldcg(&ws[64 + (size_t)b * Creal + c]);
-  }
-  s_fin[threadIdx.x] = a;
-  __syncthreads();
-  if (threadIdx.x < Creal) {
-    float t = 0.f;
-    for (int q = 0; q < parts; ++q) t += s_fin[q * Creal + threadIdx.x];
-    out[threadIdx.x] += t;
+    s_fin[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < cn) {
+      float t = 0.f;
+      for (int q = 0; q < parts; ++q) t += s_fin[q * cn + threadIdx.x];
+      out[cb + threadIdx.x] += t;
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws) = 0u;
 }
