@@ -404,16 +404,22 @@ def main():
         ema = (UNet_CCT if args.model == "unet_cct" else UNet)(1, 4).to(dev).set_precision(args.precision)
         for q in ema.parameters():
             q.detach_()
-        ustep = UAMTStep(model, ema, base_lr=0.01, max_iterations=30000, world_size=world)
+        ustep = UAMTStep(model, ema, base_lr=0.01, max_iterations=30000, world_size=world, graph=not args.no_graph)
 
         class _U:                                    # the TrainStep surface bench.py drives
-            graph_enabled, launches_per_step, ex = False, 0, ustep.ex
+            # graph_enabled = False: no input_buffers() protocol (UAMTStep copies every batch into its own static buffers);
+            # `captured` is what the JSON line reports as cuda_graph
+            graph_enabled, captured, launches_per_step, ex = False, ustep.graph_enabled, 0, ustep.ex
 
             def __call__(self, img, lab):
                 h = img.shape[0] // 2
                 c0 = _lib.COUNTERS["launch_calls"]
                 out = ustep(img[:h], lab[:h], img[h:])
-                self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0
+                if ustep.graph_enabled:
+                    self.launches_per_step = ustep.launches_per_step      # counted during the eager warm-up steps
+                    self.comm_mode = getattr(ustep, "comm_mode", None)
+                else:
+                    self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0
                 return out
         step = _U()
     else:
@@ -576,7 +582,7 @@ def main():
                     "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peaks["src"],
                     "avg_launch_ms": round(v["ms"] / v["launches"], 4), "algorithmic_MB_per_launch": round(v["bytes"] / v["launches"] / 1e6, 1)}
 
-    lps, graph_on = step.launches_per_step, step.graph_enabled     # C-ABI launches per step, counted by TrainStep at capture time
+    lps, graph_on = step.launches_per_step, getattr(step, "captured", step.graph_enabled)   # launches per step counted at capture time
     parity = modes = gpu_base = None
     if rank == 0 and world == 1 and not args.skip_extras and not uamt:
         parity = parity_report(args, dev)

@@ -139,6 +139,36 @@ def test_uamt_step_matches_oracle(precision):
     print(f"[uamt {precision}] loss {loss.item():.6f} (oracle {ref_loss.item():.6f}), mask agreement {agree:.4f}, worst update cosine {worst:.5f}")
 
 
+def test_uamt_graph_replay_equals_eager():
+    """UAMTStep(graph=True): the captured body (7 network passes, losses, two backwards, SGD) with the ramps read from device
+    memory must take the same steps as the eager body -- across the iteration where the consistency weight changes (:183 uses
+    iter_num // 300)."""
+    from wsl4mis_b200.engine import UAMTStep
+    B, hw = 2, 64
+    g = torch.Generator().manual_seed(8)
+    img_l, img_u = torch.rand(B, 1, hw, hw, generator=g).to(DEV), torch.rand(B, 1, hw, hw, generator=g).to(DEV)
+    lab_l = torch.randint(0, 4, (B, hw, hw), generator=g, dtype=torch.uint8).to(DEV)
+    losses, finals, weights = {}, {}, {}
+    for graph in (False, True):
+        torch.manual_seed(33)
+        student, teacher = UNet_CCT(1, 4).to(DEV).set_precision("fp32"), UNet_CCT(1, 4).to(DEV).set_precision("fp32")
+        step = UAMTStep(student, teacher, base_lr=0.01, max_iterations=30000, graph=graph)
+        step.iter_num = 297
+        ls, ws = [], []
+        for _ in range(6):
+            ls.append(step(img_l, lab_l, img_u).item())
+            ws.append(step.parts["weight"])
+        losses[graph], weights[graph] = ls, ws
+        finals[graph] = step.flat.clone()
+        if graph:
+            assert step._graph is not None and step.launches_per_step > 500
+    assert weights[False] == weights[True] and weights[True][0] != weights[True][-1]
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) < 1e-4 * abs(a), (losses[False], losses[True])
+    rel = ((finals[True] - finals[False]).norm() / finals[False].norm()).item()
+    assert rel < 1e-5, rel
+
+
 def test_clamped_noise_kernel_statistics():
     from wsl4mis_b200._lib import call
     x = torch.zeros(1 << 20, device=DEV)

@@ -378,10 +378,16 @@ class UAMTStep:
     Two-head models (unet_cct) use main_seg on both sides."""
 
     def __init__(self, model, ema_model, base_lr=0.01, max_iterations=30000, consistency=0.1, consistency_rampup=200.0,
-                 momentum=0.9, weight_decay=1e-4, T=8, process_group=None, world_size=1):
+                 momentum=0.9, weight_decay=1e-4, T=8, process_group=None, world_size=1, graph=False):
         """world_size > 1: batch-sharded data parallel -- every rank runs the step on its shard, the flat gradient bucket is
         all-reduced (sum) over NCCL and the fused SGD applies the 1/world mean, as `TrainStep` does.  The student replicas are
-        broadcast from rank 0 at construction; the teacher is never updated by the reference and is broadcast once."""
+        broadcast from rank 0 at construction; the teacher is never updated by the reference and is broadcast once.
+
+        graph=True: after two eager warm-up steps the whole body (two student forwards, 1 + T/2 teacher forwards, losses, two
+        backwards, SGD) is captured in ONE CUDA graph (world_size > 1: forward+backward | host-issued all-reduce | SGD, as
+        `TrainStep`) -- the eager step issues ~900 launches from Python and is host-bound.  The ramps of the script (consistency
+        weight :183, uncertainty threshold :186, poly LR :194) stay host arithmetic: they are written to a 2-float device buffer
+        before every replay and read by the kernels through their *_ptr arguments.  Needs a fixed batch shape and noises=None."""
         from .utils import ramps
         self.world_size, self.pg = int(world_size), process_group
         self.ramps = ramps
@@ -411,6 +417,10 @@ class UAMTStep:
         self.lr_dev = torch.full((1,), self.base_lr, dtype=torch.float32, device=dev)
         from .networks._engine import initial_rng_counter
         self.seed_dev = torch.full((1,), initial_rng_counter() ^ 0x5A5A5A5A, dtype=torch.int64, device=dev)
+        self.ramp_dev = torch.zeros(2, dtype=torch.float32, device=dev)            # {uncertainty threshold, consistency weight}
+        self.graph_enabled = bool(graph)
+        self._warm, self._graph, self._static = 0, None, None
+        self.launches_per_step = 0
 
     def _noisy(self, x, reps, salt, given):
         if given is not None:
@@ -419,12 +429,75 @@ class UAMTStep:
         call("wsl_add_clamped_noise", x, x.numel(), reps, 0.1, 0.2, 0xA5A5 + salt, self.seed_dev, out)
         return out
 
+    def _ramps(self):
+        """host arithmetic of :183 and :186 for the current iteration -> (threshold, weight), also written to ramp_dev"""
+        import math
+        cw = self.consistency * self.ramps.sigmoid_rampup(self.iter_num // 300, self.consistency_rampup)
+        thr = (0.75 + 0.25 * self.ramps.sigmoid_rampup(self.iter_num, self.max_iterations)) * math.log(2)
+        self.ramp_dev.copy_(torch.tensor([thr, cw], dtype=torch.float32))
+        return thr, cw
+
+    def _opt(self, g):
+        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay,
+             1.0 / self.world_size)
+
     def __call__(self, image_l, label_l, image_u, noises=None):
         """image_l/image_u: fp32 [B,1,H,W]; label_l: uint8 [B,H,W] dense.  noises (tests): list of 1 + T/2 tensors holding
         the already-clamped noise of :147-149 and :167-169.  Returns the loss (0-dim device tensor)."""
-        ex, ex_t, dev = self.ex, self.ex_t, self.dev
         self.model.train()
         self.ema_model.train()
+        thr, cw = self._ramps()
+        if not self.graph_enabled:
+            loss, g = self._body(image_l, label_l, image_u, noises)
+            if self.world_size > 1:
+                ddp.allreduce_flat(g[: self.n_trained], self.pg)
+            self._opt(g)
+        else:
+            assert noises is None, "graph mode draws the teacher noise on the device"
+            if self._static is None:
+                self._static = (torch.empty_like(image_l), torch.empty_like(label_l), torch.empty_like(image_u))
+            sl, sb, su = self._static
+            assert sl.shape == image_l.shape and su.shape == image_u.shape, "graph mode needs a fixed batch shape"
+            sl.copy_(image_l, non_blocking=True)
+            sb.copy_(label_l, non_blocking=True)
+            su.copy_(image_u, non_blocking=True)
+            if self._warm < 2:                      # eager warm-up allocates every buffer / tensor map / workspace
+                c0 = _lib.COUNTERS["launch_calls"]
+                loss, g = self._body(sl, sb, su, None)
+                if self.world_size > 1:
+                    ddp.allreduce_flat(g[: self.n_trained], self.pg)
+                self._opt(g)
+                self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0
+                self._warm += 1
+            else:
+                if self._graph is None:
+                    torch.cuda.synchronize()
+                    g1, g2 = torch.cuda.CUDAGraph(), None
+                    with torch.cuda.graph(g1):
+                        gloss, gg = self._body(sl, sb, su, None)
+                        if self.world_size == 1:
+                            self._opt(gg)
+                    if self.world_size > 1:
+                        g2 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g2):
+                            self._opt(gg)
+                    self._graph = (g1, g2, gloss, gg, dict(self.parts))
+                    self.comm_mode = "two graphs, host-issued all-reduce"
+                g1, g2, gloss, gg, self.parts = self._graph
+                g1.replay()
+                if g2 is not None:
+                    ddp.allreduce_flat(gg[: self.n_trained], self.pg)
+                    g2.replay()
+                loss = gloss.clone()                # the captured loss lives in graph-pool memory
+        self.parts = dict(self.parts, weight=cw, threshold=thr)
+        lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
+        self.lr_dev.fill_(lr_)
+        self.iter_num += 1
+        return loss
+
+    def _body(self, image_l, label_l, image_u, noises):
+        """forward passes, losses and both backward passes; returns (loss, flat gradient bucket)"""
+        ex, ex_t, dev = self.ex, self.ex_t, self.dev
         B, _, H, W = image_u.shape
         C, T = 4, self.T
         self.seed_dev.add_(1)
@@ -451,27 +524,18 @@ class UAMTStep:
         dl_l = Bf("dl_l", (B, C, H, W))
         call("wsl_head_bwd", probs, label_l, st, None, 0.5, gp, 1.0, B, C, H, W, 255, dl_l, None, self.ex.dt)
         # ---- consistency half (:181-189) ----
-        cw = self.consistency * self.ramps.sigmoid_rampup(self.iter_num // 300, self.consistency_rampup)
-        import math
-        thr = (0.75 + 0.25 * self.ramps.sigmoid_rampup(self.iter_num, self.max_iterations)) * math.log(2)
+        # threshold (:186) and weight (:183) come from ramp_dev (written by _ramps() before the body / the graph replay)
         mask, cst = Bf("mask", (B, H, W), torch.uint8), Bf("cons", (3,))
-        call("wsl_uamt_consistency_fwd", out_u, ema_out, mc, T, B, C, H, W, None, float(thr), mask, cst, workspace("uamt", dev))
+        call("wsl_uamt_consistency_fwd", out_u, ema_out, mc, T, B, C, H, W, self.ramp_dev[0:1], 0.0, mask, cst, workspace("uamt", dev))
         dl_u = Bf("dl_u", (B, C, H, W))
-        call("wsl_uamt_consistency_bwd", out_u, ema_out, mask, cst, None, float(cw), B, C, H, W, dl_u)
-        loss = 0.5 * (sums[0] + st[0]) + cw * cst[2]
-        self.parts = {"supervised": 0.5 * (sums[0] + st[0]), "consistency": cst[2], "weight": cw, "threshold": thr, "mask": mask}
+        call("wsl_uamt_consistency_bwd", out_u, ema_out, mask, cst, self.ramp_dev[1:2], 0.0, B, C, H, W, dl_u)
+        loss = 0.5 * (sums[0] + st[0]) + self.ramp_dev[1] * cst[2]
+        self.parts = {"supervised": 0.5 * (sums[0] + st[0]), "consistency": cst[2], "mask": mask}
         # ---- two backward passes through the shared student weights, gradients accumulated in the flat bucket ----
         nd = len(ex.dec)
         ex.backward(slot_u, [dl_u] + [None] * (nd - 1), zero_grads=True)
         g = ex.backward(slot_l, [dl_l] + [None] * (nd - 1), zero_grads=False)
-        if self.world_size > 1:
-            ddp.allreduce_flat(g[: self.n_trained], self.pg)
-        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay,
-             1.0 / self.world_size)
-        lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
-        self.lr_dev.fill_(lr_)
-        self.iter_num += 1
-        return loss
+        return loss, g
 
 
 class USTMStep(UAMTStep):
@@ -479,6 +543,7 @@ class USTMStep(UAMTStep):
     random rot90 transform (Python host RNG, :123) and the EMA teacher update the script really performs (:163)."""
 
     def __init__(self, model, ema_model, base_lr=0.01, max_iterations=60000, ema_decay=0.99, **kw):
+        kw.pop("graph", None)              # the random rot90 count (:123) is a host draw baked into kernel arguments: eager only
         super().__init__(model, ema_model, base_lr=base_lr, max_iterations=max_iterations, **kw)
         self.ema_decay = float(ema_decay)
         tparams = self.ex_t.params
