@@ -249,7 +249,7 @@ def gpu_reference_baseline(args, dev, img_d, lab_d):
                         ms = e0.elapsed_time(e1) / n
                         res = {"mode": name, "step": "pCE only (U-Net fwd+bwd+SGD)" if unet_only else f"{args.variant} full step", "batch": bs,
                                "ms_per_step": round(ms, 3), "images_per_sec": round(bs / ms * 1e3, 1),
-                               "peak_mem_GiB": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2), "loss": float(loss)}
+                               "peak_mem_GiB": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2), "loss": float(loss.detach())}
                         del step
                         break
                     except torch.cuda.OutOfMemoryError:
@@ -593,7 +593,7 @@ def main():
         gpu_base = gpu_reference_baseline(args, dev, img_d, lab_d)
 
     if rank == 0:
-        cb = None if (args.skip_cpu or uamt) else cpu_reference_time(args, args.cpu_sample, 3, 1)[0]
+        cb = None if (args.skip_cpu or uamt or world > 1) else cpu_reference_time(args, args.cpu_sample, 3, 1)[0]   # rank 0 at N = 1 only
         imgs = N * world * K
         line = {
             "metric": metric_name(args), "value": imgs / (ms_dev * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
