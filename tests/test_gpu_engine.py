@@ -169,6 +169,41 @@ def test_uamt_graph_replay_equals_eager():
     assert rel < 1e-5, rel
 
 
+def test_ustm_graph_replay_equals_eager():
+    """USTMStep(graph=True): one captured graph per rot90 count (a kernel argument drawn by Python's `random`, :123); threshold,
+    weight and the EMA factor (which changes every step below iteration 99) come from device memory.  The fp32 cross-check mode
+    accumulates its weight gradients with atomics, so two EAGER runs already differ; the captured run has to stay within a small
+    multiple of that run-to-run floor (a wrong EMA factor or a stale ramp shows up as >= 1e-3)."""
+    import random
+    from wsl4mis_b200.engine import USTMStep
+    B, hw = 2, 64
+    img, lab = O.synth_batch(B, hw, hw, seed=12, frac=0.1)
+    img, lab = img.to(DEV), lab.to(DEV)
+    res = {}
+    for tag, graph in (("eager", False), ("eager2", False), ("graph", True)):
+        torch.manual_seed(35)
+        random.seed(4)
+        student, teacher = UNet(1, 4).to(DEV).set_precision("fp32"), UNet(1, 4).to(DEV).set_precision("fp32")
+        step = USTMStep(student, teacher, base_lr=0.01, max_iterations=60000, graph=graph)
+        ls, ks = [], []
+        for _ in range(8):
+            ls.append(step(img, lab).item())
+            ks.append(step.rot_times)
+        res[tag] = (ls, ks, step.flat.clone(), step.tflat.clone())
+        if graph:
+            assert 1 <= len(step._graphs) <= 4 and set(step._graphs) <= set(ks[2:])
+    assert res["eager"][1] == res["graph"][1] and len(set(res["graph"][1])) > 1
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    floor = [rel(res["eager2"][i], res["eager"][i]) for i in (2, 3)]
+    got = [rel(res["graph"][i], res["eager"][i]) for i in (2, 3)]
+    print(f"[ustm graph] student/teacher weights: graph vs eager {got[0]:.2e} / {got[1]:.2e}, eager vs eager {floor[0]:.2e} / {floor[1]:.2e}; "
+          f"losses eager {res['eager'][0]} graph {res['graph'][0]}")
+    for a, b in zip(res["eager"][0], res["graph"][0]):
+        assert abs(a - b) < 1e-3 * abs(a), (res["eager"][0], res["graph"][0])
+    for gv, fl in zip(got, floor):
+        assert gv < max(2e-5, 10 * fl), (got, floor)
+
+
 def test_clamped_noise_kernel_statistics():
     from wsl4mis_b200._lib import call
     x = torch.zeros(1 << 20, device=DEV)

@@ -540,10 +540,13 @@ class UAMTStep:
 
 class USTMStep(UAMTStep):
     """Per-step body of train_weakly_supervised_ustm_2D.py:113-170: pCE on scribbles + uncertainty-aware self-ensembling with a
-    random rot90 transform (Python host RNG, :123) and the EMA teacher update the script really performs (:163)."""
+    random rot90 transform (Python host RNG, :123) and the EMA teacher update the script really performs (:163).
+
+    graph=True: the rot90 count is a kernel ARGUMENT, so one CUDA graph is captured per count (at most four, each on the first
+    step that draws it after two eager warm-up steps); threshold, consistency weight and the EMA factor reach the captured
+    kernels through `ramp_dev`."""
 
     def __init__(self, model, ema_model, base_lr=0.01, max_iterations=60000, ema_decay=0.99, **kw):
-        kw.pop("graph", None)              # the random rot90 count (:123) is a host draw baked into kernel arguments: eager only
         super().__init__(model, ema_model, base_lr=base_lr, max_iterations=max_iterations, **kw)
         self.ema_decay = float(ema_decay)
         tparams = self.ex_t.params
@@ -554,18 +557,85 @@ class USTMStep(UAMTStep):
             self.tflat[off:off + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.tflat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        self.ramp_dev = torch.zeros(3, dtype=torch.float32, device=self.dev)     # {threshold, weight, 1 - EMA alpha}
+        self._graphs = {}
+
+    def _ramps(self):
+        import math
+        cw = 1.0 * self.ramps.sigmoid_rampup(self.iter_num // 1000, 60)                                      # :145
+        thr = (0.75 + 0.25 * self.ramps.sigmoid_rampup(self.iter_num, self.max_iterations)) * math.log(2)     # :148
+        alpha = min(1 - 1 / (self.iter_num + 1), self.ema_decay)         # :63, global_step = iter_num before the increment
+        self.ramp_dev.copy_(torch.tensor([thr, cw, 1.0 - alpha], dtype=torch.float32))
+        return thr, cw, alpha
+
+    def _finish(self, g, alpha):
+        """SGD on the student, then the EMA teacher update (:163).  alpha=None (captured): the factor is read from ramp_dev"""
+        self._opt(g)
+        n = min(self.tflat.numel(), self.flat.numel())
+        if alpha is None:
+            self.tflat[:n].lerp_(self.flat[:n], self.ramp_dev[2])        # t + (1 - alpha) * (s - t)
+        else:
+            call("wsl_ema_update", self.tflat, self.flat, n, float(alpha))
 
     def __call__(self, image, label, noises=None, rot_times=None):
-        import math
-        ex, ex_t, dev = self.ex, self.ex_t, self.dev
         self.model.train()
         self.ema_model.train()
-        B, _, H, W = image.shape
-        assert H == W, "rot90 consistency needs square inputs"
-        C, T = 4, self.T
-        self.seed_dev.add_(1)
+        assert image.shape[2] == image.shape[3], "rot90 consistency needs square inputs"
         k = random.randrange(0, 4) if rot_times is None else int(rot_times)
         self.rot_times = k
+        thr, cw, alpha = self._ramps()
+        if not self.graph_enabled:
+            loss, g = self._body(image, label, noises, k)
+            if self.world_size > 1:
+                ddp.allreduce_flat(g[: self.n_trained], self.pg)
+            self._finish(g, alpha)
+        else:
+            assert noises is None, "graph mode draws the teacher noise on the device"
+            if self._static is None:
+                self._static = (torch.empty_like(image), torch.empty_like(label))
+            si, sl = self._static
+            assert si.shape == image.shape, "graph mode needs a fixed batch shape"
+            si.copy_(image, non_blocking=True)
+            sl.copy_(label, non_blocking=True)
+            if self._warm < 2:
+                c0 = _lib.COUNTERS["launch_calls"]
+                loss, g = self._body(si, sl, None, k)
+                if self.world_size > 1:
+                    ddp.allreduce_flat(g[: self.n_trained], self.pg)
+                self._finish(g, alpha)
+                self.launches_per_step = _lib.COUNTERS["launch_calls"] - c0
+                self._warm += 1
+            else:
+                if k not in self._graphs:
+                    torch.cuda.synchronize()
+                    g1, g2 = torch.cuda.CUDAGraph(), None
+                    with torch.cuda.graph(g1):
+                        gloss, gg = self._body(si, sl, None, k)
+                        if self.world_size == 1:
+                            self._finish(gg, None)
+                    if self.world_size > 1:
+                        g2 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g2):
+                            self._finish(gg, None)
+                    self._graphs[k] = (g1, g2, gloss, gg, dict(self.parts))
+                    self.comm_mode = "two graphs per rot90 count, host-issued all-reduce"
+                g1, g2, gloss, gg, self.parts = self._graphs[k]
+                g1.replay()
+                if g2 is not None:
+                    ddp.allreduce_flat(gg[: self.n_trained], self.pg)
+                    g2.replay()
+                loss = gloss.clone()
+        self.parts = dict(self.parts, weight=cw, threshold=thr)
+        lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
+        self.lr_dev.fill_(lr_)
+        self.iter_num += 1
+        return loss
+
+    def _body(self, image, label, noises, k):
+        ex, ex_t, dev = self.ex, self.ex_t, self.dev
+        B, _, H, W = image.shape
+        C, T = 4, self.T
+        self.seed_dev.add_(1)
         masks, ck = getattr(self.model, "dropout_masks", None), getattr(self.model, "channel_keep", None)
         tmasks, tck = getattr(self.ema_model, "dropout_masks", None), getattr(self.ema_model, "channel_keep", None)
         outs, slot = ex.forward(image.contiguous(), True, True, masks, ck)
@@ -585,26 +655,15 @@ class USTMStep(UAMTStep):
         call("wsl_softmax_pce_fwd", out, label, probs, B, C, H, W, 4, st, workspace("pce", dev))
         d = Bf("dl", (B, C, H, W))
         call("wsl_head_bwd", probs, label, st, None, 1.0, None, 0.0, B, C, H, W, 4, d, None, self.ex.dt)
-        # consistency on the rotated student logits
+        # consistency on the rotated student logits; threshold (:148) / weight (:145) from ramp_dev
         rout = Bf("rout", (B, C, H, W))
         call("wsl_rot90", out, B * C, H, k, 0, rout)
-        cw = 1.0 * self.ramps.sigmoid_rampup(self.iter_num // 1000, 60)
-        thr = (0.75 + 0.25 * self.ramps.sigmoid_rampup(self.iter_num, self.max_iterations)) * math.log(2)
         mask, cst = Bf("mask", (B, H, W), torch.uint8), Bf("cons", (3,))
-        call("wsl_uamt_consistency_fwd", rout, ema_out, mc, T, B, C, H, W, None, float(thr), mask, cst, workspace("uamt", dev))
+        call("wsl_uamt_consistency_fwd", rout, ema_out, mc, T, B, C, H, W, self.ramp_dev[0:1], 0.0, mask, cst, workspace("uamt", dev))
         dr = Bf("dr", (B, C, H, W))
-        call("wsl_uamt_consistency_bwd", rout, ema_out, mask, cst, None, float(cw), B, C, H, W, dr)
+        call("wsl_uamt_consistency_bwd", rout, ema_out, mask, cst, self.ramp_dev[1:2], 0.0, B, C, H, W, dr)
         call("wsl_rot90", dr, B * C, H, (4 - k) % 4, 1, d)              # rotate the gradient back and add it to the pCE part
-        loss = st[0] + cw * cst[2]
-        self.parts = {"ce": st[0], "consistency": cst[2], "weight": cw, "threshold": thr, "mask": mask}
+        loss = st[0] + self.ramp_dev[1] * cst[2]
+        self.parts = {"ce": st[0], "consistency": cst[2], "mask": mask}
         g = ex.backward(slot, [d] + [None] * (len(ex.dec) - 1))
-        if self.world_size > 1:
-            ddp.allreduce_flat(g[: self.n_trained], self.pg)
-        call("wsl_sgd_step", self.flat, g, self.mom, self.n_trained, self.lr_dev, self.base_lr, self.momentum, self.weight_decay,
-             1.0 / self.world_size)
-        alpha = min(1 - 1 / (self.iter_num + 1), self.ema_decay)         # :63, global_step = iter_num before the increment
-        call("wsl_ema_update", self.tflat, self.flat, min(self.tflat.numel(), self.flat.numel()), float(alpha))
-        lr_ = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
-        self.lr_dev.fill_(lr_)
-        self.iter_num += 1
-        return loss
+        return loss, g
